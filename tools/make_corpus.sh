@@ -1,0 +1,61 @@
+#!/bin/bash
+# Generates the bitstream corpus with the UNMODIFIED reference encoder (oracle/_ref/TAppEncoderStatic)
+# from seeded synthetic YUV (tools/gen_yuv.py) using the cfg files shipped in /root/reference/cfg.
+# Usage: tools/make_corpus.sh <name>        (one job; see table below)
+#        tools/make_corpus.sh --list
+# Outputs corpus/<name>.bin, corpus/<name>.md5 (per-frame MD5 lines printed by TAppDecoderStatic),
+# corpus/<name>.yuvmd5 (md5 of the whole decoded YUV).  Raw YUVs live in $TMP_YUV (not in the repo).
+set -e
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+REF=${REF:-/root/reference}
+ENC=$ROOT/oracle/_ref/TAppEncoderStatic
+DEC=$ROOT/oracle/_ref/TAppDecoderStatic
+TMP_YUV=${TMP_YUV:-/tmp/corpus}
+mkdir -p "$TMP_YUV" "$ROOT/corpus"
+#        name        cfg                                   W    H    frames bd chroma seed extra
+JOBS=(
+ "c1_intra8_240p     encoder_intra_main.cfg                416  240  16 8  420 1234"
+ "s_ra8_240p         encoder_randomaccess_main.cfg         416  240  17 8  420 11"
+ "s_ra8_240p_q22     encoder_randomaccess_main.cfg         416  240  17 8  420 12 -q 22"
+ "s_ra10_240p        encoder_randomaccess_main10.cfg       416  240  17 10 420 13"
+ "s_ld10_240p        encoder_lowdelay_main10.cfg           416  240  9  10 420 14"
+ "s_ldp8_240p        encoder_lowdelay_P_main.cfg           416  240  9  8  420 15"
+ "s_intra10_240p_q22 encoder_intra_main10.cfg              416  240  4  10 420 16 -q 22"
+ "s_rext444_240p     encoder_intra_high_throughput_rext.cfg 416 240  3  12 444 17 --InternalBitDepth=12"
+ "s_ra8_odd          encoder_randomaccess_main.cfg         200  136  9  8  420 18 -q 27"
+ "c2_ra8_1080p       encoder_randomaccess_main.cfg         1920 1080 64 8  420 2"
+ "c3_ra10_2160p      encoder_randomaccess_main10.cfg       3840 2160 33 10 420 3"
+ "c4_rext444_1080p   encoder_intra_high_throughput_rext.cfg 1920 1080 8 12 444 4 --InternalBitDepth=12"
+ "c5_ld10_2160p_s50  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 50"
+ "c5_ld10_2160p_s51  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 51"
+ "c5_ld10_2160p_s52  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 52"
+ "c5_ld10_2160p_s53  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 53"
+ "c5_ld10_2160p_s54  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 54"
+ "c5_ld10_2160p_s55  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 55"
+ "c5_ld10_2160p_s56  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 56"
+ "c5_ld10_2160p_s57  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 57"
+ "m_ra10_1080p       encoder_randomaccess_main10.cfg       1920 1080 17 10 420 5"
+)
+WANT=$1
+if [ "$1" == "--list" ]; then for j in "${JOBS[@]}"; do echo "$j" | awk '{print $1}'; done; exit 0; fi
+for j in "${JOBS[@]}"; do
+  set -- $j
+  name=$1; cfg=$2; W=$3; H=$4; F=$5; BD=$6; CH=$7; SEED=$8; shift 8; EXTRA="$*"
+  [ "$name" == "$WANT" ] || continue
+  out=$ROOT/corpus/$name
+  [ -s "$out.bin" ] && [ -s "$out.yuvmd5" ] && { echo "$name: exists"; exit 0; }
+  yuv=$TMP_YUV/$name.yuv
+  python "$ROOT/tools/gen_yuv.py" "$yuv" --width $W --height $H --frames $F --bitdepth $BD --seed $SEED --chroma $CH
+  CF=""; [ "$CH" != "420" ] && CF="--InputChromaFormat=$CH"
+  "$ENC" -c "$REF/cfg/$cfg" -i "$yuv" -wdt $W -hgt $H -f $F -fr 30 --InputBitDepth=$BD $CF \
+      --SEIDecodedPictureHash=1 $EXTRA -b "$out.bin.tmp" -o "$TMP_YUV/$name.rec.yuv" > "$out.enc.log" 2>&1
+  mv "$out.bin.tmp" "$out.bin"
+  "$DEC" -b "$out.bin" -d 0 -o "$TMP_YUV/$name.dec.yuv" > "$out.dec.log" 2>&1
+  cmp "$TMP_YUV/$name.rec.yuv" "$TMP_YUV/$name.dec.yuv"
+  grep -o 'POC.*' "$out.dec.log" | sed -E 's/\[DT +[0-9.]+\] //' > "$out.md5"
+  md5sum < "$TMP_YUV/$name.dec.yuv" | awk '{print $1}' > "$out.yuvmd5"
+  rm -f "$yuv" "$TMP_YUV/$name.rec.yuv"
+  echo "$name: done ($(stat -c %s "$out.bin") bytes)"
+  exit 0
+done
+echo "unknown job $WANT"; exit 1
