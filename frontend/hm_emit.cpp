@@ -1,0 +1,648 @@
+// hm_emit.cpp — frame-record emitter (host side of the drop-in boundary).
+//
+// Walks HM's per-CTU data exactly the way HM's own reconstruction walks it, but instead of
+// computing samples it appends plain records (include/hmr_records.h).  Each function names the HM
+// routine whose traversal it mirrors.  Compiled against the HM headers in /root/reference.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cassert>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <list>
+#include <map>
+#include <iostream>
+#include <sstream>
+#include <fstream>
+#include <algorithm>
+#include <limits>
+#include <iomanip>
+
+// The boundary-strength derivation is reused from HM (TComLoopFilter::xGetBoundaryStrengthSingle and
+// friends are protected, their result arrays private).  We only *read* them.
+#define private public
+#define protected public
+#include "TLibCommon/TComLoopFilter.h"
+#undef private
+#undef protected
+#include "TLibCommon/TComSampleAdaptiveOffset.h"
+#include "TLibCommon/TComPrediction.h"
+#include "TLibCommon/TComTrQuant.h"
+#include "TLibCommon/TComPic.h"
+#include "TLibCommon/TComTU.h"
+#include "TLibCommon/TComRom.h"
+
+#include "hm_emit.h"
+
+// free functions of TComPattern.cpp:558-735 (defined there, not declared in any header)
+Bool isAboveLeftAvailable ( TComDataCU* pcCU, UInt uiPartIdxLT );
+Int  isAboveAvailable     ( TComDataCU* pcCU, UInt uiPartIdxLT, UInt uiPartIdxRT, Bool* bValidFlags );
+Int  isLeftAvailable      ( TComDataCU* pcCU, UInt uiPartIdxLT, UInt uiPartIdxLB, Bool* bValidFlags );
+Int  isAboveRightAvailable( TComDataCU* pcCU, UInt uiPartIdxLT, UInt uiPartIdxRT, Bool* bValidFlags );
+Int  isBelowLeftAvailable ( TComDataCU* pcCU, UInt uiPartIdxLT, UInt uiPartIdxLB, Bool* bValidFlags );
+
+static thread_local HmEmitter* t_current = NULL;
+void       hm_emit_set_current(HmEmitter* e) { t_current = e; }
+HmEmitter* hm_emit_current()                 { return t_current; }
+
+struct HmEmitter::CuCtx
+{
+  TComDataCU* ctu;
+  unsigned    absPartIdx;   // z-order index of the CU inside the CTU
+  unsigned    depth;
+  int         cuX, cuY;     // luma position of the CU
+  uint32_t    lumaOff[256]; // coef/resid offset of the luma TU starting at partition i (CCP), HMR_NO_OFFSET if none
+};
+
+HmEmitter::HmEmitter(HmFrameSink* sink)
+  : m_sink(sink), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0)
+{
+  memset(&m_hdr, 0, sizeof(m_hdr));
+}
+
+HmEmitter::~HmEmitter() {}
+
+void HmEmitter::fail(const char* what)
+{
+  if (!m_unsupported)
+  {
+    m_unsupported = what;
+    fprintf(stderr, "hm_emit: UNSUPPORTED bitstream feature on the GPU reconstruction path: %s\n", what);
+  }
+}
+
+int HmEmitter::slotOf(TComPic* pic)
+{
+  std::map<TComPic*, int>::iterator it = m_slots.find(pic);
+  if (it != m_slots.end()) return it->second;
+  int s = (int)m_slots.size();
+  if (s >= HMR_MAX_SLOTS) { fail("more than HMR_MAX_SLOTS DPB entries"); s = HMR_MAX_SLOTS - 1; }
+  m_slots[pic] = s;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// picture start: frame header from SPS/PPS/slice (TDecTop::xActivateParameterSets, TDecTop.cpp:283-349)
+void HmEmitter::beginFrame(TComPic* pic, TComDataCU* ctu)
+{
+  TComSlice* slice = ctu->getSlice();
+  TComSPS*   sps   = slice->getSPS();
+  TComPPS*   pps   = slice->getPPS();
+  memset(&m_hdr, 0, sizeof(m_hdr));
+  m_hdr.magic   = HMR_MAGIC;
+  m_hdr.version = HMR_VERSION;
+  m_hdr.width   = sps->getPicWidthInLumaSamples();
+  m_hdr.height  = sps->getPicHeightInLumaSamples();
+  m_hdr.poc     = slice->getPOC();
+  m_hdr.chroma_format    = (uint8_t)pic->getChromaFormat();
+  m_hdr.bit_depth_luma   = (uint8_t)g_bitDepth[CHANNEL_TYPE_LUMA];
+  m_hdr.bit_depth_chroma = (uint8_t)g_bitDepth[CHANNEL_TYPE_CHROMA];
+  m_hdr.log2_ctu = (uint8_t)(g_aucConvertToBit[g_uiMaxCUWidth] + 2);
+  m_hdr.out_slot = (uint8_t)slotOf(pic);
+  m_hdr.slice_type = (uint8_t)slice->getSliceType();
+  m_hdr.pps_cb_qp_offset = (int8_t)pps->getQpOffset(COMPONENT_Cb);
+  m_hdr.pps_cr_qp_offset = (int8_t)pps->getQpOffset(COMPONENT_Cr);
+  m_hdr.n_ctu = pic->getNumCUsInFrame();
+  if (sps->getUseStrongIntraSmoothing())     m_hdr.flags |= HMR_FRM_STRONG_INTRA_SMOOTHING;
+  if (pps->getUseCrossComponentPrediction()) m_hdr.flags |= HMR_FRM_HAS_CCP;
+  if (sps->getUseExtendedPrecision())        fail("extended_precision_processing");
+  if (sps->getScalingListFlag())             fail("scaling lists");
+  if (g_uiMaxCUWidth != g_uiMaxCUHeight)     fail("non-square CTU");
+  if ((g_uiMaxCUWidth >> g_uiMaxCUDepth) != 4) fail("minimum partition size != 4");
+  if (pic->getChromaFormat() == CHROMA_400)  fail("4:0:0");
+
+  m_tu.clear(); m_coef.clear(); m_intra.clear(); m_pu.clear(); m_puPrefix.clear();
+  m_puPrefix.push_back(0);
+  m_range.assign(m_hdr.n_ctu, hmr_ctu_intra_range());
+  memset(m_range.data(), 0, m_range.size() * sizeof(hmr_ctu_intra_range));
+  m_ctu.assign(m_hdr.n_ctu, hmr_ctu());
+  memset(m_ctu.data(), 0, m_ctu.size() * sizeof(hmr_ctu));
+  m_bsStride = (m_hdr.width + 3) >> 2;
+  m_qpStride = (m_hdr.width + 7) >> 3;
+  m_bs.assign((size_t)m_bsStride * ((m_hdr.height + 3) >> 2), 0);
+  m_qp.assign((size_t)m_qpStride * ((m_hdr.height + 7) >> 3), 0);
+  m_cuFlags.assign(m_qp.size(), 0);
+  m_curPic = pic;
+  m_open = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one CTU: mirrors TDecCu::decompressCU -> xDecompressCU (TDecCu.cpp:142-145, 373-447)
+void HmEmitter::onCtuParsed(TComDataCU* ctu)
+{
+  TComPic* pic = ctu->getPic();
+  if (!m_open || pic != m_curPic) beginFrame(pic, ctu);
+  for (int c = 0; c < 3; c++) m_intraTmp[c].clear();
+  walkCU(ctu, 0, 0);
+  hmr_ctu_intra_range& r = m_range[ctu->getAddr()];
+  for (int c = 0; c < 3; c++)
+  {
+    r.first[c] = (uint32_t)m_intra.size();
+    r.count[c] = (uint32_t)m_intraTmp[c].size();
+    m_intra.insert(m_intra.end(), m_intraTmp[c].begin(), m_intraTmp[c].end());
+  }
+}
+
+void HmEmitter::walkCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth)
+{
+  TComPic*   pic   = ctu->getPic();
+  TComSlice* slice = pic->getSlice(pic->getCurrSliceIdx());
+  const unsigned picW = slice->getSPS()->getPicWidthInLumaSamples();
+  const unsigned picH = slice->getSPS()->getPicHeightInLumaSamples();
+  unsigned lx = ctu->getCUPelX() + g_auiRasterToPelX[g_auiZscanToRaster[absPartIdx]];
+  unsigned ty = ctu->getCUPelY() + g_auiRasterToPelY[g_auiZscanToRaster[absPartIdx]];
+  unsigned rx = lx + (g_uiMaxCUWidth >> depth) - 1;
+  unsigned by = ty + (g_uiMaxCUHeight >> depth) - 1;
+  unsigned curNumParts = pic->getNumPartInCU() >> (depth << 1);
+  const unsigned scu = ctu->getSCUAddr();
+  bool startInCU = scu + absPartIdx + curNumParts > slice->getSliceSegmentCurStartCUAddr() && scu + absPartIdx < slice->getSliceSegmentCurStartCUAddr();
+  bool boundary = startInCU || rx >= picW || by >= picH;
+
+  if ((depth < ctu->getDepth(absPartIdx) && depth < g_uiMaxCUDepth - g_uiAddCUDepth) || boundary)
+  {
+    unsigned qNumParts = ctu->getTotalNumPart() >> ((depth + 1) << 1);
+    unsigned idx = absPartIdx;
+    for (unsigned q = 0; q < 4; q++, idx += qNumParts)
+    {
+      unsigned qx = ctu->getCUPelX() + g_auiRasterToPelX[g_auiZscanToRaster[idx]];
+      unsigned qy = ctu->getCUPelY() + g_auiRasterToPelY[g_auiZscanToRaster[idx]];
+      bool inSlice = (scu + idx + qNumParts > slice->getSliceSegmentCurStartCUAddr()) && (scu + idx < slice->getSliceSegmentCurEndCUAddr());
+      if (inSlice && qx < picW && qy < picH) walkCU(ctu, idx, depth + 1);
+    }
+    return;
+  }
+
+  const int cuSize = g_uiMaxCUWidth >> depth;
+  switch (ctu->getPredictionMode(absPartIdx))
+  {
+    case MODE_INTER: emitInterCU(ctu, absPartIdx, depth, lx, ty, cuSize); break;
+    case MODE_INTRA: emitIntraCU(ctu, absPartIdx, depth, lx, ty); break;
+    default: fail("CU with no prediction mode"); break;
+  }
+  if (ctu->isLosslessCoded(absPartIdx)) fail("lossless CU (post-filter restoration not implemented)");
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual record for one square TU of one component: TComTrQuant::invTransformNxN (TComTrQuant.cpp:1423-1548)
+uint32_t HmEmitter::emitResidualTU(CuCtx& c, int compIdx, void* pTu, bool intra, bool coded, int alpha)
+{
+  TComTU& rTu = *(TComTU*)pTu;
+  const ComponentID compID = ComponentID(compIdx);
+  TComDataCU* ctu = c.ctu;
+  TComPic* pic = ctu->getPic();
+  const TComRectangle& rect = rTu.getRect(compID);
+  const unsigned absPartIdxTU = rTu.GetAbsPartIdxTU();
+  const int csx = pic->getComponentScaleX(compID), csy = pic->getComponentScaleY(compID);
+  const int N = rect.width;
+  assert(rect.width == rect.height);
+
+  hmr_tu t;
+  memset(&t, 0, sizeof(t));
+  t.x = (uint16_t)((c.cuX >> csx) + rect.x0);
+  t.y = (uint16_t)((c.cuY >> csy) + rect.y0);
+  t.comp = (uint8_t)compIdx;
+  t.log2_size = (uint8_t)(g_aucConvertToBit[N] + 2);
+  t.ccp_alpha = (int8_t)alpha;
+  t.luma_off = HMR_NO_OFFSET;
+  if (coded) t.flags |= HMR_TU_CODED;
+  if (intra) t.flags |= HMR_TU_INTRA;
+
+  const bool bypass = ctu->getCUTransquantBypass(absPartIdxTU);
+  const bool tskip  = ctu->getTransformSkip(absPartIdxTU, compID) != 0;
+  if (bypass) t.flags |= HMR_TU_BYPASS;
+  else if (tskip) t.flags |= HMR_TU_TSKIP;
+  if ((bypass || tskip) && rTu.isNonTransformedResidualRotated(compID)) t.flags |= HMR_TU_ROTATE;
+  if (!bypass && !tskip && N == 4 && rTu.useDST(compID)) t.flags |= HMR_TU_DST;
+
+  // invRdpcmNxN (TComTrQuant.cpp:1737-1792)
+  if (ctu->isRDPCMEnabled(absPartIdxTU) && (tskip || bypass))
+  {
+    int mode = RDPCM_OFF;
+    if (ctu->isIntra(absPartIdxTU))
+    {
+      const ChromaFormat chFmt = pic->getChromaFormat();
+      const ChannelType chType = toChannelType(compID);
+      const UInt chPredMode  = ctu->getIntraDir(chType, absPartIdxTU);
+      const UInt chCodedMode = (chPredMode == DM_CHROMA_IDX && isChroma(compID)) ? ctu->getIntraDir(CHANNEL_TYPE_LUMA, getChromasCorrespondingPULumaIdx(absPartIdxTU, chFmt)) : chPredMode;
+      const UInt chFinalMode = ((chFmt == CHROMA_422) && isChroma(compID)) ? g_chroma422IntraAngleMappingTable[chCodedMode] : chCodedMode;
+      if (chFinalMode == VER_IDX) mode = RDPCM_VER; else if (chFinalMode == HOR_IDX) mode = RDPCM_HOR;
+    }
+    else mode = ctu->getExplicitRdpcmMode(compID, absPartIdxTU);
+    if (mode == RDPCM_HOR) t.flags |= HMR_TU_RDPCM_H;
+    if (mode == RDPCM_VER) t.flags |= HMR_TU_RDPCM_V;
+  }
+
+  // QpParam::QpParam(const TComDataCU&, ComponentID) evaluated at this CU (TComTrQuant.cpp:99-119)
+  {
+    TComSlice* slice = ctu->getSlice();
+    Int chromaQpOffset = 0;
+    if (isChroma(compID))
+    {
+      chromaQpOffset += slice->getPPS()->getQpOffset(compID);
+      chromaQpOffset += slice->getSliceChromaQpDelta(compID);
+      chromaQpOffset += slice->getPPS()->getChromaQpAdjTableAt(ctu->getChromaQpAdj(c.absPartIdx)).u.offset[Int(compID) - 1];
+    }
+    QpParam qp(ctu->getQP(c.absPartIdx), toChannelType(compID), slice->getSPS()->getQpBDOffset(toChannelType(compID)), chromaQpOffset, pic->getChromaFormat());
+    t.qp = (uint8_t)qp.Qp;
+  }
+
+  // coefficient levels: int32 raster N x N at getCoeff()+offset (TDecSbac.cpp:1260); the dequantiser clips its
+  // input to 16 bits for every legal QP/bit-depth (TComTrQuant.cpp:1284-1286), so int16 transport is exact
+  t.coef_off = (uint32_t)m_coef.size();
+  m_coef.resize(m_coef.size() + (size_t)N * N);
+  int16_t* dst = &m_coef[t.coef_off];
+  if (coded)
+  {
+    const TCoeff* src = ctu->getCoeff(compID) + rTu.getCoefficientOffset(compID);
+    for (int i = 0; i < N * N; i++)
+    {
+      TCoeff v = src[i];
+      dst[i] = (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v));
+    }
+  }
+  else memset(dst, 0, sizeof(int16_t) * N * N);
+
+  if (compIdx == 0) c.lumaOff[absPartIdxTU - c.absPartIdx] = t.coef_off;
+  else if (alpha != 0) t.luma_off = c.lumaOff[absPartIdxTU - c.absPartIdx];
+
+  m_tu.push_back(t);
+  return t.coef_off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// inter CU: TDecCu::xReconInter (TDecCu.cpp:449-480) = motionCompensation + xDecodeInterTexture
+void HmEmitter::emitInterCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, int cuX, int cuY, int cuSize)
+{
+  TComSlice* slice = ctu->getSlice();
+  TComPic*   pic   = ctu->getPic();
+  if (slice->getPPS()->getUseWP() && slice->getSliceType() == P_SLICE) fail("explicit weighted prediction (P)");
+  if (slice->getPPS()->getWPBiPred() && slice->getSliceType() == B_SLICE) fail("explicit weighted prediction (B)");
+
+  // PU geometry: TComDataCU::getPartIndexAndSize (TComDataCU.cpp:2178-2230)
+  int n = 1, px[4] = {0, 0, 0, 0}, py[4] = {0, 0, 0, 0}, pw[4], ph[4];
+  const int S = cuSize, H = S >> 1, Q = S >> 2;
+  switch (ctu->getPartitionSize(absPartIdx))
+  {
+    case SIZE_2NxN:  n = 2; pw[0] = pw[1] = S; ph[0] = ph[1] = H; py[1] = H; break;
+    case SIZE_Nx2N:  n = 2; pw[0] = pw[1] = H; ph[0] = ph[1] = S; px[1] = H; break;
+    case SIZE_NxN:   n = 4; for (int i = 0; i < 4; i++) { pw[i] = ph[i] = H; px[i] = (i & 1) * H; py[i] = (i >> 1) * H; } break;
+    case SIZE_2NxnU: n = 2; pw[0] = pw[1] = S; ph[0] = Q; ph[1] = S - Q; py[1] = Q; break;
+    case SIZE_2NxnD: n = 2; pw[0] = pw[1] = S; ph[0] = S - Q; ph[1] = Q; py[1] = S - Q; break;
+    case SIZE_nLx2N: n = 2; ph[0] = ph[1] = S; pw[0] = Q; pw[1] = S - Q; px[1] = Q; break;
+    case SIZE_nRx2N: n = 2; ph[0] = ph[1] = S; pw[0] = S - Q; pw[1] = Q; px[1] = S - Q; break;
+    default:         n = 1; pw[0] = ph[0] = S; break;
+  }
+  const unsigned partStride = pic->getNumPartInWidth();
+  const unsigned cuRaster = g_auiZscanToRaster[absPartIdx];
+  const int picW = slice->getSPS()->getPicWidthInLumaSamples(), picH = slice->getSPS()->getPicHeightInLumaSamples();
+  for (int i = 0; i < n; i++)
+  {
+    const unsigned partAddr = g_auiRasterToZscan[cuRaster + (py[i] >> 2) * partStride + (px[i] >> 2)];
+    hmr_pu p;
+    memset(&p, 0, sizeof(p));
+    p.x = (uint16_t)(cuX + px[i]); p.y = (uint16_t)(cuY + py[i]);
+    p.w = (uint8_t)pw[i]; p.h = (uint8_t)ph[i];
+    int refIdx[2]; TComMv mv[2]; TComPic* ref[2] = {NULL, NULL};
+    for (int l = 0; l < 2; l++)
+    {
+      refIdx[l] = ctu->getCUMvField(RefPicList(l))->getRefIdx(partAddr);
+      mv[l]     = ctu->getCUMvField(RefPicList(l))->getMv(partAddr);
+      if (refIdx[l] >= 0) ref[l] = slice->getRefPic(RefPicList(l), refIdx[l]);
+    }
+    bool use0 = refIdx[0] >= 0, use1 = refIdx[1] >= 0;
+    // xCheckIdenticalMotion (TComPrediction.cpp:497-512)
+    if (use0 && use1 && slice->isInterB() && !slice->getPPS()->getWPBiPred() &&
+        ref[0]->getPOC() == ref[1]->getPOC() && mv[0] == mv[1]) use1 = false;
+    if (!use0 && !use1) { fail("inter PU without reference"); continue; }
+    int slot[2] = {0, 0};
+    for (int l = 0; l < 2; l++)
+    {
+      if (!(l ? use1 : use0)) continue;
+      // TComDataCU::clipMv with the CU's own position (TComDataCU.cpp:3102-3114; pcCU is the sub-CU copy there)
+      int hmax = (picW + 8 - cuX - 1) << 2, hmin = (-(int)g_uiMaxCUWidth - 8 - cuX + 1) << 2;
+      int vmax = (picH + 8 - cuY - 1) << 2, vmin = (-(int)g_uiMaxCUHeight - 8 - cuY + 1) << 2;
+      p.mv[l][0] = (int16_t)std::min(hmax, std::max(hmin, (int)mv[l].getHor()));
+      p.mv[l][1] = (int16_t)std::min(vmax, std::max(vmin, (int)mv[l].getVer()));
+      slot[l] = slotOf(ref[l]);
+      p.lists |= (l ? HMR_PU_L1 : HMR_PU_L0);
+    }
+    p.slots = (uint8_t)(slot[0] | (slot[1] << 4));
+    m_pu.push_back(p);
+    m_puPrefix.push_back(m_puPrefix.back() + ((pw[i] + 15) >> 4) * ((ph[i] + 15) >> 4));
+  }
+
+  // residual: xDecodeInterTexture -> invRecurTransformNxN per component (TDecCu.cpp:743-758, TComTrQuant.cpp:1550-1615)
+  CuCtx c;
+  c.ctu = ctu; c.absPartIdx = absPartIdx; c.depth = depth; c.cuX = cuX; c.cuY = cuY;
+  for (int i = 0; i < 256; i++) c.lumaOff[i] = HMR_NO_OFFSET;
+  TComTURecurse tuRecur(ctu, absPartIdx, depth);
+  for (UInt ch = 0; ch < pic->getNumberValidComponents(); ch++) interResidual(c, ch, &tuRecur);
+}
+
+void HmEmitter::interResidual(CuCtx& c, int compIdx, void* pTu)
+{
+  TComTU& rTu = *(TComTU*)pTu;
+  const ComponentID compID = ComponentID(compIdx);
+  if (!rTu.ProcessComponentSection(compID)) return;
+  TComDataCU* ctu = c.ctu;
+  const UInt absPartIdxTU = rTu.GetAbsPartIdxTU();
+  const UInt trMode = rTu.GetTransformDepthRel();
+  const bool ccpEnabled = ctu->getSlice()->getPPS()->getUseCrossComponentPrediction();
+  if (ctu->getCbf(absPartIdxTU, compID, trMode) == 0 && (isLuma(compID) || !ccpEnabled)) return;
+
+  if (trMode == ctu->getTransformIdx(absPartIdxTU))
+  {
+    const bool coded = ctu->getCbf(absPartIdxTU, compID, trMode) != 0;
+    int alpha = 0;
+    if (isChroma(compID) && ctu->getCrossComponentPredictionAlpha(absPartIdxTU, compID) != 0 &&
+        ctu->getCbf(absPartIdxTU, COMPONENT_Y, trMode) != 0)
+      alpha = ctu->getCrossComponentPredictionAlpha(absPartIdxTU, compID);
+    if (!coded && alpha == 0) return;
+    const TComRectangle& rect = rTu.getRect(compID);
+    if (rect.width != rect.height)
+    {
+      // 4:2:2 chroma: two square halves, both run through the transform (TComTrQuant.cpp:1437-1464)
+      TComTURecurse sub(rTu, false, TComTU::VERTICAL_SPLIT, true, compID);
+      do { emitResidualTU(c, compIdx, &sub, false, coded, alpha); } while (sub.nextSection(rTu));
+    }
+    else emitResidualTU(c, compIdx, &rTu, false, coded, alpha);
+  }
+  else
+  {
+    TComTURecurse child(rTu, false);
+    do { interResidual(c, compIdx, &child); } while (child.nextSection(rTu));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// intra CU: TDecCu::xReconIntraQT / xIntraRecQT / xIntraRecBlk (TDecCu.cpp:662-732, 483-659)
+void HmEmitter::emitIntraCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, int cuX, int cuY)
+{
+  if (ctu->getIPCMFlag(absPartIdx)) { fail("IPCM CU"); return; }
+  CuCtx c;
+  c.ctu = ctu; c.absPartIdx = absPartIdx; c.depth = depth; c.cuX = cuX; c.cuY = cuY;
+  for (int i = 0; i < 256; i++) c.lumaOff[i] = HMR_NO_OFFSET;
+  const ChromaFormat chFmt = ctu->getPic()->getChromaFormat();
+  const UInt numChType = chFmt != CHROMA_400 ? 2 : 1;
+  for (UInt chType = CHANNEL_TYPE_LUMA; chType < numChType; chType++)
+  {
+    const bool NxNPUHas4Parts = ::isChroma(ChannelType(chType)) ? enable4ChromaPUsInIntraNxNCU(chFmt) : true;
+    const UInt initTrDepth = (ctu->getPartitionSize(absPartIdx) != SIZE_2Nx2N && NxNPUHas4Parts) ? 1 : 0;
+    TComTURecurse tuCU(ctu, absPartIdx);
+    TComTURecurse tuPU(tuCU, false, (initTrDepth == 0) ? TComTU::DONT_SPLIT : TComTU::QUAD_SPLIT);
+    do { intraQT(c, chType, &tuPU); } while (tuPU.nextSection(tuCU));
+  }
+}
+
+void HmEmitter::intraQT(CuCtx& c, int chType, void* pTu)
+{
+  TComTU& rTu = *(TComTU*)pTu;
+  TComDataCU* ctu = c.ctu;
+  const UInt trDepth = rTu.GetTransformDepthRel();
+  const UInt absPartIdx = rTu.GetAbsPartIdxTU();
+  if (ctu->getTransformIdx(absPartIdx) == trDepth)
+  {
+    if (chType == CHANNEL_TYPE_LUMA) intraBlk(c, COMPONENT_Y, &rTu);
+    else
+    {
+      const UInt numValidComp = getNumberValidComponents(rTu.GetChromaFormat());
+      for (UInt comp = COMPONENT_Cb; comp < numValidComp; comp++) intraBlk(c, comp, &rTu);
+    }
+  }
+  else
+  {
+    TComTURecurse child(rTu, false);
+    do { intraQT(c, chType, &child); } while (child.nextSection(rTu));
+  }
+}
+
+void HmEmitter::intraBlk(CuCtx& c, int compIdx, void* pTu)
+{
+  TComTU& rTu = *(TComTU*)pTu;
+  const ComponentID compID = ComponentID(compIdx);
+  if (!rTu.ProcessComponentSection(compID)) return;
+  TComDataCU* ctu = c.ctu;
+  TComPic* pic = ctu->getPic();
+  const bool bIsLuma = isLuma(compID);
+  const UInt absPartIdx = rTu.GetAbsPartIdxTU();
+  const TComRectangle& rect = rTu.getRect(compID);
+  const UInt W = rect.width, Hh = rect.height;
+  const ChromaFormat chFmt = rTu.GetChromaFormat();
+  if (W != Hh)
+  {
+    TComTURecurse sub(rTu, false, TComTU::VERTICAL_SPLIT, true, compID);
+    do { intraBlk(c, compIdx, &sub); } while (sub.nextSection(rTu));
+    return;
+  }
+  const UInt chPredMode  = ctu->getIntraDir(toChannelType(compID), absPartIdx);
+  const UInt chCodedMode = (chPredMode == DM_CHROMA_IDX && !bIsLuma) ? ctu->getIntraDir(CHANNEL_TYPE_LUMA, getChromasCorrespondingPULumaIdx(absPartIdx, chFmt)) : chPredMode;
+  const UInt chFinalMode = ((chFmt == CHROMA_422) && !bIsLuma) ? g_chroma422IntraAngleMappingTable[chCodedMode] : chCodedMode;
+
+  hmr_intra r;
+  memset(&r, 0, sizeof(r));
+  const int csx = pic->getComponentScaleX(compID), csy = pic->getComponentScaleY(compID);
+  r.x = (uint16_t)((c.cuX >> csx) + rect.x0);
+  r.y = (uint16_t)((c.cuY >> csy) + rect.y0);
+  r.comp = (uint8_t)compIdx;
+  r.log2_size = (uint8_t)(g_aucConvertToBit[W] + 2);
+  r.mode = (uint8_t)chFinalMode;
+  if (TComPrediction::filteringIntraReferenceSamples(compID, chFinalMode, W, Hh, chFmt, ctu->getSlice()->getSPS()->getDisableIntraReferenceSmoothing()))
+    r.flags |= HMR_INTRA_FILTER_REFS;
+  if (bIsLuma) r.flags |= HMR_INTRA_LUMA_RULES;
+  if (ctu->isRDPCMEnabled(absPartIdx) && ctu->getCUTransquantBypass(absPartIdx)) r.flags |= HMR_INTRA_NO_EDGE_FLT;
+
+  // neighbour availability: TComPrediction::initAdiPatternChType (TComPattern.cpp:107-145)
+  {
+    const Int baseUnit = g_uiMaxCUWidth >> g_uiMaxCUDepth;
+    const Int unitW = baseUnit >> csx, unitH = baseUnit >> csy;
+    const Int wUnits = W / unitW, hUnits = Hh / unitH;
+    const Int leftUnits = hUnits << 1;
+    const Int partStride = pic->getNumPartInWidth();
+    const UInt idxLT = ctu->getZorderIdxInCU() + absPartIdx;
+    const UInt idxRT = g_auiRasterToZscan[g_auiZscanToRaster[idxLT] + wUnits - 1];
+    const UInt idxLB = g_auiRasterToZscan[g_auiZscanToRaster[idxLT] + (hUnits - 1) * partStride];
+    Bool flags[4 * MAX_NUM_SPU_W + 1];
+    memset(flags, 0, sizeof(flags));
+    flags[leftUnits] = isAboveLeftAvailable(ctu, idxLT);
+    isAboveAvailable     (ctu, idxLT, idxRT, flags + leftUnits + 1);
+    isAboveRightAvailable(ctu, idxLT, idxRT, flags + leftUnits + 1 + wUnits);
+    isLeftAvailable      (ctu, idxLT, idxLB, flags + leftUnits - 1);
+    isBelowLeftAvailable (ctu, idxLT, idxLB, flags + leftUnits - 1 - hUnits);
+    if (flags[leftUnits]) r.flags |= HMR_INTRA_AVAIL_CORNER;
+    for (int i = 0; i < wUnits; i++)
+    {
+      if (flags[leftUnits + 1 + i])          r.avail_above       |= (uint8_t)(1u << i);
+      if (flags[leftUnits + 1 + wUnits + i]) r.avail_above_right |= (uint8_t)(1u << i);
+    }
+    for (int i = 0; i < hUnits; i++)
+    {
+      if (flags[leftUnits - 1 - i])          r.avail_left        |= (uint8_t)(1u << i);
+      if (flags[leftUnits - 1 - hUnits - i]) r.avail_below_left  |= (uint8_t)(1u << i);
+    }
+  }
+
+  // residual (TDecCu.cpp:560-586) + cross-component prediction (TDecCu.cpp:600-625)
+  const bool coded = ctu->getCbf(absPartIdx, compID, rTu.GetTransformDepthRel()) != 0;
+  const int alpha = isChroma(compID) ? ctu->getCrossComponentPredictionAlpha(absPartIdx, compID) : 0;
+  const bool keepLuma = bIsLuma && (m_hdr.flags & HMR_FRM_HAS_CCP); // chroma CCP may read a zero luma residual
+  r.resid_off = HMR_NO_OFFSET;
+  if (coded || alpha != 0 || keepLuma)
+  {
+    bool lumaHasResid = c.lumaOff[absPartIdx - c.absPartIdx] != HMR_NO_OFFSET;
+    if (coded || (alpha != 0 && lumaHasResid))
+      r.resid_off = emitResidualTU(c, compIdx, &rTu, true, coded, (alpha != 0 && lumaHasResid) ? alpha : 0);
+  }
+  m_intraTmp[compIdx].push_back(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// deblocking side info: TComLoopFilter::loopFilterPic / xDeblockCU (TComLoopFilter.cpp:130-234) without the filtering
+void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, TComLoopFilter* lf)
+{
+  if (ctu->getPic() == 0 || ctu->getPartitionSize(absZorderIdx) == NUMBER_OF_PART_SIZES) return;
+  TComPic* pic = ctu->getPic();
+  const unsigned curNumParts = pic->getNumPartInCU() >> (depth << 1);
+  const unsigned qNumParts = curNumParts >> 2;
+  const unsigned picW = ctu->getSlice()->getSPS()->getPicWidthInLumaSamples();
+  const unsigned picH = ctu->getSlice()->getSPS()->getPicHeightInLumaSamples();
+  if (ctu->getDepth(absZorderIdx) > depth)
+  {
+    for (unsigned p = 0; p < 4; p++, absZorderIdx += qNumParts)
+    {
+      unsigned lx = ctu->getCUPelX() + g_auiRasterToPelX[g_auiZscanToRaster[absZorderIdx]];
+      unsigned ty = ctu->getCUPelY() + g_auiRasterToPelY[g_auiZscanToRaster[absZorderIdx]];
+      if (lx < picW && ty < picH) bsWalk(ctu, absZorderIdx, depth + 1, lf);
+    }
+    return;
+  }
+  lf->xSetLoopfilterParam(ctu, absZorderIdx);
+  TComTURecurse tuRecurse(ctu, absZorderIdx);
+  lf->xSetEdgefilterTU(tuRecurse);
+  lf->xSetEdgefilterPU(ctu, absZorderIdx);
+
+  const int cuX = ctu->getCUPelX() + g_auiRasterToPelX[g_auiZscanToRaster[absZorderIdx]];
+  const int cuY = ctu->getCUPelY() + g_auiRasterToPelY[g_auiZscanToRaster[absZorderIdx]];
+  const int cuSize = g_uiMaxCUWidth >> depth;
+  for (int dir = 0; dir < 2; dir++)
+  {
+    for (unsigned part = absZorderIdx; part < absZorderIdx + curNumParts; part++)
+    {
+      // only partitions on the 8x8 luma grid carry an edge (uiBSCheck, TComLoopFilter.cpp:199-206)
+      const unsigned raster = g_auiZscanToRaster[part];
+      const int ux = g_auiRasterToPelX[raster] >> 2, uy = g_auiRasterToPelY[raster] >> 2;
+      const bool onGrid = (dir == EDGE_VER) ? ((ux & 1) == 0) : ((uy & 1) == 0);
+      if (!onGrid) continue;
+      if (lf->m_aapbEdgeFilter[dir][part])
+      {
+        lf->xGetBoundaryStrengthSingle(ctu, DeblockEdgeDir(dir), part);
+        const unsigned bs = lf->m_aapucBS[dir][part];
+        if (bs)
+        {
+          const int gx = (ctu->getCUPelX() >> 2) + ux, gy = (ctu->getCUPelY() >> 2) + uy;
+          m_bs[(size_t)gy * m_bsStride + gx] |= (uint8_t)(bs << (dir == EDGE_VER ? 0 : 2));
+        }
+      }
+    }
+  }
+  // QP / no-filter maps per 8x8 (TComLoopFilter.cpp:587-600,607-617)
+  const int qp = ctu->getQP(absZorderIdx);
+  const bool pcmFilterOff = ctu->getSlice()->getSPS()->getUsePCM() && ctu->getSlice()->getSPS()->getPCMFilterDisableFlag();
+  const bool nofilter = (pcmFilterOff && ctu->getIPCMFlag(absZorderIdx)) || ctu->isLosslessCoded(absZorderIdx);
+  if (nofilter) m_hdr.flags |= HMR_FRM_HAS_NOFILTER;
+  for (int y = cuY >> 3; y < ((cuY + cuSize) >> 3) && y < ((m_hdr.height + 7) >> 3); y++)
+    for (int x = cuX >> 3; x < ((cuX + cuSize) >> 3) && x < m_qpStride; x++)
+    {
+      m_qp[(size_t)y * m_qpStride + x] = (int8_t)qp;
+      m_cuFlags[(size_t)y * m_qpStride + x] = nofilter ? HMR_CU_NOFILTER : 0;
+    }
+}
+
+void HmEmitter::deblockInfo(TComPic* pic, TComLoopFilter* lf)
+{
+  bool any = false;
+  for (UInt a = 0; a < pic->getNumCUsInFrame(); a++)
+  {
+    TComDataCU* ctu = pic->getCU(a);
+    ::memset(lf->m_aapucBS[EDGE_VER], 0, sizeof(UChar) * lf->m_uiNumPartitions);
+    ::memset(lf->m_aapbEdgeFilter[EDGE_VER], 0, sizeof(Bool) * lf->m_uiNumPartitions);
+    ::memset(lf->m_aapucBS[EDGE_HOR], 0, sizeof(UChar) * lf->m_uiNumPartitions);
+    ::memset(lf->m_aapbEdgeFilter[EDGE_HOR], 0, sizeof(Bool) * lf->m_uiNumPartitions);
+    bsWalk(ctu, 0, 0, lf);
+    TComSlice* s = ctu->getSlice();
+    m_ctu[a].beta_offset_div2 = (int8_t)s->getDeblockingFilterBetaOffsetDiv2();
+    m_ctu[a].tc_offset_div2   = (int8_t)s->getDeblockingFilterTcOffsetDiv2();
+    if (!s->getDeblockingFilterDisable()) any = true;
+  }
+  if (any) m_hdr.flags |= HMR_FRM_DEBLOCK;
+}
+
+// SAO side info: reconstructBlkSAOParams (TComSampleAdaptiveOffset.cpp:348-372) then per-CTU flattening
+void HmEmitter::saoInfo(TComPic* pic, TComSampleAdaptiveOffset* sao)
+{
+  SAOBlkParam* blk = pic->getPicSym()->getSAOBlkParam();
+  sao->reconstructBlkSAOParams(pic, blk);
+  const int nComp = getNumberValidComponents(pic->getChromaFormat());
+  bool any = false;
+  for (UInt a = 0; a < pic->getNumCUsInFrame(); a++)
+  {
+    Bool l, r, ab, be, al, ar, bl, br;
+    pic->getPicSym()->deriveLoopFilterBoundaryAvailibility(a, l, r, ab, be, al, ar, bl, br);
+    m_ctu[a].avail = (uint8_t)((l ? HMR_AV_L : 0) | (r ? HMR_AV_R : 0) | (ab ? HMR_AV_A : 0) | (be ? HMR_AV_B : 0) |
+                               (al ? HMR_AV_AL : 0) | (ar ? HMR_AV_AR : 0) | (bl ? HMR_AV_BL : 0) | (br ? HMR_AV_BR : 0));
+    for (int c = 0; c < nComp; c++)
+    {
+      SAOOffset& o = blk[a][c];
+      hmr_sao& d = m_ctu[a].sao[c];
+      if (o.modeIdc == SAO_MODE_OFF) { d.type = HMR_SAO_OFF; continue; }
+      any = true;
+      if (o.typeIdc == SAO_TYPE_START_BO)
+      {
+        d.type = HMR_SAO_BO;
+        d.band = (uint8_t)o.typeAuxInfo;
+        for (int i = 0; i < 4; i++) d.off[i] = (int16_t)o.offset[(o.typeAuxInfo + i) % NUM_SAO_BO_CLASSES];
+      }
+      else
+      {
+        d.type = (uint8_t)(HMR_SAO_EO_0 + (o.typeIdc - SAO_TYPE_START_EO));
+        // offset[] is indexed by edgeIdx+2 with the "plain" class (edgeIdx 0) fixed at 0 (TComSampleAdaptiveOffset.cpp:245-249)
+        d.off[0] = (int16_t)o.offset[0]; d.off[1] = (int16_t)o.offset[1];
+        d.off[2] = (int16_t)o.offset[3]; d.off[3] = (int16_t)o.offset[4];
+      }
+    }
+  }
+  if (any) m_hdr.flags |= HMR_FRM_SAO;
+}
+
+// ---------------------------------------------------------------------------------------------
+void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdaptiveOffset* sao, bool lfCrossTiles)
+{
+  if (!m_open || pic != m_curPic) { fail("filterPicture for a picture with no parsed CTU"); return; }
+  TComSlice* slice = pic->getSlice(pic->getCurrSliceIdx());
+  lf->setCfg(lfCrossTiles);
+  deblockInfo(pic, lf);
+  if (slice->getSPS()->getUseSAO()) saoInfo(pic, sao);
+  if (slice->getSPS()->getUsePCM()) { /* PCM CUs themselves are rejected in emitIntraCU */ }
+  if (slice->isReferenced()) m_hdr.flags |= HMR_FRM_IS_REFERENCE;
+  if (m_pu.empty()) m_hdr.flags |= HMR_FRM_INTRA_ONLY;
+
+  // pad the coefficient buffer to a multiple of 16 entries
+  while (m_coef.size() & 15) m_coef.push_back(0);
+  m_hdr.n_tu = (uint32_t)m_tu.size();
+  m_hdr.n_coef = (uint32_t)m_coef.size();
+  m_hdr.n_intra = (uint32_t)m_intra.size();
+  m_hdr.n_pu = (uint32_t)m_pu.size();
+  m_hdr.n_mc_tiles = m_puPrefix.back();
+
+  hmr_frame_desc d;
+  d.hdr = &m_hdr;
+  d.tu = m_tu.data(); d.coef = m_coef.data();
+  d.intra = m_intra.data(); d.intra_range = m_range.data();
+  d.pu = m_pu.data(); d.pu_tile_prefix = m_puPrefix.data();
+  d.ctu = m_ctu.data();
+  d.bs = (m_hdr.flags & HMR_FRM_DEBLOCK) ? m_bs.data() : NULL;
+  d.qp = m_qp.data();
+  d.cu_flags = (m_hdr.flags & HMR_FRM_HAS_NOFILTER) ? m_cuFlags.data() : NULL;
+  m_sink->frameReady(d, pic);
+  m_open = false;
+}

@@ -1,0 +1,88 @@
+// hm_emit.h — reference-side binding: turns HM's parsed per-CTU data (TComDataCU) into the flat
+// per-frame records of include/hmr_records.h.  This file and hm_emit.cpp are compiled against the
+// HM headers under /root/reference (they are the glue a libHM maintainer would add, see
+// INTEGRATION.md); the reconstruction engine itself (libhm_b200/csrc) never sees an HM type.
+#ifndef HM_EMIT_H
+#define HM_EMIT_H
+
+#include <stdint.h>
+#include <vector>
+#include <map>
+#include "hmr_records.h"
+
+class TComPic;
+class TComDataCU;
+class TComSlice;
+class TComLoopFilter;
+class TComSampleAdaptiveOffset;
+
+// Receives one finished picture's records.  Implementations: file dumper (tools), GPU engine
+// (hmdec_b200.cpp).  `pic` is HM's DPB entry the picture belongs to (slot bookkeeping / D2H target).
+struct HmFrameSink
+{
+  virtual ~HmFrameSink() {}
+  // Called once all CTUs of the picture are parsed and the loop-filter side info is known.
+  virtual void frameReady(const hmr_frame_desc& desc, TComPic* pic) = 0;
+  // Make HM's own TComPicYuv of `pic` hold the final reconstruction (D2H for the GPU sink; no-op when
+  // HM reconstructed on the CPU).  Needed before the SEI hash check / plane access.
+  virtual void fetchPicture(TComPic* pic) = 0;
+  // true: HM's CPU reconstruction runs as well (verification / golden generation); false: GPU only.
+  virtual bool wantHmRecon() const = 0;
+  // wantHmRecon() only: HM's CPU planes after stage 0 = CU reconstruction, 1 = deblocking, 2 = SAO (final).
+  virtual void hmStage(int stage, TComPic* pic) { (void)stage; (void)pic; }
+};
+
+class HmEmitter
+{
+public:
+  explicit HmEmitter(HmFrameSink* sink);
+  ~HmEmitter();
+
+  void onCtuParsed(TComDataCU* ctu);                                      // splice at TDecSlice.cpp:334
+  void onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdaptiveOffset* sao, bool lfCrossTiles); // splice at TDecGop.cpp:157
+  HmFrameSink* sink() { return m_sink; }
+  int  slotOf(TComPic* pic);
+  const char* unsupported() const { return m_unsupported; }
+
+private:
+  struct CuCtx;
+  void beginFrame(TComPic* pic, TComDataCU* ctu);
+  void walkCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth);
+  void emitInterCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, int cuX, int cuY, int cuSize);
+  void emitIntraCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, int cuX, int cuY);
+  void interResidual(CuCtx& c, int compID, void* rTu);
+  void intraQT(CuCtx& c, int chType, void* rTu);
+  void intraBlk(CuCtx& c, int compID, void* rTu);
+  uint32_t emitResidualTU(CuCtx& c, int compID, void* rTu, bool intra, bool coded, int alpha);
+  void deblockInfo(TComPic* pic, TComLoopFilter* lf);
+  void bsWalk(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, TComLoopFilter* lf);
+  void saoInfo(TComPic* pic, TComSampleAdaptiveOffset* sao);
+  void fail(const char* what);
+
+  HmFrameSink* m_sink;
+  TComPic*     m_curPic;
+  bool         m_open;
+  const char*  m_unsupported;
+  std::map<TComPic*, int> m_slots;
+
+  hmr_frame_hdr                    m_hdr;
+  std::vector<hmr_tu>              m_tu;
+  std::vector<int16_t>             m_coef;
+  std::vector<hmr_intra>           m_intra;
+  std::vector<hmr_intra>           m_intraTmp[3];
+  std::vector<hmr_ctu_intra_range> m_range;
+  std::vector<hmr_pu>              m_pu;
+  std::vector<uint32_t>            m_puPrefix;
+  std::vector<hmr_ctu>             m_ctu;
+  std::vector<uint8_t>             m_bs;
+  std::vector<int8_t>              m_qp;
+  std::vector<uint8_t>             m_cuFlags;
+  int m_bsStride, m_qpStride;
+};
+
+// The emitter the hooks (TDecCu::decompressCU / TDecGop::filterPicture replacements) talk to.
+// Set by the wrapper around every TDecTop call; one decoder per thread.
+void       hm_emit_set_current(HmEmitter* e);
+HmEmitter* hm_emit_current();
+
+#endif

@@ -1,0 +1,122 @@
+// hm_hooks.cpp — the two splice points of the GPU reconstruction path inside HM's decoder:
+//   * TDecCu::decompressCU   (called from TDecSlice.cpp:334 right after each CTU is parsed)
+//   * TDecGop::filterPicture (called from TDecTop::executeLoopFilters, TDecTop.cpp:202)
+// frontend/Makefile compiles HM's TDecCu.cpp / TDecGop.cpp with these two member functions renamed
+// (-DdecompressCU=decompressCU_hm, -DfilterPicture=filterPicture_hm); the definitions below take their
+// place at link time.  HM's sources are not modified.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <list>
+#include <iostream>
+#include "TLibDecoder/TDecCu.h"
+#include "TLibDecoder/TDecGop.h"
+#include "TLibCommon/TComLoopFilter.h"
+#include "TLibCommon/TComSampleAdaptiveOffset.h"
+#include "TLibCommon/SEI.h"
+#include "hm_emit.h"
+
+extern Bool g_md5_mismatch;
+void hm_call_original_decompressCU(TDecCu* dec, TComDataCU* ctu);
+
+static HmEmitter* requireEmitter()
+{
+  HmEmitter* e = hm_emit_current();
+  if (!e)
+  {
+    fprintf(stderr, "hm_hooks: no HmEmitter bound to this thread (decoder must be driven through libHMDec_*)\n");
+    abort();
+  }
+  return e;
+}
+
+Void TDecCu::decompressCU(TComDataCU* pcCU)
+{
+  HmEmitter* e = requireEmitter();
+  e->onCtuParsed(pcCU);
+  if (e->sink()->wantHmRecon()) hm_call_original_decompressCU(this, pcCU);
+}
+
+// Status line + SEI hash check, same text as TDecGop::filterPicture / calcAndPrintHashStatus (TDecGop.cpp:176-289)
+static void printStatusAndHash(TComPic* pic, TComSlice* slice, Int hashEnabled, HmEmitter* e, bool quiet)
+{
+#define P(...) do { if (!quiet) printf(__VA_ARGS__); } while (0)
+  Char c = (slice->isIntra() ? 'I' : slice->isInterP() ? 'P' : 'B');
+  if (!slice->isReferenced()) c += 32;
+  P("POC %4d TId: %1d ( %c-SLICE, QP%3d ) ", slice->getPOC(), slice->getTLayer(), c, slice->getSliceQp());
+  P("[DT %6.3f] ", 0.0);
+  for (Int l = 0; l < 2; l++)
+  {
+    P("[L%d ", l);
+    for (Int i = 0; i < slice->getNumRefIdx(RefPicList(l)); i++) P("%d ", slice->getRefPOC(RefPicList(l), i));
+    P("] ");
+  }
+  if (hashEnabled)
+  {
+    SEIMessages hashes = getSeisByType(pic->getSEIs(), SEI::DECODED_PICTURE_HASH);
+    const SEIDecodedPictureHash* hash = hashes.size() > 0 ? (SEIDecodedPictureHash*)*(hashes.begin()) : NULL;
+    if (hashes.size() > 1) P("Warning: Got multiple decoded picture hash SEI messages. Using first.");
+    TComDigest digest; Int numChar = 0; const Char* type = "\0";
+    if (hash)
+    {
+      e->sink()->fetchPicture(pic);      // D2H of the reconstructed planes into HM's TComPicYuv
+      TComPicYuv& rec = *pic->getPicYuvRec();
+      switch (hash->method)
+      {
+        case SEIDecodedPictureHash::MD5:      type = "MD5";      numChar = calcMD5(rec, digest); break;
+        case SEIDecodedPictureHash::CRC:      type = "CRC";      numChar = calcCRC(rec, digest); break;
+        case SEIDecodedPictureHash::CHECKSUM: type = "Checksum"; numChar = calcChecksum(rec, digest); break;
+        default: break;
+      }
+    }
+    const Char* ok = "(unk)"; Bool mismatch = false;
+    if (hash) { ok = "(OK)"; if (digest != hash->m_digest) { ok = "(***ERROR***)"; mismatch = true; } }
+    P("[%s:%s,%s] ", type, digestToString(digest, numChar).c_str(), ok);
+    if (mismatch)
+    {
+      g_md5_mismatch = true;
+      P("[rx%s:%s] ", type, digestToString(hash->m_digest, numChar).c_str());
+    }
+  }
+  P("\n");
+#undef P
+}
+
+Void TDecGop::filterPicture(TComPic*& rpcPic)
+{
+  HmEmitter* e = requireEmitter();
+  TComSlice* slice = rpcPic->getSlice(rpcPic->getCurrSliceIdx());
+  const Bool lfCrossTiles = slice->getPPS()->getLoopFilterAcrossTilesEnabledFlag();
+
+  // boundary strengths need the full-resolution motion field => before compressMotion()
+  e->onPictureParsed(rpcPic, m_pcLoopFilter, m_pcSAO, lfCrossTiles);
+
+  if (e->sink()->wantHmRecon())
+  {
+    // verification / golden generation: HM's own CPU filters, stage by stage (TDecGop.cpp:165-174)
+    e->sink()->hmStage(0, rpcPic);
+    m_pcLoopFilter->setCfg(lfCrossTiles);
+    m_pcLoopFilter->loopFilterPic(rpcPic);
+    e->sink()->hmStage(1, rpcPic);
+    if (slice->getSPS()->getUseSAO())
+    {
+      // SAO parameters were already merged/scaled by the emitter (reconstructBlkSAOParams is not idempotent)
+      m_pcSAO->SAOProcess(rpcPic);
+      m_pcSAO->PCMLFDisableProcess(rpcPic);
+    }
+    e->sink()->hmStage(2, rpcPic);
+  }
+
+  rpcPic->compressMotion();
+  static const bool quiet = getenv("HMDEC_B200_QUIET") != NULL;   // the hash is still verified
+  printStatusAndHash(rpcPic, slice, m_decodedPictureHashSEIEnabled, e, quiet);
+
+#if SETTING_PIC_OUTPUT_MARK
+  rpcPic->setOutputMark(rpcPic->getSlice(0)->getPicOutputFlag() ? true : false);
+#else
+  rpcPic->setOutputMark(true);
+#endif
+  rpcPic->setReconMark(true);
+}

@@ -1,0 +1,334 @@
+// hmdec_b200.cpp — drop-in implementation of the libHMDecoder C wrapper
+// (reference: source/App/libHMDecoder/libHMDecoder.{h,cpp}) on top of the B200 reconstruction engine.
+//
+// Parsing (NAL, parameter sets, CABAC, motion derivation, DPB management, output bumping) is HM's
+// TDecTop, unmodified, exactly as in the reference wrapper.  Reconstruction is NOT: every parsed CTU
+// is turned into flat records (hm_emit.cpp) and every finished picture is handed to an HmFrameSink —
+// by default the GPU engine.  Sample planes come back from the device only when somebody looks at
+// them (libHMDEC_get_image_plane, SEI hash check).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <list>
+#include <map>
+#include <mutex>
+#include <iostream>
+#include "TLibCommon/CommonDef.h"
+#include "TLibCommon/TComTU.h"
+#include "TLibDecoder/TDecTop.h"
+#include "TLibDecoder/NALread.h"
+#include "libHMDecoder_api.h"
+#include "hm_emit.h"
+
+// HM keeps the "hash mismatch seen" flag in a global that the application must define (TDecGop.cpp:48).
+bool g_md5_mismatch = false;
+
+HmFrameSink* hm_new_dump_sink(const char* path);
+HmFrameSink* hm_new_gpu_sink();           // gpu_sink.cpp
+std::vector<libHMDec_BlockValue>* hm_collect_internals(std::vector<libHMDec_BlockValue>& out, TComPic* pic, libHMDec_info_type type); // internals.cpp
+
+namespace {
+
+// picture -> owning decoder, for the ctx-less plane accessor (libHMDEC_get_image_plane has no ctx argument)
+std::mutex g_picOwnerLock;
+std::map<const void*, struct Decoder*> g_picOwner;
+
+struct Decoder
+{
+  TDecTop      top;
+  HmFrameSink* sink;
+  HmEmitter*   emitter;
+
+  // output state, cf. libHMDecoder.cpp:19-61 / TAppDecTop::xWriteOutput
+  int   maxTemporalLayer;
+  int   lastDisplayedPoc;
+  int   skipFrames;
+  TComList<TComPic*>* dpb;
+  int   cursor;              // index into *dpb of the next candidate for libHMDec_get_picture
+  int   pendingOutput;       // pictures marked for output and not yet displayed
+  int   dpbFullness;
+  unsigned reorderLimit, bufferingLimit;
+  bool  loopFilterDone;
+  bool  flushing;            // output everything that is marked, regardless of the bumping rule
+  bool  flushAfterThisPass;  // eof: one normal pass, then a flush pass
+  bool  hashMismatch;
+  std::vector<libHMDec_BlockValue> internals;
+
+  Decoder(HmFrameSink* s)
+    : sink(s), emitter(new HmEmitter(s)), maxTemporalLayer(-1), lastDisplayedPoc(-MAX_INT), skipFrames(0), dpb(NULL),
+      cursor(0), pendingOutput(0), dpbFullness(0), reorderLimit(0), bufferingLimit(0), loopFilterDone(false),
+      flushing(false), flushAfterThisPass(false), hashMismatch(false)
+  {
+    top.create();
+    top.init();
+    top.setDecodedPictureHashSEIEnabled(true);
+  }
+  ~Decoder()
+  {
+    {
+      std::lock_guard<std::mutex> g(g_picOwnerLock);
+      for (std::map<const void*, Decoder*>::iterator it = g_picOwner.begin(); it != g_picOwner.end();)
+        if (it->second == this) g_picOwner.erase(it++); else ++it;
+    }
+    hm_emit_set_current(emitter);
+    top.destroy();
+    hm_emit_set_current(NULL);
+    delete emitter;
+    delete sink;
+  }
+
+  void claimPictures()
+  {
+    if (!dpb) return;
+    std::lock_guard<std::mutex> g(g_picOwnerLock);
+    for (TComList<TComPic*>::iterator it = dpb->begin(); it != dpb->end(); ++it) g_picOwner[*it] = this;
+  }
+
+  // C.5.2.2 bumping inputs, recomputed whenever a picture completes (TAppDecTop.cpp:324-380)
+  void refreshOutputCounters()
+  {
+    TComSPS* sps = top.getActiveSPS();
+    const unsigned layers = sps->getMaxTLayers();
+    const unsigned t = (maxTemporalLayer == -1 || maxTemporalLayer >= (int)layers) ? layers - 1 : (unsigned)maxTemporalLayer;
+    reorderLimit   = sps->getNumReorderPics(t);
+    bufferingLimit = sps->getMaxDecPicBuffering(t);
+    pendingOutput = dpbFullness = 0;
+    for (TComList<TComPic*>::iterator it = dpb->begin(); it != dpb->end(); ++it)
+    {
+      TComPic* p = *it;
+      if (p->getOutputMark() && p->getPOC() > lastDisplayedPoc) { pendingOutput++; dpbFullness++; }
+      else if (p->getSlice(0)->isReferenced()) dpbFullness++;
+    }
+  }
+};
+
+inline Decoder* D(libHMDec_context* c) { return (Decoder*)c; }
+inline bool isIrapFlushType(NalUnitType t)
+{
+  return t == NAL_UNIT_CODED_SLICE_IDR_W_RADL || t == NAL_UNIT_CODED_SLICE_IDR_N_LP || t == NAL_UNIT_CODED_SLICE_BLA_N_LP ||
+         t == NAL_UNIT_CODED_SLICE_BLA_W_RADL || t == NAL_UNIT_CODED_SLICE_BLA_W_LP;
+}
+inline ComponentID toComp(libHMDec_ColorComponent c, bool& ok)
+{
+  ok = (c == LIBHMDEC_LUMA || c == LIBHMDEC_CHROMA_U || c == LIBHMDEC_CHROMA_V);
+  return c == LIBHMDEC_LUMA ? COMPONENT_Y : (c == LIBHMDEC_CHROMA_U ? COMPONENT_Cb : COMPONENT_Cr);
+}
+
+} // namespace
+
+extern "C" {
+
+const char* libHMDec_get_version(void) { return NV_VERSION; }
+
+libHMDec_context* libHMDecB200_new_decoder_ex(int backend, const char* arg)
+{
+  HmFrameSink* sink = NULL;
+  if (backend == 0) sink = hm_new_gpu_sink();
+  else if (backend == 1 && arg) sink = hm_new_dump_sink(arg);
+  if (!sink) return NULL;
+  return (libHMDec_context*)new Decoder(sink);
+}
+
+libHMDec_context* libHMDec_new_decoder(void)
+{
+  // tools may redirect the default back-end; there is deliberately no CPU reconstruction back-end
+  const char* dump = getenv("HMDEC_B200_DUMP");
+  return dump ? libHMDecB200_new_decoder_ex(1, dump) : libHMDecB200_new_decoder_ex(0, NULL);
+}
+
+libHMDec_error libHMDec_free_decoder(libHMDec_context* decCtx)
+{
+  if (!decCtx) return LIBHMDEC_ERROR;
+  delete D(decCtx);
+  return LIBHMDEC_OK;
+}
+
+void libHMDec_set_SEI_Check(libHMDec_context* decCtx, bool check_hash)
+{
+  if (decCtx) D(decCtx)->top.setDecodedPictureHashSEIEnabled(check_hash);
+}
+
+void libHMDec_set_max_temporal_layer(libHMDec_context* decCtx, int max_layer)
+{
+  if (decCtx) D(decCtx)->maxTemporalLayer = max_layer;
+}
+
+bool libHMDecB200_hash_mismatch(libHMDec_context* decCtx) { return decCtx ? D(decCtx)->hashMismatch : false; }
+const char* libHMDecB200_unsupported(libHMDec_context* decCtx) { return decCtx ? D(decCtx)->emitter->unsupported() : NULL; }
+
+libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data8, int length, bool eof, bool& bNewPicture, bool& checkOutputPictures)
+{
+  Decoder* d = D(decCtx);
+  if (!d) return LIBHMDEC_ERROR;
+  if (length <= 0) return LIBHMDEC_ERROR_READ_ERROR;
+  if (length < 4 && !eof) return LIBHMDEC_ERROR_READ_ERROR;
+
+  // tolerate a leading Annex-B start code (00 00 01 / 00 00 00 01); the payload starts at the 2-byte NAL header.
+  // (The reference tests bytes 0,1,1 for the 3-byte form, libHMDecoder.cpp:128, which never matches a real start code.)
+  const uint8_t* p = (const uint8_t*)data8;
+  int skip = 0;
+  if (length >= 3 && p[0] == 0 && p[1] == 0 && p[2] == 1) skip = 3;
+  else if (length >= 4 && p[0] == 0 && p[1] == 0 && p[2] == 0 && p[3] == 1) skip = 4;
+  std::vector<uint8_t> bytes(p + skip, p + length);
+  if (bytes.size() < 2) return LIBHMDEC_ERROR_READ_ERROR;
+
+  InputNALUnit nalu;
+  read(nalu, bytes);                                   // NALread.cpp:144-154
+
+  hm_emit_set_current(d->emitter);
+  bNewPicture = false;
+  if (!(d->maxTemporalLayer >= 0 && (int)nalu.m_temporalId > d->maxTemporalLayer))
+  {
+    g_md5_mismatch = d->hashMismatch;
+    bNewPicture = d->top.decode(nalu, d->skipFrames, d->lastDisplayedPoc);   // TDecTop.cpp:729
+    d->hashMismatch = g_md5_mismatch;
+  }
+
+  // a picture is complete when the first slice of the next one shows up, at EOS, or at end of stream
+  if (bNewPicture || eof || nalu.m_nalUnitType == NAL_UNIT_EOS)
+  {
+    if (!d->loopFilterDone || !eof)
+    {
+      int poc;
+      g_md5_mismatch = d->hashMismatch;
+      d->top.executeLoopFilters(poc, d->dpb);          // -> TDecGop::filterPicture hook -> engine
+      d->hashMismatch = g_md5_mismatch;
+      d->claimPictures();
+    }
+    d->loopFilterDone = (nalu.m_nalUnitType == NAL_UNIT_EOS);
+  }
+  hm_emit_set_current(NULL);
+
+  checkOutputPictures = false;
+  d->flushing = false;
+  if (bNewPicture && isIrapFlushType(nalu.m_nalUnitType)) { checkOutputPictures = true; d->flushing = true; }
+  if (nalu.m_nalUnitType == NAL_UNIT_EOS) checkOutputPictures = true;
+
+  const bool vclConsumed = !bNewPicture && nalu.m_nalUnitType >= NAL_UNIT_CODED_SLICE_TRAIL_N && nalu.m_nalUnitType <= NAL_UNIT_RESERVED_VCL31;
+  if ((bNewPicture || vclConsumed) && d->dpb != NULL)
+  {
+    checkOutputPictures = true;
+    d->refreshOutputCounters();
+  }
+  if (eof) { checkOutputPictures = true; d->flushAfterThisPass = true; }
+  if (checkOutputPictures) d->cursor = 0;
+  return LIBHMDEC_OK;
+}
+
+libHMDec_picture* libHMDec_get_picture(libHMDec_context* decCtx)
+{
+  Decoder* d = D(decCtx);
+  if (!d || !d->dpb || d->dpb->size() == 0) return NULL;
+  if (d->cursor < 0 || d->cursor > (int)d->dpb->size()) return NULL;
+
+  TComList<TComPic*>::iterator it = d->dpb->begin();
+  for (int i = 0; i < d->cursor; i++) ++it;
+  if (it != d->dpb->end() && (*it)->isField()) return NULL;      // field output unsupported, as in the reference
+
+  for (; it != d->dpb->end(); ++it, d->cursor++)
+  {
+    TComPic* pic = *it;
+    const bool bump = pic->getOutputMark() && pic->getPOC() > d->lastDisplayedPoc &&
+                      (d->pendingOutput > (int)d->reorderLimit || d->dpbFullness > (int)d->bufferingLimit);
+    if (!((d->flushing && pic->getOutputMark()) || bump)) continue;
+
+    if (!d->flushing) d->pendingOutput--;
+    if (!pic->getSlice(0)->isReferenced()) d->dpbFullness--;
+    d->lastDisplayedPoc = pic->getPOC();
+    if (!pic->getSlice(0)->isReferenced() && pic->getReconMark())
+    {
+      pic->setReconMark(false);
+      pic->getPicYuvRec()->setBorderExtension(false);
+    }
+    pic->setOutputMark(false);
+    return (libHMDec_picture*)pic;
+  }
+
+  if (d->flushing)
+  {
+    // NOTE: the planes of already returned pictures stay valid: TComList::clear() drops the pointers only
+    d->dpb->clear();
+    d->lastDisplayedPoc = -MAX_INT;
+    d->flushing = false;
+  }
+  if (d->flushAfterThisPass)
+  {
+    d->flushAfterThisPass = false;
+    d->flushing = true;
+    d->cursor = 0;
+    return libHMDec_get_picture(decCtx);
+  }
+  return NULL;
+}
+
+int libHMDEC_get_POC(libHMDec_picture* pic) { return pic ? ((TComPic*)pic)->getPOC() : -1; }
+
+int libHMDEC_get_picture_width(libHMDec_picture* pic, libHMDec_ColorComponent c)
+{
+  bool ok; ComponentID id = toComp(c, ok);
+  return (pic && ok) ? ((TComPic*)pic)->getPicYuvRec()->getWidth(id) : -1;
+}
+int libHMDEC_get_picture_height(libHMDec_picture* pic, libHMDec_ColorComponent c)
+{
+  bool ok; ComponentID id = toComp(c, ok);
+  return (pic && ok) ? ((TComPic*)pic)->getPicYuvRec()->getHeight(id) : -1;
+}
+int libHMDEC_get_picture_stride(libHMDec_picture* pic, libHMDec_ColorComponent c)
+{
+  bool ok; ComponentID id = toComp(c, ok);
+  return (pic && ok) ? ((TComPic*)pic)->getPicYuvRec()->getStride(id) : -1;
+}
+
+short* libHMDEC_get_image_plane(libHMDec_picture* pic, libHMDec_ColorComponent c)
+{
+  bool ok; ComponentID id = toComp(c, ok);
+  if (!pic || !ok) return NULL;
+  Decoder* owner = NULL;
+  {
+    std::lock_guard<std::mutex> g(g_picOwnerLock);
+    std::map<const void*, Decoder*>::iterator it = g_picOwner.find(pic);
+    if (it != g_picOwner.end()) owner = it->second;
+  }
+  if (owner) owner->sink->fetchPicture((TComPic*)pic);   // device -> HM's padded host plane, once per picture
+  return ((TComPic*)pic)->getPicYuvRec()->getAddr(id);
+}
+
+libHMDec_ChromaFormat libHMDEC_get_chroma_format(libHMDec_picture* pic)
+{
+  if (!pic) return LIBHMDEC_CHROMA_UNKNOWN;
+  switch (((TComPic*)pic)->getChromaFormat())
+  {
+    case CHROMA_400: return LIBHMDEC_CHROMA_400;
+    case CHROMA_420: return LIBHMDEC_CHROMA_420;
+    case CHROMA_422: return LIBHMDEC_CHROMA_422;
+    case CHROMA_444: return LIBHMDEC_CHROMA_444;
+    default:         return LIBHMDEC_CHROMA_UNKNOWN;
+  }
+}
+
+int libHMDEC_get_internal_bit_depth(libHMDec_ColorComponent c)
+{
+  if (c == LIBHMDEC_LUMA) return g_bitDepth[CHANNEL_TYPE_LUMA];
+  if (c == LIBHMDEC_CHROMA_U || c == LIBHMDEC_CHROMA_V) return g_bitDepth[CHANNEL_TYPE_CHROMA];
+  return -1;
+}
+
+std::vector<libHMDec_BlockValue>* libHMDEC_get_internal_info(libHMDec_context* decCtx, libHMDec_picture* pic, libHMDec_info_type type)
+{
+  Decoder* d = D(decCtx);
+  if (!d) return NULL;
+  d->internals.clear();
+  if (!pic) return NULL;
+  return hm_collect_internals(d->internals, (TComPic*)pic, type);
+}
+
+libHMDec_error libHMDEC_clear_internal_info(libHMDec_context* decCtx)
+{
+  if (!decCtx) return LIBHMDEC_ERROR;
+  D(decCtx)->internals.clear();
+  return LIBHMDEC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,128 @@
+// hmdec_cli.cpp — Annex-B harness around the libHMDec_* entry points (the loop documented in the
+// reference header, libHMDecoder.h:38-77): split the byte stream into NAL units, push them one at a
+// time, re-push when bNewPicture comes back, drain pictures when checkOutputPictures is set.
+//   hmdec_cli -b in.bin [-o out.yuv] [--dump records.hmr] [--no-hash] [--touch-planes]
+// -o writes the FULL coded picture (the wrapper API exposes no conformance window), 1 byte/sample for
+// 8-bit streams and 2 bytes little-endian otherwise.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <chrono>
+#include "libHMDecoder_api.h"
+
+static bool readFile(const char* path, std::vector<uint8_t>& out)
+{
+  FILE* f = fopen(path, "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+  out.resize(n);
+  bool ok = fread(out.data(), 1, n, f) == (size_t)n;
+  fclose(f);
+  return ok;
+}
+
+// Annex B (B.2): NAL units are delimited by 00 00 01; trailing zero bytes belong to the delimiter.
+static void splitAnnexB(const std::vector<uint8_t>& s, std::vector<std::pair<size_t, size_t> >& nals)
+{
+  size_t n = s.size(), i = 0, start = (size_t)-1;
+  while (i + 2 < n)
+  {
+    if (s[i] == 0 && s[i + 1] == 0 && s[i + 2] == 1)
+    {
+      if (start != (size_t)-1)
+      {
+        size_t end = i;
+        while (end > start && s[end - 1] == 0) end--;
+        nals.push_back(std::make_pair(start, end - start));
+      }
+      start = i + 3;
+      i += 3;
+    }
+    else i++;
+  }
+  if (start != (size_t)-1 && start < n)
+  {
+    size_t end = n;
+    while (end > start && s[end - 1] == 0) end--;
+    nals.push_back(std::make_pair(start, end - start));
+  }
+}
+
+static void writePicture(FILE* f, libHMDec_picture* pic, int bitDepth[2])
+{
+  for (int c = 0; c < 3; c++)
+  {
+    libHMDec_ColorComponent cc = (libHMDec_ColorComponent)c;
+    int w = libHMDEC_get_picture_width(pic, cc), h = libHMDEC_get_picture_height(pic, cc), s = libHMDEC_get_picture_stride(pic, cc);
+    const short* p = libHMDEC_get_image_plane(pic, cc);
+    if (!p || w <= 0) continue;
+    const bool is8 = bitDepth[c ? 1 : 0] <= 8;
+    std::vector<uint8_t> row((size_t)w * 2);
+    for (int y = 0; y < h; y++, p += s)
+    {
+      if (is8) { for (int x = 0; x < w; x++) row[x] = (uint8_t)p[x]; fwrite(row.data(), 1, w, f); }
+      else     { for (int x = 0; x < w; x++) { row[2 * x] = (uint8_t)(p[x] & 0xff); row[2 * x + 1] = (uint8_t)((p[x] >> 8) & 0xff); } fwrite(row.data(), 1, (size_t)w * 2, f); }
+    }
+  }
+}
+
+int main(int argc, char** argv)
+{
+  const char* in = NULL; const char* out = NULL; const char* dump = NULL;
+  bool hash = true, touch = false; int repeat = 1;
+  for (int i = 1; i < argc; i++)
+  {
+    if (!strcmp(argv[i], "-b") && i + 1 < argc) in = argv[++i];
+    else if (!strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
+    else if (!strcmp(argv[i], "--dump") && i + 1 < argc) dump = argv[++i];
+    else if (!strcmp(argv[i], "--no-hash")) hash = false;
+    else if (!strcmp(argv[i], "--touch-planes")) touch = true;
+    else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = atoi(argv[++i]);
+    else { fprintf(stderr, "usage: %s -b in.bin [-o out.yuv] [--dump file] [--no-hash] [--touch-planes] [--repeat N]\n", argv[0]); return 2; }
+  }
+  if (!in) { fprintf(stderr, "missing -b\n"); return 2; }
+  std::vector<uint8_t> stream;
+  if (!readFile(in, stream)) { perror(in); return 2; }
+  std::vector<std::pair<size_t, size_t> > nals;
+  splitAnnexB(stream, nals);
+
+  FILE* fo = out ? fopen(out, "wb") : NULL;
+  int pictures = 0; bool mismatch = false; const char* unsupported = NULL;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  for (int rep = 0; rep < repeat; rep++)
+  {
+    libHMDec_context* dec = dump ? libHMDecB200_new_decoder_ex(1, dump) : libHMDec_new_decoder();
+    if (!dec) { fprintf(stderr, "could not create decoder\n"); return 3; }
+    libHMDec_set_SEI_Check(dec, hash);
+    for (size_t k = 0; k < nals.size();)
+    {
+      const bool eof = (k + 1 == nals.size());
+      bool newPicture = false, checkOutput = false;
+      if (libHMDec_push_nal_unit(dec, &stream[nals[k].first], (int)nals[k].second, eof, newPicture, checkOutput) != LIBHMDEC_OK)
+      {
+        fprintf(stderr, "push_nal_unit failed at NAL %zu\n", k); return 4;
+      }
+      if (checkOutput)
+      {
+        while (libHMDec_picture* pic = libHMDec_get_picture(dec))
+        {
+          pictures++;
+          int bd[2] = { libHMDEC_get_internal_bit_depth(LIBHMDEC_LUMA), libHMDEC_get_internal_bit_depth(LIBHMDEC_CHROMA_U) };
+          if (fo) writePicture(fo, pic, bd);
+          else if (touch) for (int c = 0; c < 3; c++) (void)libHMDEC_get_image_plane(pic, (libHMDec_ColorComponent)c);
+        }
+      }
+      if (!newPicture) k++;      // otherwise the same NAL must be pushed again
+    }
+    mismatch = mismatch || libHMDecB200_hash_mismatch(dec);
+    if (libHMDecB200_unsupported(dec)) unsupported = libHMDecB200_unsupported(dec);
+    libHMDec_free_decoder(dec);
+  }
+  double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (fo) fclose(fo);
+  fprintf(stderr, "hmdec_cli: %d pictures in %.3f s (%.2f fps)%s%s%s\n", pictures, sec, pictures / sec,
+          mismatch ? "  HASH MISMATCH" : "", unsupported ? "  UNSUPPORTED: " : "", unsupported ? unsupported : "");
+  return (mismatch || unsupported) ? 1 : 0;
+}

@@ -1,0 +1,20 @@
+import os
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+STREAMS = ["c1_intra8_240p", "s_ra8_240p", "s_ra8_240p_q22", "s_ra10_240p", "s_ld10_240p", "s_ldp8_240p",
+           "s_intra10_240p_q22", "s_rext444_240p", "s_ra8_odd"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN

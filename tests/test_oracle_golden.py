@@ -1,0 +1,82 @@
+"""Pins the CPU oracle (oracle/hm_oracle.c) against the reference: for every golden stream the oracle must
+reproduce HM's picture after CU reconstruction, after deblocking and after SAO (MD5 per component, SEI
+definition), and the final MD5 must equal the one TAppDecoder printed and verified against the SEI."""
+import os
+import re
+import numpy as np
+import pytest
+from conftest import GOLDEN, STREAMS
+from libhm_b200 import records
+from oracle import oracle
+
+
+def _tappdecoder_md5(name):
+    out = {}
+    for line in open(os.path.join(GOLDEN, name + ".md5")):
+        m = re.search(r"POC\s+(-?\d+).*\[MD5:([0-9a-f]{32}),([0-9a-f]{32}),([0-9a-f]{32}),\(OK\)\]", line)
+        assert m, line
+        out[int(m.group(1))] = [bytes.fromhex(m.group(k)) for k in (2, 3, 4)]
+    return out
+
+
+@pytest.mark.parametrize("name", STREAMS)
+def test_oracle_matches_hm_all_stages(name):
+    frames = records.read_dump(os.path.join(GOLDEN, name + ".hmr.gz"))
+    ref = _tappdecoder_md5(name)
+    assert len(frames) == len(ref)
+    dec = oracle.Decoder()
+    pre = oracle.STAGE_MC | oracle.STAGE_RESID | oracle.STAGE_INTRA
+    for fr in frames:
+        bds = [fr.bit_depth(c) for c in range(3)]
+        dec.frame(fr, pre)
+        assert (records.picture_md5(dec.work.planes, bds) == fr.gold[0]).all(), f"CU recon, POC {fr.h['poc']}"
+        dec.frame(fr, pre | oracle.STAGE_DBV | oracle.STAGE_DBH)
+        assert (records.picture_md5(dec.work.planes, bds) == fr.gold[1]).all(), f"deblock, POC {fr.h['poc']}"
+        out = dec.frame(fr)
+        md5 = records.picture_md5(out.planes, bds)
+        assert (md5 == fr.gold[2]).all(), f"SAO, POC {fr.h['poc']}"
+        assert [bytes(md5[c]) for c in range(3)] == ref[int(fr.h["poc"])], "final picture vs TAppDecoder/SEI MD5"
+
+
+def test_fixtures_cover_the_tools():
+    """The golden set must actually exercise the tools the hot path implements."""
+    seen = dict(bi=0, uni=0, frac=0, dst=0, tskip=0, rdpcm=0, rotate=0, ccp=0, n32=0, sao_eo=0, sao_bo=0, bs1=0, bs2=0, strong_flag=0, planar=0, dc=0, ang=0)
+    for name in STREAMS:
+        for fr in records.read_dump(os.path.join(GOLDEN, name + ".hmr.gz")):
+            pu, tu, it = fr.pu, fr.tu, fr.intra
+            seen["bi"] += int((pu["lists"] == 3).sum()); seen["uni"] += int((pu["lists"] != 3).sum())
+            seen["frac"] += int(((pu["mv"] & 3) != 0).any(axis=(1, 2)).sum()) if len(pu) else 0
+            seen["dst"] += int(((tu["flags"] & records.TU_DST) != 0).sum())
+            seen["tskip"] += int(((tu["flags"] & records.TU_TSKIP) != 0).sum())
+            seen["rdpcm"] += int(((tu["flags"] & (records.TU_RDPCM_H | records.TU_RDPCM_V)) != 0).sum())
+            seen["rotate"] += int(((tu["flags"] & records.TU_ROTATE) != 0).sum())
+            seen["ccp"] += int((tu["ccp_alpha"] != 0).sum())
+            seen["n32"] += int((tu["log2_size"] == 5).sum())
+            for c in range(3):
+                t = fr.ctu["sao"]["type"][:, c]
+                seen["sao_eo"] += int(((t >= 1) & (t <= 4)).sum()); seen["sao_bo"] += int((t == 5).sum())
+            if fr.bs is not None:
+                seen["bs1"] += int((((fr.bs & 3) == 1) | (((fr.bs >> 2) & 3) == 1)).sum())
+                seen["bs2"] += int((((fr.bs & 3) == 2) | (((fr.bs >> 2) & 3) == 2)).sum())
+            seen["strong_flag"] += int(fr.h["flags"] & records.FRM_STRONG_INTRA_SMOOTHING != 0)
+            seen["planar"] += int((it["mode"] == 0).sum()); seen["dc"] += int((it["mode"] == 1).sum()); seen["ang"] += int((it["mode"] > 1).sum())
+    missing = [k for k, v in seen.items() if v == 0]
+    assert not missing, f"golden streams never exercise: {missing} ({seen})"
+
+
+def test_dct_matrix_values():
+    """Spot values of the generated HEVC core transform matrix (reference table: TComRom.cpp:335-484)."""
+    import ctypes as C
+    m = np.zeros((32, 32), np.int16)
+    oracle.lib().orc_get_dct_matrix(C.c_int(32), m.ctypes.data_as(C.c_void_p))
+    assert (m[0] == 64).all()
+    assert m[1].tolist() == [90, 90, 88, 85, 82, 78, 73, 67, 61, 54, 46, 38, 31, 22, 13, 4, -4, -13, -22, -31, -38, -46, -54, -61, -67, -73, -78, -82, -85, -88, -90, -90]
+    m4 = np.zeros((4, 4), np.int16)
+    oracle.lib().orc_get_dct_matrix(C.c_int(4), m4.ctypes.data_as(C.c_void_p))
+    assert m4.tolist() == [[64, 64, 64, 64], [83, 36, -36, -83], [64, -64, -64, 64], [36, -83, 83, -36]]
+    m8 = np.zeros((8, 8), np.int16)
+    oracle.lib().orc_get_dct_matrix(C.c_int(8), m8.ctypes.data_as(C.c_void_p))
+    assert m8[1].tolist() == [89, 75, 50, 18, -18, -50, -75, -89]
+    # every N-point matrix is orthogonal up to scaling: M M^T ~ 64*64*N/… on the diagonal, near zero elsewhere
+    g = m.astype(np.int64) @ m.astype(np.int64).T
+    assert (np.abs(g - np.diag(np.diag(g))) < 500).all() and (np.abs(np.diag(g) - 64 * 64 * 32) < 2000).all()
