@@ -628,6 +628,18 @@ void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdap
 
   // pad the coefficient buffer to a multiple of 16 entries
   while (m_coef.size() & 15) m_coef.push_back(0);
+  // group the residual records by transform size (stable: luma stays ahead of its co-located chroma for CCP)
+  {
+    std::vector<hmr_tu> sorted;
+    sorted.reserve(m_tu.size());
+    for (int k = 0; k < 4; k++)
+    {
+      m_hdr.tu_first[k] = (uint32_t)sorted.size();
+      for (size_t i = 0; i < m_tu.size(); i++) if (m_tu[i].log2_size == k + 2) sorted.push_back(m_tu[i]);
+    }
+    m_hdr.tu_first[4] = (uint32_t)sorted.size();
+    m_tu.swap(sorted);
+  }
   m_hdr.n_tu = (uint32_t)m_tu.size();
   m_hdr.n_coef = (uint32_t)m_coef.size();
   m_hdr.n_intra = (uint32_t)m_intra.size();

@@ -20,7 +20,7 @@ extern "C" {
 #endif
 
 #define HMR_MAGIC        0x52524d48u /* "HMRR" */
-#define HMR_VERSION      3u
+#define HMR_VERSION      4u
 #define HMR_MAX_SLOTS    16          /* DPB slots addressable by a PU record (HM grows the DPB on demand, TDecTop.cpp:180-186) */
 #define HMR_NO_OFFSET    0xffffffffu
 
@@ -58,8 +58,9 @@ typedef struct hmr_frame_hdr {
   uint32_t n_pu;             /* inter records     (hmr_pu)    */
   uint32_t n_mc_tiles;       /* total 16x16-luma tiles over all PUs == pu_tile_prefix[n_pu] */
   uint32_t n_ctu;            /* CTUs in the picture, raster order */
-  uint32_t reserved[2];
-} hmr_frame_hdr;             /* 64 bytes */
+  uint32_t tu_first[5];      /* hmr_tu records are grouped by size: [tu_first[k], tu_first[k+1]) hold log2_size == k+2 */
+  uint32_t reserved[1];
+} hmr_frame_hdr;             /* 80 bytes */
 
 /* ---- residual (dequant + inverse transform) records: TComTrQuant::invTransformNxN (TComTrQuant.cpp:1423-1548) ---- */
 enum {

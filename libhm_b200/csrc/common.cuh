@@ -1,0 +1,48 @@
+// common.cuh — device-side view of one picture's job (shared by all kernels of libhmrecon.so)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hmr_records.h"
+
+struct PlaneSet
+{
+  int16_t* p[3];
+  int      pitch[3];   // in samples
+};
+
+// Everything a kernel needs, passed by value as a __grid_constant__ kernel parameter (~1 KB).
+struct FrameParams
+{
+  hmr_frame_hdr hdr;
+  int w[3], h[3];          // component sizes in samples
+  int csx, csy;            // chroma subsampling shifts
+  int ctus_w, ctus_h;
+  int w4, h4, w8;          // BS-map / QP-map strides
+  PlaneSet work;           // picture under construction (before SAO)
+  PlaneSet out;            // DPB slot the finished picture goes to
+  PlaneSet dpb[HMR_MAX_SLOTS];
+  const hmr_tu*              tu;
+  const int16_t*             coef;
+  int16_t*                   resid;     // compact residual buffer, same offsets as coef
+  const hmr_intra*           intra;
+  const hmr_ctu_intra_range* irange;
+  const hmr_pu*              pu;
+  const uint32_t*            pu_prefix;
+  const hmr_ctu*             ctu;
+  const uint8_t*             bs;
+  const int8_t*              qp;
+  const uint8_t*             cu_flags;
+  unsigned long long*        intra_progress;  // [3][ctus_h], (epoch << 32) | CTUs finished in that row
+  unsigned long long         epoch;
+};
+
+__device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(hi, max(lo, v)); }
+
+// launchers (one per kernel file)
+void launch_mc(const FrameParams& P, cudaStream_t s);
+int  launch_resid(const FrameParams& P, cudaStream_t s);             // returns number of launches
+cudaError_t launch_intra(const FrameParams& P, cudaStream_t s);
+void launch_deblock(const FrameParams& P, int dir, cudaStream_t s);
+void launch_sao(const FrameParams& P, cudaStream_t s);
+void launch_hash(const PlaneSet& pic, const int w[3], const int h[3], const int bd[3], int type, uint32_t* d_out, uint32_t* d_scratch, cudaStream_t s);
+int  intra_max_coresident_blocks(int device);

@@ -1,0 +1,541 @@
+// engine.cu — host side of libhmrecon.so: the C ABI of include/hmrecon.h, device memory management
+// (DPB slots resident in HBM, pinned staging ring, compact residual buffer) and the per-picture kernel sequence.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "hmrecon.h"
+
+#define RING 3
+#define ALIGN_UP(v, a) (((v) + (a) - 1) / (a) * (a))
+
+struct Section { size_t off, bytes; };
+struct Layout
+{
+  Section hdr, tu, coef, intra, irange, pu, prefix, ctu, bs, qp, cuf;
+  size_t total;
+};
+
+struct hmr_resident_frame
+{
+  uint8_t* dev;
+  hmr_frame_hdr hdr;
+  Layout lay;
+  bool hasBs, hasCuf;
+};
+
+struct FrameEvents { cudaEvent_t ev[HMR_T_COUNT + 1]; bool used[HMR_T_COUNT + 1]; };
+
+struct hmr_engine
+{
+  int device;
+  cudaStream_t stream;
+  std::string err;
+  // geometry (from the first frame header)
+  bool haveGeom;
+  int fmt, w[3], h[3], pitch[3], csx, csy, log2ctu, ctusW, ctusH, bdLuma, bdChroma;
+  PlaneSet slots[HMR_MAX_SLOTS];
+  bool slotAlloc[HMR_MAX_SLOTS];
+  PlaneSet work;
+  bool workAlloc;
+  // staging ring
+  struct Stage { uint8_t* host; uint8_t* dev; size_t cap; cudaEvent_t done; bool inflight; } ring[RING];
+  int ringPos;
+  int16_t* resid; size_t residCap;
+  unsigned long long* progress; size_t progressCap;
+  unsigned long long epoch;
+  int stageMask;
+  bool timing;
+  std::vector<FrameEvents> pending, freeEvents;
+  float accMs[HMR_T_COUNT];
+  uint32_t accFrames, accLaunches;
+  uint32_t* dHash; uint32_t* dHashRows; size_t hashRowsCap;
+  void* flushBuf; size_t flushCap;
+  int coopLimit;
+};
+
+static int fail(hmr_engine* e, int code, const std::string& msg) { if (e) e->err = msg; return code; }
+#define CK(call) do { cudaError_t _r = (call); if (_r != cudaSuccess) return fail(e, HMR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); } while (0)
+
+static Layout make_layout(const hmr_frame_hdr& h, bool hasBs, bool hasCuf)
+{
+  Layout L;
+  size_t off = 0;
+  auto put = [&](Section& s, size_t bytes) { s.off = off; s.bytes = bytes; off = ALIGN_UP(off + bytes, 256); };
+  const size_t nbs = (size_t)((h.width + 3) >> 2) * ((h.height + 3) >> 2);
+  const size_t nqp = (size_t)((h.width + 7) >> 3) * ((h.height + 7) >> 3);
+  put(L.hdr, sizeof(hmr_frame_hdr));
+  put(L.tu, sizeof(hmr_tu) * h.n_tu);
+  put(L.coef, sizeof(int16_t) * h.n_coef);
+  put(L.intra, sizeof(hmr_intra) * h.n_intra);
+  put(L.irange, sizeof(hmr_ctu_intra_range) * h.n_ctu);
+  put(L.pu, sizeof(hmr_pu) * h.n_pu);
+  put(L.prefix, sizeof(uint32_t) * (h.n_pu + 1));
+  put(L.ctu, sizeof(hmr_ctu) * h.n_ctu);
+  put(L.bs, hasBs ? nbs : 0);
+  put(L.qp, nqp);
+  put(L.cuf, hasCuf ? nqp : 0);
+  L.total = off;
+  return L;
+}
+
+static void pack(uint8_t* dst, const Layout& L, const hmr_frame_desc* f)
+{
+  memcpy(dst + L.hdr.off, f->hdr, L.hdr.bytes);
+  if (L.tu.bytes)     memcpy(dst + L.tu.off, f->tu, L.tu.bytes);
+  if (L.coef.bytes)   memcpy(dst + L.coef.off, f->coef, L.coef.bytes);
+  if (L.intra.bytes)  memcpy(dst + L.intra.off, f->intra, L.intra.bytes);
+  if (L.irange.bytes) memcpy(dst + L.irange.off, f->intra_range, L.irange.bytes);
+  if (L.pu.bytes)     memcpy(dst + L.pu.off, f->pu, L.pu.bytes);
+  memcpy(dst + L.prefix.off, f->pu_tile_prefix, L.prefix.bytes);
+  if (L.ctu.bytes)    memcpy(dst + L.ctu.off, f->ctu, L.ctu.bytes);
+  if (L.bs.bytes)     memcpy(dst + L.bs.off, f->bs, L.bs.bytes);
+  if (L.qp.bytes)     memcpy(dst + L.qp.off, f->qp, L.qp.bytes);
+  if (L.cuf.bytes)    memcpy(dst + L.cuf.off, f->cu_flags, L.cuf.bytes);
+}
+
+static int validate(hmr_engine* e, const hmr_frame_desc* f)
+{
+  if (!f || !f->hdr) return fail(e, HMR_ERR_ARG, "null frame");
+  const hmr_frame_hdr& h = *f->hdr;
+  if (h.magic != HMR_MAGIC || h.version != HMR_VERSION) return fail(e, HMR_ERR_FORMAT, "bad magic/version in frame header");
+  if (h.width <= 0 || h.height <= 0 || (h.width & 7) || (h.height & 7)) return fail(e, HMR_ERR_FORMAT, "picture size must be a positive multiple of 8");
+  if (h.chroma_format < HMR_CHROMA_420 || h.chroma_format > HMR_CHROMA_444) return fail(e, HMR_ERR_FORMAT, "unsupported chroma format");
+  if (h.log2_ctu < 4 || h.log2_ctu > 6) return fail(e, HMR_ERR_FORMAT, "unsupported CTU size");
+  if (h.bit_depth_luma < 8 || h.bit_depth_luma > 12 || h.bit_depth_chroma < 8 || h.bit_depth_chroma > 12) return fail(e, HMR_ERR_FORMAT, "bit depth outside 8..12");
+  if (h.out_slot >= HMR_MAX_SLOTS) return fail(e, HMR_ERR_FORMAT, "out_slot out of range");
+  if (h.tu_first[4] != h.n_tu) return fail(e, HMR_ERR_FORMAT, "tu_first does not cover n_tu");
+  if ((h.n_tu && (!f->tu || !f->coef)) || (h.n_intra && !f->intra) || (h.n_pu && !f->pu) || !f->pu_tile_prefix || !f->ctu || !f->intra_range || !f->qp)
+    return fail(e, HMR_ERR_ARG, "missing record array");
+  if ((h.flags & HMR_FRM_DEBLOCK) && !f->bs) return fail(e, HMR_ERR_ARG, "HMR_FRM_DEBLOCK without a BS map");
+  return HMR_OK;
+}
+
+static int alloc_planes(hmr_engine* e, PlaneSet& ps)
+{
+  size_t total = 0, offs[3];
+  for (int c = 0; c < 3; c++) { offs[c] = total; total += ALIGN_UP((size_t)e->pitch[c] * e->h[c] * sizeof(int16_t), 512); }
+  uint8_t* base = nullptr;
+  CK(cudaMalloc(&base, total));
+  CK(cudaMemsetAsync(base, 0, total, e->stream));
+  for (int c = 0; c < 3; c++) { ps.p[c] = (int16_t*)(base + offs[c]); ps.pitch[c] = e->pitch[c]; }
+  return HMR_OK;
+}
+
+static void free_geometry(hmr_engine* e)
+{
+  cudaStreamSynchronize(e->stream);
+  for (int s = 0; s < HMR_MAX_SLOTS; s++) if (e->slotAlloc[s]) { cudaFree(e->slots[s].p[0]); e->slotAlloc[s] = false; }
+  if (e->workAlloc) { cudaFree(e->work.p[0]); e->workAlloc = false; }
+  e->haveGeom = false;
+}
+
+static int ensure_geometry(hmr_engine* e, const hmr_frame_hdr& h)
+{
+  const int csx = (h.chroma_format == HMR_CHROMA_420 || h.chroma_format == HMR_CHROMA_422) ? 1 : 0;
+  const int csy = h.chroma_format == HMR_CHROMA_420 ? 1 : 0;
+  e->bdLuma = h.bit_depth_luma; e->bdChroma = h.bit_depth_chroma;
+  if (e->haveGeom && (e->w[0] != h.width || e->h[0] != h.height || e->fmt != h.chroma_format || e->log2ctu != h.log2_ctu)) free_geometry(e);
+  if (!e->haveGeom)
+  {
+    e->fmt = h.chroma_format; e->csx = csx; e->csy = csy; e->log2ctu = h.log2_ctu;
+    for (int c = 0; c < 3; c++)
+    {
+      e->w[c] = c ? h.width >> csx : h.width;
+      e->h[c] = c ? h.height >> csy : h.height;
+      e->pitch[c] = (int)ALIGN_UP((size_t)e->w[c], 64);      // 128-byte rows
+    }
+    e->ctusW = (h.width + (1 << h.log2_ctu) - 1) >> h.log2_ctu;
+    e->ctusH = (h.height + (1 << h.log2_ctu) - 1) >> h.log2_ctu;
+    if (3 * e->ctusH > e->coopLimit) return fail(e, HMR_ERR_FORMAT, "picture has more CTU rows than the intra wavefront can keep co-resident");
+    const size_t need = (size_t)3 * e->ctusH;
+    if (need > e->progressCap)
+    {
+      if (e->progress) cudaFree(e->progress);
+      CK(cudaMalloc(&e->progress, need * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(e->progress, 0, need * sizeof(unsigned long long), e->stream));
+      e->progressCap = need;
+    }
+    int r = alloc_planes(e, e->work);
+    if (r) return r;
+    e->workAlloc = true;
+    e->haveGeom = true;
+  }
+  return HMR_OK;
+}
+
+static int ensure_slot(hmr_engine* e, int slot)
+{
+  if (e->slotAlloc[slot]) return HMR_OK;
+  int r = alloc_planes(e, e->slots[slot]);
+  if (r) return r;
+  e->slotAlloc[slot] = true;
+  return HMR_OK;
+}
+
+static void fill_params(hmr_engine* e, FrameParams& P, const hmr_frame_hdr& h, const Layout& L, uint8_t* dev, bool hasBs, bool hasCuf)
+{
+  memset(&P, 0, sizeof(P));
+  P.hdr = h;
+  for (int c = 0; c < 3; c++) { P.w[c] = e->w[c]; P.h[c] = e->h[c]; }
+  P.csx = e->csx; P.csy = e->csy; P.ctus_w = e->ctusW; P.ctus_h = e->ctusH;
+  P.w4 = (h.width + 3) >> 2; P.h4 = (h.height + 3) >> 2; P.w8 = (h.width + 7) >> 3;
+  P.work = e->work;
+  P.out = e->slots[h.out_slot];
+  for (int s = 0; s < HMR_MAX_SLOTS; s++) P.dpb[s] = e->slotAlloc[s] ? e->slots[s] : e->slots[h.out_slot];
+  P.tu = (const hmr_tu*)(dev + L.tu.off);
+  P.coef = (const int16_t*)(dev + L.coef.off);
+  P.resid = e->resid;
+  P.intra = (const hmr_intra*)(dev + L.intra.off);
+  P.irange = (const hmr_ctu_intra_range*)(dev + L.irange.off);
+  P.pu = (const hmr_pu*)(dev + L.pu.off);
+  P.pu_prefix = (const uint32_t*)(dev + L.prefix.off);
+  P.ctu = (const hmr_ctu*)(dev + L.ctu.off);
+  P.bs = hasBs ? dev + L.bs.off : nullptr;
+  P.qp = (const int8_t*)(dev + L.qp.off);
+  P.cu_flags = hasCuf ? dev + L.cuf.off : nullptr;
+  P.intra_progress = e->progress;
+  P.epoch = e->epoch;
+}
+
+static int fold_timing(hmr_engine* e)
+{
+  if (e->pending.empty()) return HMR_OK;
+  CK(cudaStreamSynchronize(e->stream));
+  for (size_t i = 0; i < e->pending.size(); i++)
+  {
+    FrameEvents& fe = e->pending[i];
+    for (int k = 0; k < HMR_T_COUNT; k++)
+      if (fe.used[k] && fe.used[k + 1])
+      {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, fe.ev[k], fe.ev[k + 1]) == cudaSuccess) e->accMs[k] += ms;
+      }
+    e->freeEvents.push_back(fe);
+  }
+  e->pending.clear();
+  return HMR_OK;
+}
+
+// The per-picture kernel sequence.  `uploaded` = an H2D copy was enqueued just before (timing slot HMR_T_H2D).
+static int run_frame(hmr_engine* e, FrameParams& P, FrameEvents* fe)
+{
+  const hmr_frame_hdr& h = P.hdr;
+  if (h.n_coef > e->residCap)
+  {
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->resid) cudaFree(e->resid);
+    e->residCap = ALIGN_UP((size_t)h.n_coef * 3 / 2 + 4096, 4096);
+    CK(cudaMalloc(&e->resid, e->residCap * sizeof(int16_t)));
+    P.resid = e->resid;
+  }
+  auto mark = [&](int k) { if (fe) { cudaEventRecord(fe->ev[k], e->stream); fe->used[k] = true; } };
+  const int m = e->stageMask;
+  uint32_t launches = 0;
+  mark(HMR_T_MC);
+  if ((m & HMR_STAGE_MC) && h.n_mc_tiles) { launch_mc(P, e->stream); launches++; }
+  mark(HMR_T_RESID);
+  if ((m & HMR_STAGE_RESID) && h.n_tu) launches += launch_resid(P, e->stream);
+  mark(HMR_T_INTRA);
+  if ((m & HMR_STAGE_INTRA) && h.n_intra) { CK(launch_intra(P, e->stream)); launches++; }
+  mark(HMR_T_DEBLOCK_V);
+  if ((m & HMR_STAGE_DEBLOCK_V) && (h.flags & HMR_FRM_DEBLOCK)) { launch_deblock(P, 0, e->stream); launches++; }
+  mark(HMR_T_DEBLOCK_H);
+  if ((m & HMR_STAGE_DEBLOCK_H) && (h.flags & HMR_FRM_DEBLOCK)) { launch_deblock(P, 1, e->stream); launches++; }
+  mark(HMR_T_SAO);
+  if (m & HMR_STAGE_SAO) { launch_sao(P, e->stream); launches++; }
+  mark(HMR_T_COUNT);
+  CK(cudaGetLastError());
+  e->epoch++;
+  e->accFrames++;
+  e->accLaunches += launches;
+  return HMR_OK;
+}
+
+static FrameEvents* grab_events(hmr_engine* e)
+{
+  if (!e->timing) return nullptr;
+  if (e->pending.size() >= 512) fold_timing(e);
+  FrameEvents fe;
+  if (!e->freeEvents.empty()) { fe = e->freeEvents.back(); e->freeEvents.pop_back(); }
+  else for (int k = 0; k <= HMR_T_COUNT; k++) cudaEventCreate(&fe.ev[k]);
+  for (int k = 0; k <= HMR_T_COUNT; k++) fe.used[k] = false;
+  e->pending.push_back(fe);
+  return &e->pending.back();
+}
+
+extern "C" {
+
+const char* hmr_version(void) { return "hmrecon-b200 0.1 (records v4)"; }
+
+int hmr_engine_create(hmr_engine** out, int device)
+{
+  if (!out) return HMR_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
+  {
+    fprintf(stderr, "hmrecon: no usable CUDA device %d (count %d): %s\n", device, n, cudaGetErrorString(cudaGetLastError()));
+    return HMR_ERR_CUDA;
+  }
+  hmr_engine* e = new hmr_engine();
+  e->device = device;
+  e->haveGeom = false; e->workAlloc = false;
+  memset(e->slotAlloc, 0, sizeof(e->slotAlloc));
+  memset(e->ring, 0, sizeof(e->ring));
+  e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
+  e->stageMask = HMR_STAGE_ALL; e->timing = false;
+  memset(e->accMs, 0, sizeof(e->accMs)); e->accFrames = e->accLaunches = 0;
+  e->dHash = nullptr; e->dHashRows = nullptr; e->hashRowsCap = 0; e->flushBuf = nullptr; e->flushCap = 0;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+  {
+    fprintf(stderr, "hmrecon: cannot initialise device %d: %s\n", device, cudaGetErrorString(cudaGetLastError()));
+    delete e;
+    return HMR_ERR_CUDA;
+  }
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  e->coopLimit = coop ? intra_max_coresident_blocks(device) : 0;
+  for (int i = 0; i < RING; i++) cudaEventCreateWithFlags(&e->ring[i].done, cudaEventDisableTiming);
+  *out = e;
+  return HMR_OK;
+}
+
+void hmr_engine_destroy(hmr_engine* e)
+{
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  free_geometry(e);
+  for (int i = 0; i < RING; i++)
+  {
+    if (e->ring[i].host) cudaFreeHost(e->ring[i].host);
+    if (e->ring[i].dev) cudaFree(e->ring[i].dev);
+    cudaEventDestroy(e->ring[i].done);
+  }
+  if (e->resid) cudaFree(e->resid);
+  if (e->progress) cudaFree(e->progress);
+  if (e->dHash) cudaFree(e->dHash);
+  if (e->dHashRows) cudaFree(e->dHashRows);
+  if (e->flushBuf) cudaFree(e->flushBuf);
+  fold_timing(e);
+  for (size_t i = 0; i < e->freeEvents.size(); i++) for (int k = 0; k <= HMR_T_COUNT; k++) cudaEventDestroy(e->freeEvents[i].ev[k]);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* hmr_error_string(const hmr_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int hmr_submit_frame(hmr_engine* e, const hmr_frame_desc* f)
+{
+  if (!e) return HMR_ERR_ARG;
+  int r = validate(e, f);
+  if (r) return r;
+  CK(cudaSetDevice(e->device));
+  const hmr_frame_hdr& h = *f->hdr;
+  if ((r = ensure_geometry(e, h))) return r;
+  if ((r = ensure_slot(e, h.out_slot))) return r;
+  const bool hasBs = f->bs != nullptr, hasCuf = f->cu_flags != nullptr;
+  const Layout L = make_layout(h, hasBs, hasCuf);
+
+  hmr_engine::Stage& st = e->ring[e->ringPos];
+  e->ringPos = (e->ringPos + 1) % RING;
+  if (st.inflight) { CK(cudaEventSynchronize(st.done)); st.inflight = false; }
+  if (L.total > st.cap)
+  {
+    if (st.host) cudaFreeHost(st.host);
+    if (st.dev) cudaFree(st.dev);
+    st.cap = ALIGN_UP(L.total * 3 / 2, 1 << 20);
+    CK(cudaMallocHost(&st.host, st.cap));
+    CK(cudaMalloc(&st.dev, st.cap));
+  }
+  pack(st.host, L, f);
+  FrameEvents* fe = grab_events(e);
+  if (fe) { cudaEventRecord(fe->ev[HMR_T_H2D], e->stream); fe->used[HMR_T_H2D] = true; }
+  CK(cudaMemcpyAsync(st.dev, st.host, L.total, cudaMemcpyHostToDevice, e->stream));
+  FrameParams P;
+  fill_params(e, P, h, L, st.dev, hasBs, hasCuf);
+  r = run_frame(e, P, fe);
+  CK(cudaEventRecord(st.done, e->stream));
+  st.inflight = true;
+  return r;
+}
+
+int hmr_sync(hmr_engine* e)
+{
+  if (!e) return HMR_ERR_ARG;
+  CK(cudaStreamSynchronize(e->stream));
+  return HMR_OK;
+}
+
+static int read_planeset(hmr_engine* e, const PlaneSet& ps, int comp, int16_t* dst, size_t dstStride, bool async)
+{
+  if (!e->haveGeom || comp < 0 || comp > 2 || !dst) return fail(e, HMR_ERR_ARG, "read_plane: bad argument");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpy2DAsync(dst, dstStride * sizeof(int16_t), ps.p[comp], (size_t)ps.pitch[comp] * sizeof(int16_t),
+                       (size_t)e->w[comp] * sizeof(int16_t), e->h[comp], cudaMemcpyDeviceToHost, e->stream));
+  if (!async) CK(cudaStreamSynchronize(e->stream));
+  return HMR_OK;
+}
+
+int hmr_read_plane(hmr_engine* e, int slot, int comp, int16_t* dst, size_t dst_stride)
+{
+  if (!e || slot < 0 || slot >= HMR_MAX_SLOTS || !e->slotAlloc[slot]) return fail(e, HMR_ERR_ARG, "read_plane: slot not allocated");
+  return read_planeset(e, e->slots[slot], comp, dst, dst_stride, false);
+}
+int hmr_read_plane_async(hmr_engine* e, int slot, int comp, int16_t* dst, size_t dst_stride)
+{
+  if (!e || slot < 0 || slot >= HMR_MAX_SLOTS || !e->slotAlloc[slot]) return fail(e, HMR_ERR_ARG, "read_plane: slot not allocated");
+  return read_planeset(e, e->slots[slot], comp, dst, dst_stride, true);
+}
+int hmr_read_work_plane(hmr_engine* e, int comp, int16_t* dst, size_t dst_stride)
+{
+  if (!e || !e->workAlloc) return fail(e, HMR_ERR_ARG, "read_work_plane: no picture yet");
+  return read_planeset(e, e->work, comp, dst, dst_stride, false);
+}
+
+int hmr_write_plane(hmr_engine* e, int slot, int comp, const int16_t* src, size_t src_stride, int width, int height)
+{
+  if (!e || slot < 0 || slot >= HMR_MAX_SLOTS || comp < 0 || comp > 2 || !src) return fail(e, HMR_ERR_ARG, "write_plane: bad argument");
+  if (!e->haveGeom || width != e->w[comp] || height != e->h[comp]) return fail(e, HMR_ERR_ARG, "write_plane: geometry mismatch (submit a frame first)");
+  CK(cudaSetDevice(e->device));
+  int r = ensure_slot(e, slot);
+  if (r) return r;
+  CK(cudaMemcpy2DAsync(e->slots[slot].p[comp], (size_t)e->pitch[comp] * sizeof(int16_t), src, src_stride * sizeof(int16_t),
+                       (size_t)width * sizeof(int16_t), height, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return HMR_OK;
+}
+
+// GF(2) polynomial arithmetic modulo the CRC-16/CCITT polynomial x^16 + x^12 + x^5 + 1
+static uint32_t gf_mul(uint32_t a, uint32_t b)
+{
+  uint32_t r = 0;
+  for (int i = 15; i >= 0; i--)
+  {
+    r = ((r << 1) & 0xffff) ^ (((r >> 15) & 1) * 0x1021);
+    if ((b >> i) & 1) r ^= a;
+  }
+  return r;
+}
+static uint32_t gf_xpow(uint64_t n)
+{
+  uint32_t result = 1, base = 2;     // base = x
+  while (n) { if (n & 1) result = gf_mul(result, base); base = gf_mul(base, base); n >>= 1; }
+  return result;
+}
+
+int hmr_picture_hash(hmr_engine* e, int slot, int type, uint32_t out[3])
+{
+  if (!e || !out || slot < 0 || slot >= HMR_MAX_SLOTS || !e->slotAlloc[slot] || (type != 2 && type != 3)) return fail(e, HMR_ERR_ARG, "picture_hash: bad argument");
+  CK(cudaSetDevice(e->device));
+  if (!e->dHash) CK(cudaMalloc(&e->dHash, 3 * sizeof(uint32_t)));
+  const size_t rows = (size_t)e->h[0] + e->h[1] + e->h[2];
+  if (rows > e->hashRowsCap)
+  {
+    if (e->dHashRows) cudaFree(e->dHashRows);
+    CK(cudaMalloc(&e->dHashRows, rows * sizeof(uint32_t)));
+    e->hashRowsCap = rows;
+  }
+  const int bd[3] = { e->bdLuma, e->bdChroma, e->bdChroma };   // all pictures of a stream share the SPS bit depths
+  launch_hash(e->slots[slot], e->w, e->h, bd, type, e->dHash, e->dHashRows, e->stream);
+  CK(cudaGetLastError());
+  if (type == 3)
+  {
+    CK(cudaMemcpyAsync(out, e->dHash, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return HMR_OK;
+  }
+  std::vector<uint32_t> rc(rows);
+  CK(cudaMemcpyAsync(rc.data(), e->dHashRows, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  size_t base = 0;
+  for (int c = 0; c < 3; c++)
+  {
+    const uint64_t rowBits = (uint64_t)e->w[c] * (bd[c] > 8 ? 16 : 8);
+    const uint32_t shiftRow = gf_xpow(rowBits);
+    uint32_t crc = 0xffff;
+    for (int y = 0; y < e->h[c]; y++) crc = gf_mul(crc, shiftRow) ^ rc[base + y];
+    crc = gf_mul(crc, gf_xpow(16));
+    out[c] = crc;
+    base += e->h[c];
+  }
+  return HMR_OK;
+}
+
+int hmr_set_stage_mask(hmr_engine* e, int mask) { if (!e) return HMR_ERR_ARG; e->stageMask = mask; return HMR_OK; }
+int hmr_enable_timing(hmr_engine* e, int on) { if (!e) return HMR_ERR_ARG; if (!on) fold_timing(e); e->timing = on != 0; return HMR_OK; }
+
+int hmr_get_stage_times(hmr_engine* e, float ms[HMR_T_COUNT], uint32_t* n_frames, uint32_t* n_launches)
+{
+  if (!e) return HMR_ERR_ARG;
+  int r = fold_timing(e);
+  if (r) return r;
+  if (ms) memcpy(ms, e->accMs, sizeof(e->accMs));
+  if (n_frames) *n_frames = e->accFrames;
+  if (n_launches) *n_launches = e->accLaunches;
+  memset(e->accMs, 0, sizeof(e->accMs));
+  e->accFrames = e->accLaunches = 0;
+  return HMR_OK;
+}
+
+int hmr_upload_frame(hmr_engine* e, const hmr_frame_desc* f, hmr_resident_frame** out)
+{
+  if (!e || !out) return HMR_ERR_ARG;
+  int r = validate(e, f);
+  if (r) return r;
+  CK(cudaSetDevice(e->device));
+  if ((r = ensure_geometry(e, *f->hdr))) return r;
+  hmr_resident_frame* rf = new hmr_resident_frame();
+  rf->hdr = *f->hdr;
+  rf->hasBs = f->bs != nullptr; rf->hasCuf = f->cu_flags != nullptr;
+  rf->lay = make_layout(rf->hdr, rf->hasBs, rf->hasCuf);
+  std::vector<uint8_t> tmp(rf->lay.total);
+  pack(tmp.data(), rf->lay, f);
+  cudaError_t ce = cudaMalloc(&rf->dev, rf->lay.total);
+  if (ce != cudaSuccess) { delete rf; return fail(e, HMR_ERR_NOMEM, cudaGetErrorString(ce)); }
+  CK(cudaMemcpy(rf->dev, tmp.data(), rf->lay.total, cudaMemcpyHostToDevice));
+  *out = rf;
+  return HMR_OK;
+}
+
+int hmr_run_resident(hmr_engine* e, const hmr_resident_frame* f)
+{
+  if (!e || !f) return HMR_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  int r = ensure_geometry(e, f->hdr);
+  if (r) return r;
+  if ((r = ensure_slot(e, f->hdr.out_slot))) return r;
+  FrameParams P;
+  fill_params(e, P, f->hdr, f->lay, f->dev, f->hasBs, f->hasCuf);
+  return run_frame(e, P, grab_events(e));
+}
+
+void hmr_free_resident(hmr_engine* e, hmr_resident_frame* f)
+{
+  if (!f) return;
+  if (e) { cudaSetDevice(e->device); cudaStreamSynchronize(e->stream); }
+  cudaFree(f->dev);
+  delete f;
+}
+
+void* hmr_alloc_pinned(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }
+void  hmr_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int hmr_flush_l2(hmr_engine* e, size_t bytes)
+{
+  if (!e) return HMR_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  if (bytes > e->flushCap)
+  {
+    if (e->flushBuf) cudaFree(e->flushBuf);
+    CK(cudaMalloc(&e->flushBuf, bytes));
+    e->flushCap = bytes;
+  }
+  CK(cudaMemsetAsync(e->flushBuf, 0x5a, bytes, e->stream));
+  return HMR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,216 @@
+// k_resid.cu — batched dequantisation + inverse transform over all TUs of a picture, fused with the
+// reconstruction add for inter TUs.
+//
+// Replaces TComTrQuant::invTransformNxN (TComTrQuant.cpp:1423-1548): xDeQuant flat path (:1203-1313),
+// xIT -> xITrMxN -> partialButterflyInverse4/8/16/32 + fastInverseDst (:437-491,539-573,638-685,765-828,894-948),
+// xITransformSkip (:1920-1959), transquant-bypass copy (:1475-1487), invRdpcmNxN (:1737-1792),
+// crossComponentPrediction (:3294-3335), and TComYuv::addClip (TComYuv.cpp:264-299) for inter CUs.
+//
+// One launch per transform size (the host groups the TU records by size).  A group of N threads owns one NxN TU:
+// stage 1: thread j transforms coefficient column j (dequantising on load, skipping zero levels);
+// stage 2: thread y transforms row y of the transposed intermediate.  The two stages exchange the N x N
+// intermediate through shared memory (pitch N+2 -> conflict-free both ways).  Integer MACs in registers; the
+// HEVC matrices live in __constant__ memory and are always addressed uniformly across a warp.
+#include "common.cuh"
+
+#define RS_THREADS 128
+
+__constant__ int16_t c_T32[32][32];
+static const int16_t h_cosTab[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                                      61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
+__constant__ int16_t c_dst4[4][4] = { {29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29} };
+__constant__ int c_invq[6] = { 40, 45, 51, 57, 64, 72 };
+static bool g_resid_tables_uploaded[64] = {false};
+
+// HEVC core transform matrix (TComRom.cpp:335-484): entry (k, n) = +-cos-table[(2n+1)k folded to the first quadrant]
+static void upload_tables(int device)
+{
+  if (device < 64 && g_resid_tables_uploaded[device]) return;
+  static int16_t T[32][32];
+  for (int k = 0; k < 32; k++)
+    for (int n = 0; n < 32; n++)
+    {
+      if (k == 0) { T[k][n] = 64; continue; }
+      int m = ((2 * n + 1) * k) & 127;
+      if (m > 64) m = 128 - m;
+      T[k][n] = (int16_t)(m > 32 ? -h_cosTab[64 - m] : h_cosTab[m]);
+    }
+  cudaMemcpyToSymbol(c_T32, T, sizeof(T));
+  if (device < 64) g_resid_tables_uploaded[device] = true;
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(RS_THREADS) resid_kernel(const __grid_constant__ FrameParams P, const uint32_t first, const uint32_t count, const int phase)
+{
+  constexpr int N = 1 << LOG2N, NN = N * N, LD = N + 2, PER_BLOCK = RS_THREADS / N, STEP = 32 / N;
+  __shared__ int16_t s_buf[PER_BLOCK][N * LD];
+  const int g = threadIdx.x / N;          // TU slot inside the CTA
+  const int j = threadIdx.x % N;          // my column (stage 1) / row (stage 2) / column again (store)
+  const uint32_t idx = blockIdx.x * PER_BLOCK + g;
+  bool active = idx < count;
+  hmr_tu t;
+  if (active)
+  {
+    t = P.tu[first + idx];
+    // phase 0: everything that does not need a luma residual; phase 1: chroma TUs with cross-component prediction
+    if (phase >= 0 && ((t.ccp_alpha != 0) != (phase == 1))) active = false;
+  }
+  int16_t* sb = s_buf[g];
+  const int bd = active ? (t.comp ? P.hdr.bit_depth_chroma : P.hdr.bit_depth_luma) : 8;
+  const int16_t* __restrict__ lev = active ? P.coef + t.coef_off : nullptr;
+  const bool coded = active && (t.flags & HMR_TU_CODED);
+  const bool plainTransform = coded && !(t.flags & (HMR_TU_BYPASS | HMR_TU_TSKIP));
+
+  int acc[N];
+  // ---------------- stage 1 (or the non-transform paths, written straight into residual layout [y][x]) ----------------
+  if (plainTransform)
+  {
+    const int per = t.qp / 6, rem = t.qp - per * 6, scale = c_invq[rem];
+    const int rshift = 6 - ((15 - bd - LOG2N) + per);
+    const int inBits = min(16, 32 + rshift - 7);
+    const int inMin = -(1 << (inBits - 1)), inMax = (1 << (inBits - 1)) - 1;
+    const bool dst = (LOG2N == 2) && (t.flags & HMR_TU_DST);
+#pragma unroll
+    for (int k = 0; k < N; k++) acc[k] = 0;
+    for (int n = 0; n < N; n++)
+    {
+      const int q = lev[n * N + j];
+      if (q == 0) continue;
+      const int qc = clip3i(inMin, inMax, q);
+      int c = rshift > 0 ? (qc * scale + (1 << (rshift - 1))) >> rshift : (int)((unsigned)(qc * scale) << (-rshift));
+      c = clip3i(-32768, 32767, c);
+#pragma unroll
+      for (int k = 0; k < N; k++)
+      {
+        const int m = (LOG2N == 2 && dst) ? c_dst4[n][k] : c_T32[n * STEP][k];
+        acc[k] += m * c;
+      }
+    }
+    // tmp[j][k] = clip16((acc + 64) >> 7)
+#pragma unroll
+    for (int k = 0; k < N; k++) sb[j * LD + k] = (int16_t)clip3i(-32768, 32767, (acc[k] + 64) >> 7);
+  }
+  __syncthreads();
+  if (plainTransform)
+  {
+    const bool dst = (LOG2N == 2) && (t.flags & HMR_TU_DST);
+    const int shift2 = 20 - bd, rnd2 = 1 << (shift2 - 1);
+#pragma unroll
+    for (int k = 0; k < N; k++) acc[k] = 0;
+    for (int n = 0; n < N; n++)
+    {
+      const int c = sb[n * LD + j];          // tmp[n][y = j]
+      if (c == 0) continue;
+#pragma unroll
+      for (int k = 0; k < N; k++)
+      {
+        const int m = (LOG2N == 2 && dst) ? c_dst4[n][k] : c_T32[n * STEP][k];
+        acc[k] += m * c;
+      }
+    }
+  }
+  __syncthreads();                           // everybody has read the intermediate; the tile now becomes resi[y][x]
+  if (plainTransform)
+  {
+    const int shift2 = 20 - bd, rnd2 = 1 << (shift2 - 1);
+#pragma unroll
+    for (int k = 0; k < N; k++) sb[j * LD + k] = (int16_t)clip3i(-32768, 32767, (acc[k] + rnd2) >> shift2);   // row y = j
+  }
+  else if (active)
+  {
+    // thread j fills column j of resi[y][x]
+    if (!coded) { for (int y = 0; y < N; y++) sb[y * LD + j] = 0; }
+    else if (t.flags & HMR_TU_BYPASS)
+    {
+      for (int y = 0; y < N; y++)
+      {
+        const int i = y * N + j;
+        sb[y * LD + j] = lev[(t.flags & HMR_TU_ROTATE) ? NN - 1 - i : i];
+      }
+    }
+    else   // transform skip: dequantise, then (c + rnd) >> tsShift
+    {
+      const int per = t.qp / 6, rem = t.qp - per * 6, scale = c_invq[rem];
+      const int trShift = 15 - bd - LOG2N;
+      const int rshift = 6 - (trShift + per);
+      const int inBits = min(16, 32 + rshift - 7);
+      const int inMin = -(1 << (inBits - 1)), inMax = (1 << (inBits - 1)) - 1;
+      for (int y = 0; y < N; y++)
+      {
+        const int i = y * N + j;
+        const int qc = clip3i(inMin, inMax, (int)lev[(t.flags & HMR_TU_ROTATE) ? NN - 1 - i : i]);
+        int c = rshift > 0 ? (qc * scale + (1 << (rshift - 1))) >> rshift : (int)((unsigned)(qc * scale) << (-rshift));
+        c = clip3i(-32768, 32767, c);
+        const int r = trShift >= 0 ? (c + (trShift == 0 ? 0 : (1 << (trShift - 1)))) >> trShift : c << (-trShift);
+        sb[y * LD + j] = (int16_t)r;
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- RDPCM: running sums down columns / along rows, Pel (int16) wrap-around ----------------
+  if (active && (t.flags & HMR_TU_RDPCM_V))
+    for (int y = 1; y < N; y++) sb[y * LD + j] = (int16_t)(sb[y * LD + j] + sb[(y - 1) * LD + j]);
+  if (active && (t.flags & HMR_TU_RDPCM_H))
+    for (int x = 1; x < N; x++) sb[j * LD + x] = (int16_t)(sb[j * LD + x] + sb[j * LD + x - 1]);
+  __syncthreads();
+  if (!active) return;
+  // ---------------- cross-component prediction, store / reconstruct: thread j owns column j ----------------
+  const bool ccp = t.ccp_alpha != 0 && t.luma_off != HMR_NO_OFFSET;
+  const int diffBd = P.hdr.bit_depth_luma - P.hdr.bit_depth_chroma;
+  const bool keep = (t.flags & HMR_TU_INTRA) || (t.comp == 0 && (P.hdr.flags & HMR_FRM_HAS_CCP));
+  const bool add = !(t.flags & HMR_TU_INTRA);
+  const int maxv = (1 << bd) - 1;
+  int16_t* plane = P.work.p[t.comp];
+  const int pitch = P.work.pitch[t.comp];
+  for (int y = 0; y < N; y++)
+  {
+    int r = sb[y * LD + j];
+    if (ccp)
+    {
+      const int l = P.resid[t.luma_off + y * N + j];
+      const int ls = diffBd >= 0 ? (l >> diffBd) : (l << (-diffBd));
+      r = (int16_t)(r + ((t.ccp_alpha * ls) >> 3));
+    }
+    if (keep) P.resid[t.coef_off + y * N + j] = (int16_t)r;
+    if (add)
+    {
+      int16_t* d = plane + (size_t)(t.y + y) * pitch + t.x + j;
+      *d = (int16_t)clip3i(0, maxv, *d + r);
+    }
+  }
+}
+
+template <int LOG2N>
+static int launch_size(const FrameParams& P, cudaStream_t s)
+{
+  const uint32_t first = P.hdr.tu_first[LOG2N - 2], count = P.hdr.tu_first[LOG2N - 1] - first;
+  if (!count) return 0;
+  constexpr int PER_BLOCK = RS_THREADS >> LOG2N;
+  const uint32_t blocks = (count + PER_BLOCK - 1) / PER_BLOCK;
+  if (P.hdr.flags & HMR_FRM_HAS_CCP)
+  {
+    resid_kernel<LOG2N><<<blocks, RS_THREADS, 0, s>>>(P, first, count, 0);
+    resid_kernel<LOG2N><<<blocks, RS_THREADS, 0, s>>>(P, first, count, 1);
+    return 2;
+  }
+  resid_kernel<LOG2N><<<blocks, RS_THREADS, 0, s>>>(P, first, count, -1);
+  return 1;
+}
+
+int launch_resid(const FrameParams& P, cudaStream_t s)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  upload_tables(dev);
+  int n = 0;
+  if (P.hdr.flags & HMR_FRM_HAS_CCP)
+  {
+    // all luma (and non-CCP chroma) TUs of every size first, then the chroma TUs that read luma residuals
+    // (co-located TUs have the same size in 4:4:4, but ordering across sizes keeps the rule simple)
+  }
+  n += launch_size<2>(P, s);
+  n += launch_size<3>(P, s);
+  n += launch_size<4>(P, s);
+  n += launch_size<5>(P, s);
+  return n;
+}

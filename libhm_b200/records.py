@@ -8,7 +8,7 @@ import struct
 import numpy as np
 
 HMR_MAGIC = 0x52524D48
-HMR_VERSION = 3
+HMR_VERSION = 4
 HMR_NO_OFFSET = 0xFFFFFFFF
 
 FRM_STRONG_INTRA_SMOOTHING, FRM_DEBLOCK, FRM_SAO, FRM_HAS_NOFILTER, FRM_HAS_CCP, FRM_IS_REFERENCE, FRM_INTRA_ONLY = (1 << i for i in range(7))
@@ -18,7 +18,7 @@ HDR_DT = np.dtype([("magic", "<u4"), ("version", "<u4"), ("width", "<i4"), ("hei
                    ("chroma_format", "u1"), ("bit_depth_luma", "u1"), ("bit_depth_chroma", "u1"), ("log2_ctu", "u1"),
                    ("out_slot", "u1"), ("slice_type", "u1"), ("pps_cb_qp_offset", "i1"), ("pps_cr_qp_offset", "i1"),
                    ("flags", "<u4"), ("n_tu", "<u4"), ("n_coef", "<u4"), ("n_intra", "<u4"), ("n_pu", "<u4"),
-                   ("n_mc_tiles", "<u4"), ("n_ctu", "<u4"), ("reserved", "<u4", (2,))])
+                   ("n_mc_tiles", "<u4"), ("n_ctu", "<u4"), ("tu_first", "<u4", (5,)), ("reserved", "<u4", (1,))])
 TU_DT = np.dtype([("x", "<u2"), ("y", "<u2"), ("comp", "u1"), ("log2_size", "u1"), ("flags", "u1"), ("qp", "u1"),
                   ("ccp_alpha", "i1"), ("pad", "u1", (3,)), ("coef_off", "<u4"), ("luma_off", "<u4")])
 INTRA_DT = np.dtype([("x", "<u2"), ("y", "<u2"), ("comp", "u1"), ("log2_size", "u1"), ("mode", "u1"), ("flags", "u1"),
@@ -28,7 +28,7 @@ IRNG_DT = np.dtype([("first", "<u4", (3,)), ("count", "<u4", (3,))])
 PU_DT = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("lists", "u1"), ("slots", "u1"), ("mv", "<i2", (2, 2))])
 SAO_DT = np.dtype([("type", "u1"), ("band", "u1"), ("off", "<i2", (4,))])
 CTU_DT = np.dtype([("sao", SAO_DT, (3,)), ("avail", "u1"), ("beta_offset_div2", "i1"), ("tc_offset_div2", "i1"), ("pad", "u1", (3,))])
-assert (HDR_DT.itemsize, TU_DT.itemsize, INTRA_DT.itemsize, IRNG_DT.itemsize, PU_DT.itemsize, SAO_DT.itemsize, CTU_DT.itemsize) == (64, 20, 16, 24, 16, 10, 36)
+assert (HDR_DT.itemsize, TU_DT.itemsize, INTRA_DT.itemsize, IRNG_DT.itemsize, PU_DT.itemsize, SAO_DT.itemsize, CTU_DT.itemsize) == (80, 20, 16, 24, 16, 10, 36)
 
 
 class FrameDesc(C.Structure):

@@ -11,7 +11,8 @@ _SO = os.path.join(_HERE, "_build", "libhm_oracle.so")
 
 def build(force=False):
     src = os.path.join(_HERE, "hm_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    hdr = os.path.join(_HERE, "..", "include", "hmr_records.h")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=gnu99", "-I", os.path.join(_HERE, "..", "include"), src, "-o", _SO])
     return _SO
