@@ -30,6 +30,8 @@ struct HmFrameSink
   virtual bool wantHmRecon() const = 0;
   // wantHmRecon() only: HM's CPU planes after stage 0 = CU reconstruction, 1 = deblocking, 2 = SAO (final).
   virtual void hmStage(int stage, TComPic* pic) { (void)stage; (void)pic; }
+  // SEI hash methods that parallelise (2 = CRC, 3 = checksum) computed where the picture lives; false = not available.
+  virtual bool deviceHash(TComPic* pic, int method, uint32_t out[3]) { (void)pic; (void)method; (void)out; return false; }
 };
 
 class HmEmitter

@@ -61,14 +61,28 @@ static void printStatusAndHash(TComPic* pic, TComSlice* slice, Int hashEnabled, 
     TComDigest digest; Int numChar = 0; const Char* type = "\0";
     if (hash)
     {
-      e->sink()->fetchPicture(pic);      // D2H of the reconstructed planes into HM's TComPicYuv
-      TComPicYuv& rec = *pic->getPicYuvRec();
-      switch (hash->method)
+      uint32_t dv[3];
+      const int method = hash->method == SEIDecodedPictureHash::CRC ? 2 : (hash->method == SEIDecodedPictureHash::CHECKSUM ? 3 : 1);
+      if (method != 1 && e->sink()->deviceHash(pic, method, dv))
       {
-        case SEIDecodedPictureHash::MD5:      type = "MD5";      numChar = calcMD5(rec, digest); break;
-        case SEIDecodedPictureHash::CRC:      type = "CRC";      numChar = calcCRC(rec, digest); break;
-        case SEIDecodedPictureHash::CHECKSUM: type = "Checksum"; numChar = calcChecksum(rec, digest); break;
-        default: break;
+        // CRC / checksum are computed on the device (no plane transfer); digest bytes are big-endian (TComPicYuvMD5.cpp:120-121,157-160)
+        type = method == 2 ? "CRC" : "Checksum";
+        numChar = method == 2 ? 2 : 4;
+        digest.hash.clear();
+        for (int c = 0; c < pic->getNumberValidComponents(); c++)
+          for (int b = numChar - 1; b >= 0; b--) digest.hash.push_back((UChar)((dv[c] >> (8 * b)) & 0xff));
+      }
+      else
+      {
+        e->sink()->fetchPicture(pic);      // D2H of the reconstructed planes into HM's TComPicYuv
+        TComPicYuv& rec = *pic->getPicYuvRec();
+        switch (hash->method)
+        {
+          case SEIDecodedPictureHash::MD5:      type = "MD5";      numChar = calcMD5(rec, digest); break;
+          case SEIDecodedPictureHash::CRC:      type = "CRC";      numChar = calcCRC(rec, digest); break;
+          case SEIDecodedPictureHash::CHECKSUM: type = "Checksum"; numChar = calcChecksum(rec, digest); break;
+          default: break;
+        }
       }
     }
     const Char* ok = "(unk)"; Bool mismatch = false;

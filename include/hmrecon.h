@@ -76,6 +76,14 @@ int  hmr_get_stage_times(hmr_engine* e, float ms[HMR_T_COUNT], uint32_t* n_frame
 int  hmr_upload_frame(hmr_engine* e, const hmr_frame_desc* frame, hmr_resident_frame** out);
 int  hmr_run_resident(hmr_engine* e, const hmr_resident_frame* f);
 void hmr_free_resident(hmr_engine* e, hmr_resident_frame* f);
+/* Enqueue n resident pictures in order (one call instead of n: keeps the host out of the measured loop). */
+int  hmr_run_resident_list(hmr_engine* e, hmr_resident_frame* const* frames, int n);
+/* Device-side stopwatch over several engines (= several CUDA streams) of one GPU, CUDA events only:
+ * begin records the start event on `master`'s stream; join makes `master` wait for everything queued so far on
+ * `other`; end records the stop event on `master`, synchronises and returns the elapsed milliseconds. */
+int  hmr_timer_begin(hmr_engine* master);
+int  hmr_timer_join(hmr_engine* master, hmr_engine* other);
+int  hmr_timer_end(hmr_engine* master, float* ms);
 /* Allocate / free page-locked host memory (so that callers without a CUDA binding can stage pinned buffers). */
 void* hmr_alloc_pinned(size_t bytes);
 void  hmr_free_pinned(void* p);

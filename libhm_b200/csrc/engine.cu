@@ -54,6 +54,8 @@ struct hmr_engine
   uint32_t* dHash; uint32_t* dHashRows; size_t hashRowsCap;
   void* flushBuf; size_t flushCap;
   int coopLimit;
+  cudaEvent_t tBegin, tEnd, tJoin;
+  bool timerInit;
 };
 
 static int fail(hmr_engine* e, int code, const std::string& msg) { if (e) e->err = msg; return code; }
@@ -288,6 +290,7 @@ int hmr_engine_create(hmr_engine** out, int device)
   e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
   e->stageMask = HMR_STAGE_ALL; e->timing = false;
   memset(e->accMs, 0, sizeof(e->accMs)); e->accFrames = e->accLaunches = 0;
+  e->timerInit = false;
   e->dHash = nullptr; e->dHashRows = nullptr; e->hashRowsCap = 0; e->flushBuf = nullptr; e->flushCap = 0;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
   {
@@ -511,6 +514,51 @@ int hmr_run_resident(hmr_engine* e, const hmr_resident_frame* f)
   FrameParams P;
   fill_params(e, P, f->hdr, f->lay, f->dev, f->hasBs, f->hasCuf);
   return run_frame(e, P, grab_events(e));
+}
+
+int hmr_run_resident_list(hmr_engine* e, hmr_resident_frame* const* frames, int n)
+{
+  if (!e || (!frames && n > 0)) return HMR_ERR_ARG;
+  for (int i = 0; i < n; i++) { int r = hmr_run_resident(e, frames[i]); if (r) return r; }
+  return HMR_OK;
+}
+
+static int timer_init(hmr_engine* e)
+{
+  if (e->timerInit) return HMR_OK;
+  CK(cudaEventCreate(&e->tBegin)); CK(cudaEventCreate(&e->tEnd)); CK(cudaEventCreateWithFlags(&e->tJoin, cudaEventDisableTiming));
+  e->timerInit = true;
+  return HMR_OK;
+}
+
+int hmr_timer_begin(hmr_engine* e)
+{
+  if (!e) return HMR_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  int r = timer_init(e); if (r) return r;
+  CK(cudaEventRecord(e->tBegin, e->stream));
+  return HMR_OK;
+}
+
+int hmr_timer_join(hmr_engine* e, hmr_engine* other)
+{
+  if (!e || !other || e->device != other->device) return HMR_ERR_ARG;
+  if (e == other) return HMR_OK;
+  CK(cudaSetDevice(e->device));
+  { hmr_engine* keep = e; e = other; int r = timer_init(e); e = keep; if (r) return r; }
+  CK(cudaEventRecord(other->tJoin, other->stream));
+  CK(cudaStreamWaitEvent(e->stream, other->tJoin, 0));
+  return HMR_OK;
+}
+
+int hmr_timer_end(hmr_engine* e, float* ms)
+{
+  if (!e || !ms || !e->timerInit) return HMR_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaEventRecord(e->tEnd, e->stream));
+  CK(cudaEventSynchronize(e->tEnd));
+  CK(cudaEventElapsedTime(ms, e->tBegin, e->tEnd));
+  return HMR_OK;
 }
 
 void hmr_free_resident(hmr_engine* e, hmr_resident_frame* f)

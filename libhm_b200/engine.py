@@ -41,7 +41,9 @@ def load():
                            ("hmr_get_stage_times", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
                            ("hmr_upload_frame", [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
                            ("hmr_run_resident", [C.c_void_p, C.c_void_p]), ("hmr_free_resident", [C.c_void_p, C.c_void_p]),
-                           ("hmr_flush_l2", [C.c_void_p, C.c_size_t])):
+                           ("hmr_flush_l2", [C.c_void_p, C.c_size_t]),
+                           ("hmr_run_resident_list", [C.c_void_p, C.c_void_p, C.c_int]), ("hmr_timer_begin", [C.c_void_p]),
+                           ("hmr_timer_join", [C.c_void_p, C.c_void_p]), ("hmr_timer_end", [C.c_void_p, C.c_void_p])):
             getattr(lib, name).argtypes = args
         _lib = lib
     return _lib
@@ -131,6 +133,21 @@ class Engine:
 
     def free_resident(self, handle):
         self.lib.hmr_free_resident(self.h, handle)
+
+    def run_resident_list(self, handles):
+        arr = (C.c_void_p * len(handles))(*[h.value for h in handles])
+        self._ck(self.lib.hmr_run_resident_list(self.h, arr, len(handles)), "hmr_run_resident_list")
+
+    def timer_begin(self):
+        self._ck(self.lib.hmr_timer_begin(self.h), "hmr_timer_begin")
+
+    def timer_join(self, other):
+        self._ck(self.lib.hmr_timer_join(self.h, other.h), "hmr_timer_join")
+
+    def timer_end(self):
+        ms = C.c_float()
+        self._ck(self.lib.hmr_timer_end(self.h, C.byref(ms)), "hmr_timer_end")
+        return float(ms.value)
 
     def flush_l2(self, nbytes=256 << 20):
         self._ck(self.lib.hmr_flush_l2(self.h, nbytes), "hmr_flush_l2")
