@@ -15,6 +15,16 @@
 #include <map>
 #include <mutex>
 #include <iostream>
+#include <sstream>
+#include <fstream>
+#include <algorithm>
+#include <limits>
+#include <iomanip>
+#include <cmath>
+#include <cassert>
+#define private public
+#include "TLibCommon/TComSlice.h"
+#undef private
 #include "TLibCommon/CommonDef.h"
 #include "TLibCommon/TComTU.h"
 #include "TLibDecoder/TDecTop.h"
@@ -54,12 +64,13 @@ struct Decoder
   bool  flushing;            // output everything that is marked, regardless of the bumping rule
   bool  flushAfterThisPass;  // eof: one normal pass, then a flush pass
   bool  hashMismatch;
+  Int   prevTid0POC;         // per-decoder copy of TComSlice::m_prevTid0POC (thread_local in this build)
   std::vector<libHMDec_BlockValue> internals;
 
   Decoder(HmFrameSink* s)
     : sink(s), emitter(new HmEmitter(s)), maxTemporalLayer(-1), lastDisplayedPoc(-MAX_INT), skipFrames(0), dpb(NULL),
       cursor(0), pendingOutput(0), dpbFullness(0), reorderLimit(0), bufferingLimit(0), loopFilterDone(false),
-      flushing(false), flushAfterThisPass(false), hashMismatch(false)
+      flushing(false), flushAfterThisPass(false), hashMismatch(false), prevTid0POC(0)
   {
     top.create();
     top.init();
@@ -182,7 +193,9 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
   if (!(d->maxTemporalLayer >= 0 && (int)nalu.m_temporalId > d->maxTemporalLayer))
   {
     g_md5_mismatch = d->hashMismatch;
+    TComSlice::m_prevTid0POC = d->prevTid0POC;
     bNewPicture = d->top.decode(nalu, d->skipFrames, d->lastDisplayedPoc);   // TDecTop.cpp:729
+    d->prevTid0POC = TComSlice::m_prevTid0POC;
     d->hashMismatch = g_md5_mismatch;
   }
 

@@ -1,0 +1,107 @@
+// hmdec_mt.cpp — throughput harness: T decoder threads in ONE process (one libHMDec_* decoder per thread, each with
+// its own engine/CUDA stream, all sharing one CUDA context), every thread decoding the given Annex-B stream R times
+// through the public entry points exactly as a YUView-style caller would (push NAL, re-push on bNewPicture, drain
+// pictures, touch every plane).  Prints one JSON line with the wall time of the steady-state part.
+//   hmdec_mt -b in.bin [--threads T] [--repeat R] [--no-hash] [--no-planes] [--pin FIRSTCORE]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <vector>
+#include <pthread.h>
+#include "libHMDecoder_api.h"
+#include "annexb.h"
+
+struct Shared
+{
+  const std::vector<uint8_t>* stream;
+  const std::vector<std::pair<size_t, size_t> >* nals;
+  bool hash, planes;
+  int repeat;
+  std::atomic<int> ready, failures;
+  std::atomic<long> pictures;
+  std::atomic<bool> go;
+};
+
+static int decodeOnce(Shared& sh, long& pictures, uint64_t& sink)
+{
+  libHMDec_context* dec = libHMDec_new_decoder();
+  if (!dec) return 3;
+  libHMDec_set_SEI_Check(dec, sh.hash);
+  const std::vector<uint8_t>& s = *sh.stream;
+  const std::vector<std::pair<size_t, size_t> >& nals = *sh.nals;
+  for (size_t k = 0; k < nals.size();)
+  {
+    bool newPicture = false, checkOutput = false;
+    if (libHMDec_push_nal_unit(dec, &s[nals[k].first], (int)nals[k].second, k + 1 == nals.size(), newPicture, checkOutput) != LIBHMDEC_OK) return 4;
+    if (checkOutput)
+      while (libHMDec_picture* pic = libHMDec_get_picture(dec))
+      {
+        pictures++;
+        if (sh.planes)
+          for (int c = 0; c < 3; c++)
+          {
+            const short* p = libHMDEC_get_image_plane(pic, (libHMDec_ColorComponent)c);
+            if (p) sink += (uint64_t)p[0];
+          }
+      }
+    if (!newPicture) k++;
+  }
+  int rc = (libHMDecB200_hash_mismatch(dec) || libHMDecB200_unsupported(dec)) ? 1 : 0;
+  libHMDec_free_decoder(dec);
+  return rc;
+}
+
+static void worker(Shared* sh, int core)
+{
+  if (core >= 0)
+  {
+    cpu_set_t set; CPU_ZERO(&set); CPU_SET(core, &set);
+    pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+  }
+  long pics = 0; uint64_t sink = 0;
+  // warm-up pass outside the timed region: CUDA context, first allocations, page cache
+  if (decodeOnce(*sh, pics, sink)) sh->failures++;
+  pics = 0;
+  sh->ready++;
+  while (!sh->go.load()) std::this_thread::yield();
+  for (int r = 0; r < sh->repeat; r++) if (decodeOnce(*sh, pics, sink)) sh->failures++;
+  sh->pictures += pics;
+  if (sink == 0x12345678abcdefull) fprintf(stderr, "~");
+}
+
+int main(int argc, char** argv)
+{
+  const char* in = NULL; int threads = 1, repeat = 1, pin = -1; bool hash = true, planes = true;
+  for (int i = 1; i < argc; i++)
+  {
+    if (!strcmp(argv[i], "-b") && i + 1 < argc) in = argv[++i];
+    else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--pin") && i + 1 < argc) pin = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--no-hash")) hash = false;
+    else if (!strcmp(argv[i], "--no-planes")) planes = false;
+    else { fprintf(stderr, "usage: %s -b in.bin [--threads T] [--repeat R] [--no-hash] [--no-planes] [--pin FIRSTCORE]\n", argv[0]); return 2; }
+  }
+  if (!in) return 2;
+  setenv("HMDEC_B200_QUIET", "1", 0);
+  std::vector<uint8_t> stream;
+  if (!readFile(in, stream)) { perror(in); return 2; }
+  std::vector<std::pair<size_t, size_t> > nals;
+  splitAnnexB(stream, nals);
+  Shared sh;
+  sh.stream = &stream; sh.nals = &nals; sh.hash = hash; sh.planes = planes; sh.repeat = repeat;
+  sh.ready = 0; sh.failures = 0; sh.pictures = 0; sh.go = false;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) pool.emplace_back(worker, &sh, pin >= 0 ? pin + t : -1);
+  while (sh.ready.load() < threads) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  sh.go = true;
+  for (size_t t = 0; t < pool.size(); t++) pool[t].join();
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  printf("{\"threads\": %d, \"repeat\": %d, \"pictures\": %ld, \"seconds\": %.6f, \"fps\": %.3f, \"hash\": %s, \"planes\": %s, \"failures\": %d}\n",
+         threads, repeat, sh.pictures.load(), sec, sh.pictures.load() / sec, hash ? "true" : "false", planes ? "true" : "false", sh.failures.load());
+  return sh.failures.load() ? 1 : 0;
+}

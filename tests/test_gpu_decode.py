@@ -1,0 +1,37 @@
+"""End-to-end on the B200 box (-m gpu): the libHMDec_* drop-in (frontend/_build/libHMDecoder_b200.so = HM's parser +
+record emitter + CUDA engine) decodes the golden bitstreams; every picture's SEI MD5 check must pass in-process and the
+printed MD5s must equal the ones the unmodified TAppDecoder printed for the same stream (tests/golden/*.md5)."""
+import os
+import re
+import subprocess
+import pytest
+from conftest import GOLDEN, STREAMS, ROOT
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "frontend", "_build", "hmdec_cli")
+
+
+def _md5s(text):
+    return [(int(m.group(1)), m.group(2)) for m in re.finditer(r"POC\s+(-?\d+).*?\[MD5:([0-9a-f,]+),\(OK\)\]", text)]
+
+
+@pytest.mark.parametrize("name", STREAMS)
+def test_dropin_decoder_matches_tappdecoder(name):
+    if not os.path.exists(CLI):
+        pytest.skip("frontend/_build/hmdec_cli not built (needs the reference sources at build time)")
+    r = subprocess.run([CLI, "-b", os.path.join(GOLDEN, name + ".bin"), "--touch-planes"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "***ERROR***" not in r.stdout
+    got = _md5s(r.stdout)
+    ref = _md5s(open(os.path.join(GOLDEN, name + ".md5")).read())
+    assert got == ref and len(ref) > 0
+
+
+def test_dropin_decoder_selfcheck_against_hm_cpu_recon():
+    """HMDEC_B200_VERIFY=1 also runs HM's CPU reconstruction and compares every fetched plane byte for byte."""
+    if not os.path.exists(CLI):
+        pytest.skip("frontend not built")
+    env = dict(os.environ, HMDEC_B200_VERIFY="1")
+    r = subprocess.run([CLI, "-b", os.path.join(GOLDEN, "s_ra10_240p.bin"), "--touch-planes"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.count("(OK)") == 17
