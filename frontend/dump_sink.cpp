@@ -92,3 +92,14 @@ private:
 };
 
 HmFrameSink* hm_new_dump_sink(const char* path) { return new DumpSink(path); }
+
+// Profiling aid (HMDEC_B200_DUMP=null): parse + record emission only.  Nothing is reconstructed, pictures are NOT valid
+// and every hash check fails by construction — it exists to time the host side without a GPU.
+class NullSink : public HmFrameSink
+{
+public:
+  virtual void frameReady(const hmr_frame_desc&, TComPic*) {}
+  virtual void fetchPicture(TComPic*) {}
+  virtual bool wantHmRecon() const { return false; }
+};
+HmFrameSink* hm_new_null_sink() { return new NullSink(); }

@@ -40,7 +40,7 @@ public:
     s.slot = d.hdr->out_slot;
     s.hostStale = true;
     // the engine clamps coordinates instead of padding: spare HM the per-reference extendPicBorder() (TComSlice.cpp:350-376)
-    pic->getPicYuvRec()->setBorderExtension(true);
+    if (!m_verify) pic->getPicYuvRec()->setBorderExtension(true);   // (HM's own CPU MC in verify mode needs the real border)
   }
 
   virtual void fetchPicture(TComPic* pic)

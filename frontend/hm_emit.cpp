@@ -34,6 +34,8 @@
 #include "TLibCommon/TComRom.h"
 
 #include "hm_emit.h"
+#include <chrono>
+static inline double nowSec() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // free functions of TComPattern.cpp:558-735 (defined there, not declared in any header)
 Bool isAboveLeftAvailable ( TComDataCU* pcCU, UInt uiPartIdxLT );
@@ -56,12 +58,17 @@ struct HmEmitter::CuCtx
 };
 
 HmEmitter::HmEmitter(HmFrameSink* sink)
-  : m_sink(sink), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0)
+  : m_sink(sink), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0), m_tCtu(0), m_tBs(0), m_tPic(0), m_tSink(0), m_nPic(0)
 {
   memset(&m_hdr, 0, sizeof(m_hdr));
 }
 
-HmEmitter::~HmEmitter() {}
+HmEmitter::~HmEmitter()
+{
+  if (getenv("HMDEC_B200_STATS") && m_nPic)
+    fprintf(stderr, "hm_emit stats: %d pictures; per picture: CTU record emission %.2f ms, BS/QP maps %.2f ms, SAO+pack %.2f ms, sink submit %.2f ms\n",
+            m_nPic, 1e3 * m_tCtu / m_nPic, 1e3 * m_tBs / m_nPic, 1e3 * m_tPic / m_nPic, 1e3 * m_tSink / m_nPic);
+}
 
 void HmEmitter::fail(const char* what)
 {
@@ -131,6 +138,7 @@ void HmEmitter::beginFrame(TComPic* pic, TComDataCU* ctu)
 // one CTU: mirrors TDecCu::decompressCU -> xDecompressCU (TDecCu.cpp:142-145, 373-447)
 void HmEmitter::onCtuParsed(TComDataCU* ctu)
 {
+  const double t0 = nowSec();
   TComPic* pic = ctu->getPic();
   if (!m_open || pic != m_curPic) beginFrame(pic, ctu);
   for (int c = 0; c < 3; c++) m_intraTmp[c].clear();
@@ -142,6 +150,7 @@ void HmEmitter::onCtuParsed(TComDataCU* ctu)
     r.count[c] = (uint32_t)m_intraTmp[c].size();
     m_intra.insert(m_intra.end(), m_intraTmp[c].begin(), m_intraTmp[c].end());
   }
+  m_tCtu += nowSec() - t0;
 }
 
 void HmEmitter::walkCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth)
@@ -618,9 +627,11 @@ void HmEmitter::saoInfo(TComPic* pic, TComSampleAdaptiveOffset* sao)
 void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdaptiveOffset* sao, bool lfCrossTiles)
 {
   if (!m_open || pic != m_curPic) { fail("filterPicture for a picture with no parsed CTU"); return; }
+  const double t0 = nowSec();
   TComSlice* slice = pic->getSlice(pic->getCurrSliceIdx());
   lf->setCfg(lfCrossTiles);
   deblockInfo(pic, lf);
+  const double t1 = nowSec();
   if (slice->getSPS()->getUseSAO()) saoInfo(pic, sao);
   if (slice->getSPS()->getUsePCM()) { /* PCM CUs themselves are rejected in emitIntraCU */ }
   if (slice->isReferenced()) m_hdr.flags |= HMR_FRM_IS_REFERENCE;
@@ -655,6 +666,9 @@ void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdap
   d.bs = (m_hdr.flags & HMR_FRM_DEBLOCK) ? m_bs.data() : NULL;
   d.qp = m_qp.data();
   d.cu_flags = (m_hdr.flags & HMR_FRM_HAS_NOFILTER) ? m_cuFlags.data() : NULL;
+  const double t2 = nowSec();
   m_sink->frameReady(d, pic);
+  const double t3 = nowSec();
+  m_tBs += t1 - t0; m_tPic += t2 - t1; m_tSink += t3 - t2; m_nPic++;
   m_open = false;
 }

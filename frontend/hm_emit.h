@@ -80,6 +80,8 @@ private:
   std::vector<int8_t>              m_qp;
   std::vector<uint8_t>             m_cuFlags;
   int m_bsStride, m_qpStride;
+  double m_tCtu, m_tBs, m_tPic, m_tSink;   // HMDEC_B200_STATS: host time spent emitting records
+  int m_nPic;
 };
 
 // The emitter the hooks (TDecCu::decompressCU / TDecGop::filterPicture replacements) talk to.

@@ -22,6 +22,7 @@
 #include <iomanip>
 #include <cmath>
 #include <cassert>
+#include <malloc.h>
 #define private public
 #include "TLibCommon/TComSlice.h"
 #undef private
@@ -36,6 +37,7 @@
 bool g_md5_mismatch = false;
 
 HmFrameSink* hm_new_dump_sink(const char* path);
+HmFrameSink* hm_new_null_sink();
 HmFrameSink* hm_new_gpu_sink();           // gpu_sink.cpp
 std::vector<libHMDec_BlockValue>* hm_collect_internals(std::vector<libHMDec_BlockValue>& out, TComPic* pic, libHMDec_info_type type); // internals.cpp
 
@@ -133,10 +135,27 @@ extern "C" {
 
 const char* libHMDec_get_version(void) { return NV_VERSION; }
 
+// HM allocates and frees every picture buffer and ~50 KB of per-CTU arrays for EVERY picture (TDecTop::xGetNewPicBuffer:
+// rpcPic->destroy(); rpcPic->create(), TDecTop.cpp:187-189).  With glibc's defaults those blocks are mmap'ed, so each
+// picture costs ~100 MB of page faults and, with several decoder threads in one process, serialises on the mm lock.
+// Keeping freed blocks in the malloc arenas removes both (set HMDEC_B200_KEEP_MALLOC=1 to leave malloc untouched).
+static void tuneMallocOnce()
+{
+  static std::once_flag once;
+  std::call_once(once, []() {
+    if (getenv("HMDEC_B200_KEEP_MALLOC")) return;
+    mallopt(M_MMAP_THRESHOLD, 32 << 20);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_TOP_PAD, 64 << 20);
+  });
+}
+
 libHMDec_context* libHMDecB200_new_decoder_ex(int backend, const char* arg)
 {
+  tuneMallocOnce();
   HmFrameSink* sink = NULL;
   if (backend == 0) sink = hm_new_gpu_sink();
+  else if (backend == 1 && arg && !strcmp(arg, "null")) sink = hm_new_null_sink();
   else if (backend == 1 && arg) sink = hm_new_dump_sink(arg);
   if (!sink) return NULL;
   return (libHMDec_context*)new Decoder(sink);

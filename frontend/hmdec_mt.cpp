@@ -74,13 +74,14 @@ static void worker(Shared* sh, int core)
 
 int main(int argc, char** argv)
 {
-  const char* in = NULL; int threads = 1, repeat = 1, pin = -1; bool hash = true, planes = true;
+  const char* in = NULL; int threads = 1, repeat = 1, pin = -1; bool hash = true, planes = true; double startAt = 0;
   for (int i = 1; i < argc; i++)
   {
     if (!strcmp(argv[i], "-b") && i + 1 < argc) in = argv[++i];
     else if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--pin") && i + 1 < argc) pin = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--start-at") && i + 1 < argc) startAt = atof(argv[++i]);   // unix time: common start of several processes
     else if (!strcmp(argv[i], "--no-hash")) hash = false;
     else if (!strcmp(argv[i], "--no-planes")) planes = false;
     else { fprintf(stderr, "usage: %s -b in.bin [--threads T] [--repeat R] [--no-hash] [--no-planes] [--pin FIRSTCORE]\n", argv[0]); return 2; }
@@ -97,11 +98,14 @@ int main(int argc, char** argv)
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; t++) pool.emplace_back(worker, &sh, pin >= 0 ? pin + t : -1);
   while (sh.ready.load() < threads) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  if (startAt > 0)
+    while (std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count() < startAt) std::this_thread::sleep_for(std::chrono::microseconds(200));
+  const double wallStart = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   sh.go = true;
   for (size_t t = 0; t < pool.size(); t++) pool[t].join();
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  printf("{\"threads\": %d, \"repeat\": %d, \"pictures\": %ld, \"seconds\": %.6f, \"fps\": %.3f, \"hash\": %s, \"planes\": %s, \"failures\": %d}\n",
-         threads, repeat, sh.pictures.load(), sec, sh.pictures.load() / sec, hash ? "true" : "false", planes ? "true" : "false", sh.failures.load());
+  printf("{\"threads\": %d, \"repeat\": %d, \"pictures\": %ld, \"seconds\": %.6f, \"fps\": %.3f, \"hash\": %s, \"planes\": %s, \"failures\": %d, \"t_start\": %.6f, \"t_end\": %.6f}\n",
+         threads, repeat, sh.pictures.load(), sec, sh.pictures.load() / sec, hash ? "true" : "false", planes ? "true" : "false", sh.failures.load(), wallStart, wallStart + sec);
   return sh.failures.load() ? 1 : 0;
 }
