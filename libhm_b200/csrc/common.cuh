@@ -28,6 +28,7 @@ struct FrameParams
   const hmr_ctu_intra_range* irange;
   const hmr_pu*              pu;
   const uint32_t*            pu_prefix;
+  hmr_pu*                    mc_tiles;        // [n_mc_tiles] scratch: one record per 16x16-luma tile (k_mc.cu pre-pass)
   const hmr_ctu*             ctu;
   const uint8_t*             bs;
   const int8_t*              qp;

@@ -44,6 +44,7 @@ struct hmr_engine
   struct Stage { uint8_t* host; uint8_t* dev; size_t cap; cudaEvent_t done; bool inflight; } ring[RING];
   int ringPos;
   int16_t* resid; size_t residCap;
+  hmr_pu* mcTiles; size_t mcTilesCap;
   unsigned long long* progress; size_t progressCap;
   unsigned long long epoch;
   int stageMask;
@@ -190,6 +191,7 @@ static void fill_params(hmr_engine* e, FrameParams& P, const hmr_frame_hdr& h, c
   P.tu = (const hmr_tu*)(dev + L.tu.off);
   P.coef = (const int16_t*)(dev + L.coef.off);
   P.resid = e->resid;
+  P.mc_tiles = e->mcTiles;
   P.intra = (const hmr_intra*)(dev + L.intra.off);
   P.irange = (const hmr_ctu_intra_range*)(dev + L.irange.off);
   P.pu = (const hmr_pu*)(dev + L.pu.off);
@@ -232,12 +234,21 @@ static int run_frame(hmr_engine* e, FrameParams& P, FrameEvents* fe)
     e->residCap = ALIGN_UP((size_t)h.n_coef * 3 / 2 + 4096, 4096);
     CK(cudaMalloc(&e->resid, e->residCap * sizeof(int16_t)));
     P.resid = e->resid;
+  P.mc_tiles = e->mcTiles;
+  }
+  if (h.n_mc_tiles > e->mcTilesCap)
+  {
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->mcTiles) cudaFree(e->mcTiles);
+    e->mcTilesCap = ALIGN_UP((size_t)h.n_mc_tiles * 3 / 2 + 1024, 1024);
+    CK(cudaMalloc(&e->mcTiles, e->mcTilesCap * sizeof(hmr_pu)));
+    P.mc_tiles = e->mcTiles;
   }
   auto mark = [&](int k) { if (fe) { cudaEventRecord(fe->ev[k], e->stream); fe->used[k] = true; } };
   const int m = e->stageMask;
   uint32_t launches = 0;
   mark(HMR_T_MC);
-  if ((m & HMR_STAGE_MC) && h.n_mc_tiles) { launch_mc(P, e->stream); launches++; }
+  if ((m & HMR_STAGE_MC) && h.n_mc_tiles) { launch_mc(P, e->stream); launches += 2; }
   mark(HMR_T_RESID);
   if ((m & HMR_STAGE_RESID) && h.n_tu) launches += launch_resid(P, e->stream);
   mark(HMR_T_INTRA);
@@ -287,7 +298,7 @@ int hmr_engine_create(hmr_engine** out, int device)
   e->haveGeom = false; e->workAlloc = false;
   memset(e->slotAlloc, 0, sizeof(e->slotAlloc));
   memset(e->ring, 0, sizeof(e->ring));
-  e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
+  e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->mcTiles = nullptr; e->mcTilesCap = 0; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
   e->stageMask = HMR_STAGE_ALL; e->timing = false;
   memset(e->accMs, 0, sizeof(e->accMs)); e->accFrames = e->accLaunches = 0;
   e->timerInit = false;
@@ -319,6 +330,7 @@ void hmr_engine_destroy(hmr_engine* e)
     cudaEventDestroy(e->ring[i].done);
   }
   if (e->resid) cudaFree(e->resid);
+  if (e->mcTiles) cudaFree(e->mcTiles);
   if (e->progress) cudaFree(e->progress);
   if (e->dHash) cudaFree(e->dHash);
   if (e->dHashRows) cudaFree(e->dHashRows);

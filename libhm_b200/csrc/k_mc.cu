@@ -4,117 +4,280 @@
 // (TComPrediction.cpp:514-698), TComInterpolationFilter::filter / filterCopy (TComInterpolationFilter.cpp:94-251)
 // and TComYuv::addAvg (TComYuv.cpp:336-391).
 //
-// One CTA per 16x16-luma tile of a PU (plus the co-located chroma tiles).  The reference window of each list is
-// staged in shared memory with clamped coordinates, which is exactly HM's replicated picture border
-// (TComPicYuv::extendPicBorder, TComPicYuv.cpp:173-217) without ever materialising it.  Every case of HM
-// (copy / H only / V only / H+V, uni / bi) is evaluated as ONE separable pipeline H -> 14-bit intermediate -> V,
-// using the identity tap set for a zero fraction; that is bit-identical to HM's special cases because the
-// intermediate offset (8192 << s1) is a multiple of the first-stage divisor.
+// Work unit: one 16x16-luma tile of a PU (plus the co-located chroma tiles), owned by ONE WARP — no block-level
+// synchronisation anywhere.  A tiny pre-pass (mc_expand_kernel) turns the PU records into one 16-byte record per tile
+// so that the main kernel needs a single dependent load before it can fetch samples.
+//
+// Per tile: every reference window (luma + 2 chroma, up to 2 lists = 6 windows) is fetched up front with 16-byte
+// cp.async copies that are all in flight together (rows start at the 16-byte boundary below the window; the
+// sub-alignment `off` is handled when reading shared memory).  Windows that touch the picture border are gathered with
+// clamped coordinates instead, which is exactly HM's replicated border (TComPicYuv::extendPicBorder,
+// TComPicYuv.cpp:173-217) without ever materialising it.
+//
+// Arithmetic: every case of HM (copy / H only / V only / H+V, uni / bi) is ONE separable pipeline
+// H -> 14-bit intermediate -> V with the identity tap set for a zero fraction; that is bit-identical to HM's special
+// cases because the intermediate offset (8192 << s1) is a multiple of the first-stage divisor.  Both passes run on
+// packed int16 pairs with dp2a (2 MACs per instruction, no unpacking): the H pass reads sample pairs along a row, and
+// writes its 14-bit results packed as (row r, row r+1) pairs so that the V pass again sees pairs along its filter
+// direction.  An output at an even position uses NT/2 dp2a with taps (t0,t1)(t2,t3)..; an output at an odd position
+// uses NT/2+1 with the taps shifted by one half-word (0,t0)(t1,t2)..(t7,0).  All sums are exact int32, as in HM.
 #include "common.cuh"
 
-#define MC_T 16                     // luma tile edge
-#define MC_WIN (MC_T + 7)           // 23: tile + 8-tap support
-#define MC_LD 24                    // row pitch of the staged window
+#define MC_WARPS 4
+#define MC_PITCH 40                 // int16 per staged window row: up to 32 loaded + 8 pad (80 B: 16-byte aligned, conflict-free row pairs)
+#define MC_TMPW 16                  // words per row pair of the H-pass output
 
 __constant__ int8_t c_lumaTaps[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
 __constant__ int8_t c_chromaTaps[8][4] = { {0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4}, {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2} };
 
-__global__ void __launch_bounds__(256) mc_kernel(const __grid_constant__ FrameParams P)
+__device__ __forceinline__ void mc_cp_async16(void* smem, const void* gmem)
 {
-  __shared__ int16_t s_ref[MC_WIN * MC_LD];
-  __shared__ int16_t s_tmp[MC_WIN * MC_T];
-  __shared__ int s_pu;
-  const int tid = threadIdx.x;
-  const uint32_t tile = blockIdx.x;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void mc_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void mc_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
-  if (tid == 0)
-  {
-    int lo = 0, hi = (int)P.hdr.n_pu;                 // last PU with prefix[pu] <= tile
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.pu_prefix[mid] <= tile) lo = mid; else hi = mid; }
-    s_pu = lo;
-  }
-  __syncthreads();
-  const hmr_pu pu = P.pu[s_pu];
-  const int t = (int)(tile - P.pu_prefix[s_pu]);
-  const int tiles_x = (pu.w + MC_T - 1) / MC_T;
-  const int lx0 = pu.x + MC_T * (t % tiles_x), ly0 = pu.y + MC_T * (t / tiles_x);
-  const int lw = min(MC_T, pu.x + pu.w - lx0), lh = min(MC_T, pu.y + pu.h - ly0);
-  const bool bi = pu.lists == (HMR_PU_L0 | HMR_PU_L1);
-
-  for (int comp = 0; comp < 3; comp++)
-  {
-    const int cx = comp ? P.csx : 0, cy = comp ? P.csy : 0;
-    const int x0 = lx0 >> cx, y0 = ly0 >> cy, w = lw >> cx, h = lh >> cy;
-    const int ntaps = comp ? 4 : 8, half = ntaps / 2 - 1;
-    const int bd = comp ? P.hdr.bit_depth_chroma : P.hdr.bit_depth_luma;
-    const int headroom = max(2, 14 - bd);
-    const int maxv = (1 << bd) - 1;
-    const int ox = tid % w, oy = tid / w;            // the output sample this thread owns (w*h <= 256)
-    const bool owner = tid < w * h;
-    int val[2] = {0, 0};
-
-    for (int list = 0; list < 2; list++)
+// PU records -> one record per 16x16-luma tile (same struct: x, y, w, h describe the tile)
+__global__ void __launch_bounds__(256) mc_expand_kernel(const __grid_constant__ FrameParams P)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.hdr.n_pu) return;
+  const hmr_pu pu = P.pu[p];
+  const uint32_t base = P.pu_prefix[p];
+  const int tx = (pu.w + 15) >> 4, ty = (pu.h + 15) >> 4;
+  for (int j = 0; j < ty; j++)
+    for (int i = 0; i < tx; i++)
     {
-      if (!(pu.lists & (1 << list))) continue;       // uniform across the CTA
-      const int slot = list ? (pu.slots >> 4) : (pu.slots & 15);
-      const int16_t* __restrict__ ref = P.dpb[slot].p[comp];
-      const int rpitch = P.dpb[slot].pitch[comp];
-      const int mvx = pu.mv[list][0], mvy = pu.mv[list][1];
-      const int sx = 2 + cx, sy = 2 + cy;
-      const int ix = x0 + (mvx >> sx) - half, iy = y0 + (mvy >> sy) - half;
-      const int fx = mvx & ((1 << sx) - 1), fy = mvy & ((1 << sy) - 1);
-      const int8_t* tapx = comp ? c_chromaTaps[fx << (1 - cx)] : c_lumaTaps[fx];
-      const int8_t* tapy = comp ? c_chromaTaps[fy << (1 - cy)] : c_lumaTaps[fy];
-      const int rows = h + ntaps - 1, cols = w + ntaps - 1;
-      const int wmax = P.w[comp] - 1, hmax = P.h[comp] - 1;
-
-      for (int i = tid; i < rows * cols; i += 256)
-      {
-        const int r = i / cols, c = i - r * cols;
-        const int yy = clip3i(0, hmax, iy + r), xx = clip3i(0, wmax, ix + c);
-        s_ref[r * MC_LD + c] = ref[(size_t)yy * rpitch + xx];
-      }
-      __syncthreads();
-      // horizontal: isFirst, !isLast  (shift = 6 - headroom, offset = -8192 << shift); result truncated to Pel
-      const int s1 = 6 - headroom, o1 = -(8192 << s1);
-      for (int i = tid; i < rows * w; i += 256)
-      {
-        const int r = i / w, c = i - r * w;
-        int sum = 0;
-        for (int k = 0; k < ntaps; k++) sum += tapx[k] * s_ref[r * MC_LD + c + k];
-        s_tmp[r * MC_T + c] = (int16_t)((sum + o1) >> s1);
-      }
-      __syncthreads();
-      // vertical: !isFirst, isLast = !bi
-      if (owner)
-      {
-        int sum = 0;
-        for (int k = 0; k < ntaps; k++) sum += tapy[k] * s_tmp[(oy + k) * MC_T + ox];
-        const int s2 = bi ? 6 : 6 + headroom;
-        const int o2 = bi ? 0 : (1 << (s2 - 1)) + (8192 << 6);
-        int v = (int16_t)((sum + o2) >> s2);
-        if (!bi) v = clip3i(0, maxv, v);
-        val[list] = v;
-      }
-      __syncthreads();                               // s_ref / s_tmp are reused by the next list / component
+      hmr_pu t = pu;
+      t.x = (uint16_t)(pu.x + 16 * i); t.y = (uint16_t)(pu.y + 16 * j);
+      t.w = (uint8_t)min(16, pu.w - 16 * i); t.h = (uint8_t)min(16, pu.h - 16 * j);
+      P.mc_tiles[base + j * tx + i] = t;
     }
+}
 
-    if (owner)
+// Stage rows [iy, iy+rows) x columns [xa, xa + 8*nvec) of `ref` into s (pitch MC_PITCH).  Returns nothing; async on the fast path.
+__device__ __forceinline__ void mc_stage(int16_t* s, const int16_t* __restrict__ ref, int rpitch, int Wc, int Hc,
+                                         int ix, int iy, int xa, int rows, int cols, int nvec, int lane)
+{
+  const bool inside = iy >= 0 && iy + rows <= Hc && ix >= 0 && ix + cols <= Wc && xa + 8 * nvec <= rpitch;
+  if (inside)
+  {
+    const int16_t* g = ref + (size_t)iy * rpitch + xa;
+    if (nvec == 4)
+      for (int i = lane; i < rows * 4; i += 32) mc_cp_async16(s + (i >> 2) * MC_PITCH + 8 * (i & 3), g + (size_t)(i >> 2) * rpitch + 8 * (i & 3));
+    else
+      for (int i = lane; i < rows * nvec; i += 32)
+      {
+        const int r = i / nvec, q = i - r * nvec;
+        mc_cp_async16(s + r * MC_PITCH + 8 * q, g + (size_t)r * rpitch + 8 * q);
+      }
+  }
+  else
+  {
+    const int n = 8 * nvec;
+    for (int i = lane; i < rows * n; i += 32)
     {
-      int v;
+      const int r = i / n, c = i - r * n;
+      const int yy = clip3i(0, Hc - 1, iy + r), xx = clip3i(0, Wc - 1, xa + c);
+      s[r * MC_PITCH + c] = ref[(size_t)yy * rpitch + xx];
+    }
+  }
+}
+
+template <int NT> struct McTaps { int e[NT / 2]; int o[NT / 2 + 1]; };
+
+template <int NT>
+__device__ __forceinline__ McTaps<NT> mc_pack_taps(const int8_t* t)
+{
+  McTaps<NT> r;
+#pragma unroll
+  for (int j = 0; j < NT / 2; j++) r.e[j] = (t[2 * j] & 0xff) | ((t[2 * j + 1] & 0xff) << 8);
+#pragma unroll
+  for (int j = 0; j <= NT / 2; j++) r.o[j] = (j > 0 ? (t[2 * j - 1] & 0xff) : 0) | (j < NT / 2 ? ((t[2 * j] & 0xff) << 8) : 0);
+  return r;
+}
+
+template <int NT> __device__ __forceinline__ int mc_even(const int* w, const McTaps<NT>& t)
+{
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < NT / 2; j++) s = __dp2a_lo(w[j], t.e[j], s);
+  return s;
+}
+template <int NT> __device__ __forceinline__ int mc_odd(const int* w, const McTaps<NT>& t)
+{
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j <= NT / 2; j++) s = __dp2a_lo(w[j], t.o[j], s);
+  return s;
+}
+
+// H pass over one staged window: rows 2*rp, 2*rp+1 x output columns 2*cp, 2*cp+1 per item; results packed (row 2rp | row 2rp+1 << 16)
+template <int NT>
+__device__ __forceinline__ void mc_hpass(const int16_t* s, uint32_t* tmp, int off, int rowPairs, int log2ColPairs,
+                                         const McTaps<NT>& tx, int s1, int o1, int lane)
+{
+  const int nItems = rowPairs << log2ColPairs;
+  const bool oddStart = off & 1;
+  for (int it = lane; it < nItems; it += 32)
+  {
+    const int cp = it & ((1 << log2ColPairs) - 1), rp = it >> log2ColPairs;
+    const int* r0 = (const int*)(s + 2 * rp * MC_PITCH) + (off >> 1) + cp;
+    const int* r1 = r0 + MC_PITCH / 2;
+    int w0[NT / 2 + 1], w1[NT / 2 + 1];
+#pragma unroll
+    for (int j = 0; j <= NT / 2; j++) { w0[j] = r0[j]; w1[j] = r1[j]; }
+    int a0, a1, b0, b1;             // a: row 2rp, b: row 2rp+1; 0/1: output columns 2cp, 2cp+1
+    if (!oddStart) { a0 = mc_even<NT>(w0, tx); a1 = mc_odd<NT>(w0, tx); b0 = mc_even<NT>(w1, tx); b1 = mc_odd<NT>(w1, tx); }
+    else           { a0 = mc_odd<NT>(w0, tx);  a1 = mc_even<NT>(w0 + 1, tx); b0 = mc_odd<NT>(w1, tx); b1 = mc_even<NT>(w1 + 1, tx); }
+    a0 = (a0 + o1) >> s1; a1 = (a1 + o1) >> s1; b0 = (b0 + o1) >> s1; b1 = (b1 + o1) >> s1;     // truncated to Pel by the packing
+    uint2 out;
+    out.x = (uint32_t)(a0 & 0xffff) | ((uint32_t)b0 << 16);
+    out.y = (uint32_t)(a1 & 0xffff) | ((uint32_t)b1 << 16);
+    *(uint2*)(tmp + rp * MC_TMPW + 2 * cp) = out;
+  }
+}
+
+// V pass for this lane's item: output rows 2*yg, 2*yg+1 x columns 4*x4 .. 4*x4+3.  v[0..3] = row 2yg, v[4..7] = row 2yg+1 (raw sums).
+template <int NT>
+__device__ __forceinline__ void mc_vpass(const uint32_t* tmp, int x4, int yg, const McTaps<NT>& ty, int v[8])
+{
+  int w[4][NT / 2 + 1];
+#pragma unroll
+  for (int j = 0; j <= NT / 2; j++)
+  {
+    const uint4 q = *(const uint4*)(tmp + (yg + j) * MC_TMPW + 4 * x4);
+    w[0][j] = (int)q.x; w[1][j] = (int)q.y; w[2][j] = (int)q.z; w[3][j] = (int)q.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) { v[c] = mc_even<NT>(w[c], ty); v[4 + c] = mc_odd<NT>(w[c], ty); }
+}
+
+template <int NT>
+__device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu& t, int comp, int cx, int cy, int16_t* const sref[2],
+                                             const int offs[2], uint32_t* tmp, int lane)
+{
+  const int tw = 16 >> cx, th = 16 >> cy;                    // full tile in this component
+  const int x0 = t.x >> cx, y0 = t.y >> cy, w = t.w >> cx, h = t.h >> cy;
+  const int bd = comp ? P.hdr.bit_depth_chroma : P.hdr.bit_depth_luma;
+  const int headroom = max(2, 14 - bd), maxv = (1 << bd) - 1;
+  const int s1 = 6 - headroom, o1 = -(8192 << s1);
+  const bool bi = t.lists == (HMR_PU_L0 | HMR_PU_L1);
+  const int rowPairs = (th + NT) >> 1;                       // th + NT - 1 rows, rounded up to even
+  const int log2ColPairs = tw == 16 ? 3 : 2;
+  const int nV = (tw >> 2) * (th >> 1);                      // V items: 4 columns x 2 rows each (<= 32)
+  const int x4 = lane & ((tw >> 2) - 1), yg = lane / (tw >> 2);
+  int acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0;
+
+  for (int list = 0; list < 2; list++)
+  {
+    if (!(t.lists & (1 << list))) continue;                  // warp-uniform
+    const int mvx = t.mv[list][0], mvy = t.mv[list][1];
+    const int fx = mvx & ((4 << cx) - 1), fy = mvy & ((4 << cy) - 1);
+    const McTaps<NT> tx = mc_pack_taps<NT>(NT == 8 ? c_lumaTaps[fx] : c_chromaTaps[fx << (1 - cx)]);
+    const McTaps<NT> ty = mc_pack_taps<NT>(NT == 8 ? c_lumaTaps[fy] : c_chromaTaps[fy << (1 - cy)]);
+    mc_hpass<NT>(sref[list], tmp, offs[list], rowPairs, log2ColPairs, tx, s1, o1, lane);
+    __syncwarp();
+    if (lane < nV)
+    {
+      int v[8];
+      mc_vpass<NT>(tmp, x4, yg, ty, v);
       if (bi)
       {
-        const int sh = headroom + 1, off = (1 << (sh - 1)) + 2 * 8192;   // TComYuv::addAvg
-        v = clip3i(0, maxv, (val[0] + val[1] + off) >> sh);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] += (int)(int16_t)(v[i] >> 6);       // xPredInterBlk, !isLast: Pel result
       }
-      else v = (pu.lists & HMR_PU_L0) ? val[0] : val[1];
-      P.work.p[comp][(size_t)(y0 + oy) * P.work.pitch[comp] + x0 + ox] = (int16_t)v;
+      else
+      {
+        const int s2 = 6 + headroom, o2 = (1 << (s2 - 1)) + (8192 << 6);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = clip3i(0, maxv, (int)(int16_t)((v[i] + o2) >> s2));
+      }
+    }
+    __syncwarp();                                            // tmp is reused by the next list / component
+  }
+  if (lane >= nV) return;
+  if (bi)
+  {
+    const int sh = headroom + 1, off = (1 << (sh - 1)) + 2 * 8192;             // TComYuv::addAvg
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = clip3i(0, maxv, (acc[i] + off) >> sh);
+  }
+  int16_t* dst = P.work.p[comp] + (size_t)(y0 + 2 * yg) * P.work.pitch[comp] + x0 + 4 * x4;
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+  {
+    if (2 * yg + r >= h) break;
+    int16_t* d = dst + (size_t)r * P.work.pitch[comp];
+    const uint32_t lo = (uint32_t)(acc[4 * r] & 0xffff) | ((uint32_t)acc[4 * r + 1] << 16);
+    const uint32_t hi = (uint32_t)(acc[4 * r + 2] & 0xffff) | ((uint32_t)acc[4 * r + 3] << 16);
+    if (4 * x4 + 4 <= w && (((x0 + 4 * x4) & 3) == 0)) *(uint2*)d = make_uint2(lo, hi);
+    else
+    {
+      if (4 * x4 + 2 <= w) *(uint32_t*)d = lo;
+      if (4 * x4 + 4 <= w) *(uint32_t*)(d + 2) = hi;
     }
   }
+}
+
+__global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant__ FrameParams P, const int warpBytes, const int chromaRows)
+{
+  extern __shared__ __align__(16) uint8_t s_mc[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t tile = blockIdx.x * MC_WARPS + warp;
+  if (tile >= P.hdr.n_mc_tiles) return;
+  uint8_t* base = s_mc + (size_t)warp * warpBytes;
+  uint32_t* tmp = (uint32_t*)base;                                        // 12 row pairs x 16 words
+  int16_t* lumaWin = (int16_t*)(base + 12 * MC_TMPW * 4);                 // 2 lists x 24 rows
+  int16_t* chromaWin = lumaWin + 2 * 24 * MC_PITCH;                       // 2 planes x 2 lists x chromaRows
+
+  const uint4 raw = __ldg((const uint4*)(P.mc_tiles + tile));
+  const hmr_pu t = *(const hmr_pu*)&raw;
+  const bool chroma = P.hdr.chroma_format != HMR_CHROMA_400;
+  int16_t* sref[3][2];
+  int offs[3][2];
+
+  // ---- stage all windows: luma first (own commit group), then chroma ----
+#pragma unroll
+  for (int comp = 0; comp < 3; comp++)
+  {
+    if (comp > 0 && !chroma) continue;
+    const int cx = comp ? P.csx : 0, cy = comp ? P.csy : 0;
+    const int nt = comp ? 4 : 8, half = nt / 2 - 1;
+    const int tw = 16 >> cx, th = 16 >> cy;
+    const int rows = (th + nt) & ~1, cols = tw + nt - 1;
+#pragma unroll
+    for (int list = 0; list < 2; list++)
+    {
+      int16_t* s = comp == 0 ? lumaWin + list * 24 * MC_PITCH : chromaWin + ((comp - 1) * 2 + list) * chromaRows * MC_PITCH;
+      sref[comp][list] = s;
+      offs[comp][list] = 0;
+      if (!(t.lists & (1 << list))) continue;
+      const int slot = list ? (t.slots >> 4) : (t.slots & 15);
+      const int ix = (t.x >> cx) + (t.mv[list][0] >> (2 + cx)) - half, iy = (t.y >> cy) + (t.mv[list][1] >> (2 + cy)) - half;
+      const int xa = ix & ~7, off = ix - xa;
+      offs[comp][list] = off;
+      mc_stage(s, P.dpb[slot].p[comp], P.dpb[slot].pitch[comp], P.w[comp], P.h[comp], ix, iy, xa, rows, cols, (off + cols + 7) >> 3, lane);
+    }
+    if (comp == 0 || comp == 2) mc_cp_async_commit();
+  }
+  if (chroma) mc_cp_async_wait<1>(); else mc_cp_async_wait<0>();
+  __syncwarp();
+  mc_component<8>(P, t, 0, 0, 0, sref[0], offs[0], tmp, lane);
+  if (!chroma) return;
+  mc_cp_async_wait<0>();
+  __syncwarp();
+  mc_component<4>(P, t, 1, P.csx, P.csy, sref[1], offs[1], tmp, lane);
+  mc_component<4>(P, t, 2, P.csx, P.csy, sref[2], offs[2], tmp, lane);
 }
 
 void launch_mc(const FrameParams& P, cudaStream_t s)
 {
   if (P.hdr.n_mc_tiles == 0) return;
-  mc_kernel<<<P.hdr.n_mc_tiles, 256, 0, s>>>(P);
+  mc_expand_kernel<<<(P.hdr.n_pu + 255) / 256, 256, 0, s>>>(P);
+  const int chromaRows = ((16 >> P.csy) + 4) & ~1;
+  const int warpBytes = 12 * MC_TMPW * 4 + 2 * 24 * MC_PITCH * 2 + 4 * chromaRows * MC_PITCH * 2;
+  mc_kernel<<<(P.hdr.n_mc_tiles + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, MC_WARPS * warpBytes, s>>>(P, warpBytes, chromaRows);
 }

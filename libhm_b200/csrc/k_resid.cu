@@ -6,8 +6,10 @@
 // xITransformSkip (:1920-1959), transquant-bypass copy (:1475-1487), invRdpcmNxN (:1737-1792),
 // crossComponentPrediction (:3294-3335), and TComYuv::addClip (TComYuv.cpp:264-299) for inter CUs.
 //
-// One launch per transform size (the host groups the TU records by size).  A group of N threads owns one NxN TU:
-// stage 1: thread j transforms coefficient column j (dequantising on load, skipping zero levels);
+// ONE launch per picture: the host groups the TU records by size, and a CTA finds its size class from four block-count
+// prefixes.  A group of N threads owns one NxN TU:
+// stage 1: thread j transforms coefficient column j (all N levels of the column are loaded up front so that the loads
+//          overlap; dequantising on load; coefficient rows that are zero across the whole warp are skipped);
 // stage 2: thread y transforms row y of the transposed intermediate.  The two stages exchange the N x N
 // intermediate through shared memory (pitch N+2 -> conflict-free both ways).  Integer MACs in registers; the
 // HEVC matrices live in __constant__ memory and are always addressed uniformly across a warp.
@@ -40,13 +42,13 @@ static void upload_tables(int device)
 }
 
 template <int LOG2N>
-__global__ void __launch_bounds__(RS_THREADS) resid_kernel(const __grid_constant__ FrameParams P, const uint32_t first, const uint32_t count, const int phase)
+__device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all, const uint32_t first, const uint32_t count, const uint32_t block, const int phase)
 {
   constexpr int N = 1 << LOG2N, NN = N * N, LD = N + 2, PER_BLOCK = RS_THREADS / N, STEP = 32 / N;
-  __shared__ int16_t s_buf[PER_BLOCK][N * LD];
+  int16_t (*s_buf)[N * LD] = (int16_t (*)[N * LD])s_all;
   const int g = threadIdx.x / N;          // TU slot inside the CTA
   const int j = threadIdx.x % N;          // my column (stage 1) / row (stage 2) / column again (store)
-  const uint32_t idx = blockIdx.x * PER_BLOCK + g;
+  const uint32_t idx = block * PER_BLOCK + g;
   bool active = idx < count;
   hmr_tu t;
   if (active)
@@ -72,9 +74,13 @@ __global__ void __launch_bounds__(RS_THREADS) resid_kernel(const __grid_constant
     const bool dst = (LOG2N == 2) && (t.flags & HMR_TU_DST);
 #pragma unroll
     for (int k = 0; k < N; k++) acc[k] = 0;
+    int lv[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) lv[n] = __ldg(lev + n * N + j);
+#pragma unroll
     for (int n = 0; n < N; n++)
     {
-      const int q = lev[n * N + j];
+      const int q = lv[n];
       if (q == 0) continue;
       const int qc = clip3i(inMin, inMax, q);
       int c = rshift > 0 ? (qc * scale + (1 << (rshift - 1))) >> rshift : (int)((unsigned)(qc * scale) << (-rshift));
@@ -180,21 +186,16 @@ __global__ void __launch_bounds__(RS_THREADS) resid_kernel(const __grid_constant
   }
 }
 
-template <int LOG2N>
-static int launch_size(const FrameParams& P, cudaStream_t s)
+struct ResidGrid { uint32_t first[4], count[4], blockEnd[4]; };   // per size class 4x4 .. 32x32
+
+__global__ void __launch_bounds__(RS_THREADS) resid_kernel(const __grid_constant__ FrameParams P, const ResidGrid G, const int phase)
 {
-  const uint32_t first = P.hdr.tu_first[LOG2N - 2], count = P.hdr.tu_first[LOG2N - 1] - first;
-  if (!count) return 0;
-  constexpr int PER_BLOCK = RS_THREADS >> LOG2N;
-  const uint32_t blocks = (count + PER_BLOCK - 1) / PER_BLOCK;
-  if (P.hdr.flags & HMR_FRM_HAS_CCP)
-  {
-    resid_kernel<LOG2N><<<blocks, RS_THREADS, 0, s>>>(P, first, count, 0);
-    resid_kernel<LOG2N><<<blocks, RS_THREADS, 0, s>>>(P, first, count, 1);
-    return 2;
-  }
-  resid_kernel<LOG2N><<<blocks, RS_THREADS, 0, s>>>(P, first, count, -1);
-  return 1;
+  __shared__ __align__(16) int16_t s_all[(RS_THREADS / 32) * 32 * 34];     // largest user: 4 TUs of 32x32, pitch 34
+  const uint32_t b = blockIdx.x;
+  if (b < G.blockEnd[0])      resid_block<2>(P, s_all, G.first[0], G.count[0], b, phase);
+  else if (b < G.blockEnd[1]) resid_block<3>(P, s_all, G.first[1], G.count[1], b - G.blockEnd[0], phase);
+  else if (b < G.blockEnd[2]) resid_block<4>(P, s_all, G.first[2], G.count[2], b - G.blockEnd[1], phase);
+  else                        resid_block<5>(P, s_all, G.first[3], G.count[3], b - G.blockEnd[2], phase);
 }
 
 int launch_resid(const FrameParams& P, cudaStream_t s)
@@ -202,15 +203,24 @@ int launch_resid(const FrameParams& P, cudaStream_t s)
   int dev = 0;
   cudaGetDevice(&dev);
   upload_tables(dev);
-  int n = 0;
+  ResidGrid G;
+  uint32_t blocks = 0;
+  for (int k = 0; k < 4; k++)
+  {
+    G.first[k] = P.hdr.tu_first[k];
+    G.count[k] = P.hdr.tu_first[k + 1] - P.hdr.tu_first[k];
+    const uint32_t perBlock = RS_THREADS >> (k + 2);
+    blocks += (G.count[k] + perBlock - 1) / perBlock;
+    G.blockEnd[k] = blocks;
+  }
+  if (!blocks) return 0;
   if (P.hdr.flags & HMR_FRM_HAS_CCP)
   {
-    // all luma (and non-CCP chroma) TUs of every size first, then the chroma TUs that read luma residuals
-    // (co-located TUs have the same size in 4:4:4, but ordering across sizes keeps the rule simple)
+    // phase 0: all luma (and non-CCP chroma) TUs of every size; phase 1: the chroma TUs that read luma residuals
+    resid_kernel<<<blocks, RS_THREADS, 0, s>>>(P, G, 0);
+    resid_kernel<<<blocks, RS_THREADS, 0, s>>>(P, G, 1);
+    return 2;
   }
-  n += launch_size<2>(P, s);
-  n += launch_size<3>(P, s);
-  n += launch_size<4>(P, s);
-  n += launch_size<5>(P, s);
-  return n;
+  resid_kernel<<<blocks, RS_THREADS, 0, s>>>(P, G, -1);
+  return 1;
 }

@@ -35,3 +35,25 @@ def test_dropin_decoder_selfcheck_against_hm_cpu_recon():
     r = subprocess.run([CLI, "-b", os.path.join(GOLDEN, "s_ra10_240p.bin"), "--touch-planes"], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("(OK)") == 17
+
+
+BENCH = os.path.join(ROOT, "bench_data")
+BENCH_STREAMS = ["c3_ra10_2160p", "c4_rext444_1080p", "c5_ld10_2160p_s50", "m_ra10_1080p"]
+
+
+@pytest.mark.parametrize("name", BENCH_STREAMS)
+def test_full_size_streams_pass_the_sei_md5_check(name):
+    """BASELINE.json's full sizes (2160p Main10 RA / LD, 1080p 4:4:4 12-bit): every picture the drop-in decodes must pass
+    the encoder-embedded SEI MD5 (the same check the unmodified TAppDecoder performs), and, where the reference's
+    printed MD5 list is shipped, equal it."""
+    path = os.path.join(BENCH, name + ".bin")
+    if not os.path.exists(CLI) or not os.path.exists(path):
+        pytest.skip("frontend or bench stream not present")
+    r = subprocess.run([CLI, "-b", path, "--touch-planes"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "***ERROR***" not in r.stdout and "(unk)" not in r.stdout
+    got = _md5s(r.stdout)
+    assert len(got) >= 4
+    ref_file = os.path.join(BENCH, name + ".md5")
+    if os.path.exists(ref_file):
+        assert got == _md5s(open(ref_file).read())
