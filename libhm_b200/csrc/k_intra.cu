@@ -12,21 +12,30 @@
 // WPP dependency.  Progress counters carry an epoch so they never need clearing; a row publishes "all CTUs before
 // my next CTU that has intra TUs", so rows/CTUs without intra blocks cost nothing.
 //
-// The per-TU chain is the critical path (an I picture at 2160p is ~3300 dependent TU steps), so it is latency
-// engineered: when a CTU has intra TUs, all 4 warps stage in shared memory (a) the CTU's current samples plus the
-// row above (x = -1 .. CTU+31) and the column to the left, (b) the CTU's intra records, (c) the residuals of those
-// TUs, with 8/16-byte loads that are all in flight together; then ONE warp runs the TUs back to back out of shared
-// memory (reference line -> smoothing -> prediction -> + residual -> back into the tile) with warp-level
-// synchronisation only, and the tile is written back once, coalesced, by all warps.  Cross-CTA reads go through L2
-// (ld.global.cg); the producer fences before publishing.
+// The per-TU chain is the critical path (an I picture at 2160p is ~3300 dependent TU steps; a dataflow simulation over
+// real streams shows TU-level parallelism inside a CTU is < 1.2x, z-order makes every TU depend on its predecessor),
+// so the design minimises the latency of ONE warp walking the TUs:
+//   * all 4 warps stage in shared memory the CTU's current samples plus the row above (x = -1 .. CTU+31) and the
+//     column to the left, and the residuals of the CTU's TUs, with 16-byte cp.async copies all in flight together;
+//   * warps 1-3 ("helpers") turn the NEXT intra CTU's records into reference-address tables while warp 0 runs the
+//     current CTU: for every TU, entry i = shared-memory position of reference sample i AFTER HM's substitution of
+//     unavailable samples (pure function of the record, no sample data) — the whole fillReferenceSamples logic is off
+//     the critical path and double-buffered;
+//   * warp 0 ("chain") runs size-templated, fully unrolled code per TU: gather the line through the table -> optional
+//     smoothing -> prediction (main-reference projection folded into the index) -> + residual -> back into the tile,
+//     with warp-level synchronisation only;
+//   * the tile is written back once, coalesced, by all warps.  Cross-CTA reads go through L2 (ld.global.cg); the
+//     producer fences before publishing.
 #include "common.cuh"
 
 #define IN_THREADS 128
 #define IN_MAXCT 64
 #define IN_LD (8 + IN_MAXCT + 32)          // tile pitch: 8 columns of left margin (x = -1 lives at column 7), CTU, 32 above-right
+#define IN_TILE ((IN_MAXCT + 1) * IN_LD)   // row 0 = y -1; element 0 (y = -1, x = -8) holds the "nothing available" constant
 #define IN_MAXREC 256                      // intra records of one CTU and component (64x64 in 4x4 blocks)
-#define IN_MAXRES (IN_MAXCT * IN_MAXCT * 3) // compact residual span of one CTU, all components (4:4:4 worst case)
+#define IN_ADDR (16 * 16 * 17)             // address-table entries per CTU: 17 per 4x4 block, a TU owns the slots of its first block row
 #define IN_MAXCOLS 512                     // CTU columns per picture row whose record ranges are cached (8192 / 16)
+#define TIDX(y, x) (((y) + 1) * IN_LD + 8 + (x))
 
 __constant__ int c_angTab[9] = { 0, 2, 5, 9, 13, 17, 21, 26, 32 };
 __constant__ int c_invTab[9] = { 0, 4096, 1638, 910, 630, 482, 390, 315, 256 };
@@ -52,17 +61,221 @@ __device__ __forceinline__ int next_intra_ctu(const uint16_t* cnt, int from, int
   return n;
 }
 
-__global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant__ FrameParams P)
+struct IntraGeom { int ox, oy, CTW, CTH, uws, uhs, gw; };   // CTU origin / size in component samples, log2 unit size, 4x4 blocks per CTU row
+
+__device__ __forceinline__ int intra_slot(const hmr_intra& r, const IntraGeom& g) { return ((((r.y - g.oy) >> 2) * g.gw) + ((r.x - g.ox) >> 2)) * 17; }
+
+// Reference-sample positions of one TU with HM's substitution (TComPattern.cpp:309-520) resolved: entry i of the line
+// ([0] bottom-most below-left ... [2N] corner ... [4N] last above-right) = tile index to read.  Unit-granular availability.
+__device__ __forceinline__ void intra_addr_table(const hmr_intra& r, uint16_t* __restrict__ addr, const IntraGeom& g, int lane)
 {
-  __shared__ __align__(16) int16_t s_tile[(IN_MAXCT + 1) * IN_LD];   // row 0 = y -1
-  __shared__ __align__(16) int16_t s_res[IN_MAXRES];                 // residuals of this CTU, compact layout relative to s_minoff
-  __shared__ __align__(16) hmr_intra s_rec[IN_MAXREC];
-  __shared__ int s_line[4 * 32 + 1];      // unfiltered reference line: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right
-  __shared__ int s_flt[4 * 32 + 1];       // smoothed
-  __shared__ int s_rm[3 * 32 + 2];        // angular main reference, index -N..2N stored at +32
+  const int N = 1 << r.log2_size, N2 = 2 * N, L = 4 * N + 1;
+  const int x0 = r.x - g.ox, y0 = r.y - g.oy;
+  const int nl = N >> g.uhs, na = N >> g.uws;
+  unsigned long long M = 0;                               // bit u = unit u available, units in line order
+  M |= (unsigned long long)(__brev((unsigned)r.avail_below_left) >> (32 - nl));
+  M |= (unsigned long long)(__brev((unsigned)r.avail_left) >> (32 - nl)) << nl;
+  if (r.flags & HMR_INTRA_AVAIL_CORNER) M |= 1ull << (2 * nl);
+  M |= (unsigned long long)r.avail_above << (2 * nl + 1);
+  M |= (unsigned long long)r.avail_above_right << (2 * nl + 1 + na);
+  const int q = __ffsll((long long)M) - 1;                // first available unit
+  const int qsrc = q < 2 * nl ? (q << g.uhs) : (q == 2 * nl ? N2 : N2 + 1 + ((q - 2 * nl - 1) << g.uws));
+  for (int i = lane; i < L; i += 32)
+  {
+    int a = 0;                                            // nothing available: the constant slot
+    if (M)
+    {
+      const int u = i < N2 ? (i >> g.uhs) : (i == N2 ? 2 * nl : 2 * nl + 1 + ((i - N2 - 1) >> g.uws));
+      int src = i;
+      if (!((M >> u) & 1))
+      {
+        const unsigned long long lower = M & ((1ull << u) - 1);
+        if (lower)
+        {
+          const int p = 63 - __clzll((long long)lower);   // nearest available unit before: its LAST sample
+          src = p < 2 * nl ? ((p + 1) << g.uhs) - 1 : (p == 2 * nl ? N2 : N2 + ((p - 2 * nl) << g.uws));
+        }
+        else src = qsrc;                                  // first available unit after: its FIRST sample
+      }
+      if (src < N2)       a = TIDX(min(y0 + N2 - 1 - src, g.CTH - 1), x0 - 1);
+      else if (src == N2) a = TIDX(y0 - 1, x0 - 1);
+      else                a = TIDX(y0 - 1, min(x0 + (src - N2 - 1), g.CTW + 31));
+    }
+    addr[i] = (uint16_t)a;
+  }
+}
+
+// One TU on one warp, everything in shared memory.  `line`/`flt` are warp-private scratch (4N+1 ints each).
+template <int LG>
+__device__ __forceinline__ void intra_tu(const hmr_intra r, const uint16_t* __restrict__ addr, int16_t* __restrict__ tile,
+                                         const int16_t* __restrict__ res, int* __restrict__ line, int* __restrict__ flt,
+                                         const int x0, const int y0, const int bd, const bool strongAllowed, const int lane)
+{
+  constexpr int N = 1 << LG, N2 = 2 * N, L = 4 * N + 1, NJ = (L + 31) / 32, S = (N * N + 31) / 32;
+  const int maxv = (1 << bd) - 1;
+  // ---- reference line through the address table ----
+#pragma unroll
+  for (int j = 0; j < NJ; j++)
+  {
+    const int i = lane + 32 * j;
+    if (i < L) line[i] = tile[addr[i]];
+  }
+  __syncwarp();
+  const int* ref = line;
+  if (r.flags & HMR_INTRA_FILTER_REFS)
+  {
+    const int bl = line[0], tl = line[N2], tr = line[4 * N];
+    bool strong = false;
+    if (N == 32 && strongAllowed && (r.flags & HMR_INTRA_LUMA_RULES))
+    {
+      const int thr = 1 << (bd - 5);
+      strong = abs(bl + tl - 2 * line[N]) < thr && abs(tl + tr - 2 * line[3 * N]) < thr;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+    {
+      const int i = lane + 32 * j;
+      if (i < L)
+      {
+        int v;
+        if (i == 0 || i == 4 * N) v = line[i];
+        else if (strong) v = i < N2 ? ((N2 - i) * bl + i * tl + N) >> (LG + 1) : (i == N2 ? tl : ((N2 - (i - N2)) * tl + (i - N2) * tr + N) >> (LG + 1));
+        else v = (line[i - 1] + 2 * line[i] + line[i + 1] + 2) >> 2;
+        flt[i] = v;
+      }
+    }
+    ref = flt;
+    __syncwarp();
+  }
+#define LEFT(y) ref[N2 - 1 - (y)]
+#define TOP(x)  ref[N2 + 1 + (x)]
+#define EMIT(i, y, x, v) tile[TIDX(y0 + (y), x0 + (x))] = (int16_t)clip3i(0, maxv, (int)(int16_t)(v) + (hasRes ? (int)res[i] : 0))
+  const int mode = r.mode;
+  const bool lumaRules = r.flags & HMR_INTRA_LUMA_RULES;
+  const bool hasRes = r.resid_off != HMR_NO_OFFSET;
+  if (mode == 0)
+  {
+    const int tn = TOP(N), ln = LEFT(N);
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      const int i = lane + 32 * j;
+      if (N * N >= 32 || i < N * N)
+      {
+        const int y = i >> LG, x = i & (N - 1);
+        const int v = ((N - 1 - x) * LEFT(y) + (x + 1) * tn + (N - 1 - y) * TOP(x) + (y + 1) * ln + N) >> (LG + 1);
+        EMIT(i, y, x, v);
+      }
+    }
+  }
+  else if (mode == 1)
+  {
+    const int part = lane < N ? TOP(lane) + LEFT(lane) : 0;
+    const int dc = (__reduce_add_sync(0xffffffffu, part) + N) >> (LG + 1);
+    const bool edge = lumaRules && N <= 16;
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      const int i = lane + 32 * j;
+      if (N * N >= 32 || i < N * N)
+      {
+        const int y = i >> LG, x = i & (N - 1);
+        int v = dc;
+        if (edge)
+        {
+          if (x == 0 && y == 0) v = (TOP(0) + LEFT(0) + 2 * dc + 2) >> 2;
+          else if (y == 0) v = (TOP(x) + 3 * dc + 2) >> 2;
+          else if (x == 0) v = (LEFT(y) + 3 * dc + 2) >> 2;
+        }
+        EMIT(i, y, x, v);
+      }
+    }
+  }
+  else
+  {
+    const bool ver = mode >= 18;
+    const int am = ver ? mode - 26 : 10 - mode;
+    const int aa = abs(am);
+    const int angle = am < 0 ? -c_angTab[aa] : c_angTab[aa];
+    const int sgn = ver ? 1 : -1;                          // main reference rm[j >= 0] = ref[N2 + sgn*j]
+    if (angle == 0)
+    {
+      const bool edge = lumaRules && N <= 16 && !(r.flags & HMR_INTRA_NO_EDGE_FLT);
+      const int corner = ref[N2];
+#pragma unroll
+      for (int j = 0; j < S; j++)
+      {
+        const int i = lane + 32 * j;
+        if (N * N >= 32 || i < N * N)
+        {
+          const int y = i >> LG, x = i & (N - 1);
+          const int yy = ver ? y : x, xx = ver ? x : y;
+          int v = ref[N2 + sgn * (xx + 1)];
+          if (edge && xx == 0) v = clip3i(0, maxv, v + ((ref[N2 - sgn * (yy + 1)] - corner) >> 1));
+          EMIT(i, y, x, v);
+        }
+      }
+    }
+    else if (angle > 0)
+    {
+#pragma unroll
+      for (int j = 0; j < S; j++)
+      {
+        const int i = lane + 32 * j;
+        if (N * N >= 32 || i < N * N)
+        {
+          const int y = i >> LG, x = i & (N - 1);
+          const int yy = ver ? y : x, xx = ver ? x : y;
+          const int pos = (yy + 1) * angle, di = pos >> 5, df = pos & 31;
+          const int k = xx + di + 1;
+          const int a = ref[N2 + sgn * k], b = ref[N2 + sgn * (k + 1)];     // df == 0: b has weight 0 (index <= 2N+... stays inside the line)
+          const int v = ((32 - df) * a + df * b + 16) >> 5;
+          EMIT(i, y, x, v);
+        }
+      }
+    }
+    else
+    {
+      const int inv = c_invTab[aa];
+      // negative angle: rm[k < 0] is the side edge projected onto the main edge: side sample ((128 - k*inv) >> 8) - 1  (TComPrediction.cpp:396-404)
+#pragma unroll
+      for (int j = 0; j < S; j++)
+      {
+        const int i = lane + 32 * j;
+        if (N * N >= 32 || i < N * N)
+        {
+          const int y = i >> LG, x = i & (N - 1);
+          const int yy = ver ? y : x, xx = ver ? x : y;
+          const int pos = (yy + 1) * angle, di = pos >> 5, df = pos & 31;
+          const int k0 = xx + di + 1, k1 = k0 + 1;
+          const int i0 = k0 >= 0 ? N2 + sgn * k0 : N2 - sgn * ((128 - k0 * inv) >> 8);
+          const int i1 = k1 >= 0 ? N2 + sgn * k1 : N2 - sgn * ((128 - k1 * inv) >> 8);
+          const int a = ref[i0], b = ref[i1];
+          const int v = ((32 - df) * a + df * b + 16) >> 5;
+          EMIT(i, y, x, v);
+        }
+      }
+    }
+  }
+#undef LEFT
+#undef TOP
+#undef EMIT
+}
+
+__global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant__ FrameParams P, const int resSamples)
+{
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  int16_t* s_tile = (int16_t*)s_dyn;                                         // IN_TILE (+ pad to 16 bytes)
+  int16_t* s_res = s_tile + ((IN_TILE + 7) & ~7);                            // residuals of this CTU, compact layout relative to minoff
+  hmr_intra* s_rec = (hmr_intra*)(s_res + resSamples);                       // [2][IN_MAXREC]
+  uint16_t* s_addr = (uint16_t*)(s_rec + 2 * IN_MAXREC);                     // [2][IN_ADDR]
+  __shared__ int s_lineBuf[4 * 32 + 8];   // unfiltered reference line: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right
+  __shared__ int s_fltBuf[4 * 32 + 8];    // smoothed
+  int* const s_line = s_lineBuf + 2;      // indices -1 and 4N+1 are touched (with weight 0) by the 45-degree modes
+  int* const s_flt = s_fltBuf + 2;
   __shared__ uint32_t s_first[IN_MAXCOLS];
   __shared__ uint16_t s_count[IN_MAXCOLS];
-  __shared__ unsigned s_minoff;
+  __shared__ unsigned s_minoff[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int comp = blockIdx.x / P.ctus_h, row = blockIdx.x % P.ctus_h;
   if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) return;
@@ -71,15 +284,18 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   const unsigned long long base = P.epoch << 32;
 
   const int bd = comp ? P.hdr.bit_depth_chroma : P.hdr.bit_depth_luma;
-  const int maxv = (1 << bd) - 1;
   const int csx = comp ? P.csx : 0, csy = comp ? P.csy : 0;
-  const int uw = 4 >> csx, uh = 4 >> csy;
-  const int CTW = (1 << P.hdr.log2_ctu) >> csx, CTH = (1 << P.hdr.log2_ctu) >> csy;
+  IntraGeom g;
+  g.CTW = (1 << P.hdr.log2_ctu) >> csx; g.CTH = (1 << P.hdr.log2_ctu) >> csy;
+  g.uws = 2 - csx; g.uhs = 2 - csy; g.gw = g.CTW >> 2;
+  g.oy = row * g.CTH; g.ox = 0;
+  const int CTW = g.CTW, CTH = g.CTH;
   const int W = P.w[comp], H = P.h[comp];
   const int ctusW = P.ctus_w;
+  const bool strongAllowed = P.hdr.flags & HMR_FRM_STRONG_INTRA_SMOOTHING;
   int16_t* plane = P.work.p[comp];
   const int pitch = P.work.pitch[comp];
-#define T(y, x) s_tile[((y) + 1) * IN_LD + 8 + (x)]
+#define T(y, x) s_tile[TIDX(y, x)]
 
   for (int c = tid; c < ctusW; c += IN_THREADS)
   {
@@ -87,16 +303,36 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
     s_first[c] = rg.first[comp];
     s_count[c] = (uint16_t)min(rg.count[comp], (uint32_t)IN_MAXREC);
   }
-  if (tid == 0) s_minoff = 0xffffffffu;
+  if (tid == 0) { s_minoff[0] = s_minoff[1] = 0xffffffffu; s_tile[0] = (int16_t)(1 << (bd - 1)); }
   __syncthreads();
 
   int c = next_intra_ctu(s_count, 0, ctusW, lane);
   if (tid == 0) *(volatile unsigned long long*)myProg = base + (unsigned long long)c;   // nothing to do before CTU c
+  if (c >= ctusW) return;
+
+  // prologue: records + address tables of the first intra CTU into buffer 0 (all warps)
+  int buf = 0;
+  {
+    const int count = s_count[c];
+    const uint32_t first = s_first[c];
+    for (int i = tid; i < count; i += IN_THREADS)
+    {
+      const uint4 rec = __ldcg((const uint4*)(P.intra + first) + i);
+      ((uint4*)s_rec)[i] = rec;
+      if (rec.w != HMR_NO_OFFSET) atomicMin(&s_minoff[0], rec.w);
+    }
+    __syncthreads();
+    g.ox = c * CTW;
+    for (int k = warp; k < count; k += IN_THREADS / 32) intra_addr_table(s_rec[k], s_addr + intra_slot(s_rec[k], g), g, lane);
+    __syncthreads();
+  }
 
   while (c < ctusW)
   {
-    const uint32_t first = s_first[c];
     const int count = s_count[c];
+    hmr_intra* rec = s_rec + buf * IN_MAXREC;
+    uint16_t* addrTab = s_addr + buf * IN_ADDR;
+    const int cn = next_intra_ctu(s_count, c + 1, ctusW, lane);           // next CTU with intra TUs in this row
     if (upProg)
     {
       if (tid == 0)
@@ -110,7 +346,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
     const int ox = c * CTW, oy = row * CTH;                 // CTU origin in this component
     const int cw = min(CTW, W - ox), ch = min(CTH, H - oy); // part inside the picture
 
-    // ---- stage 1: tile interior (async), records, row above, column to the left: all loads in flight together ----
+    // ---- stage: tile interior + residuals (async), row above, column to the left, next CTU's records ----
     if ((cw & 7) == 0)
     {
       const int vecPerRow = cw >> 3;
@@ -129,178 +365,67 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
         cp_async8(&T(y, 4 * v), plane + (size_t)(oy + y) * pitch + ox + 4 * v);
       }
     }
+    const unsigned minoff = s_minoff[buf];
+    for (int k = warp; k < count; k += IN_THREADS / 32)
+    {
+      const uint32_t off = rec[k].resid_off;
+      if (off == HMR_NO_OFFSET) continue;
+      const int units = 1 << (2 * rec[k].log2_size - 3);     // N*N int16 in 16-byte units
+      const uint32_t rel = off - minoff;
+      if (rel + 8u * units > (uint32_t)resSamples) continue; // cannot happen for a well-formed frame (one CTU's levels are contiguous)
+      for (int u = lane; u < units; u += 32) cp_async16(s_res + rel + 8 * u, P.resid + off + 8 * u);
+    }
     {
       uint4 rec0 = make_uint4(0, 0, 0, 0), rec1 = rec0;
       int top = 0, left = 0;
       const int gx = ox + tid - 1;
       const bool hasTop = oy > 0 && tid < CTW + 33 && gx >= 0 && gx < W;
       const bool hasLeft = ox > 0 && tid < ch;
-      if (tid < count) rec0 = __ldcg((const uint4*)(P.intra + first) + tid);
-      if (tid + IN_THREADS < count) rec1 = __ldcg((const uint4*)(P.intra + first) + tid + IN_THREADS);
+      const int countN = cn < ctusW ? (int)s_count[cn] : 0;
+      const uint32_t firstN = cn < ctusW ? s_first[cn] : 0;
+      if (tid < countN) rec0 = __ldcg((const uint4*)(P.intra + firstN) + tid);
+      if (tid + IN_THREADS < countN) rec1 = __ldcg((const uint4*)(P.intra + firstN) + tid + IN_THREADS);
       if (hasTop) top = __ldcg(plane + (size_t)(oy - 1) * pitch + gx);
       if (hasLeft) left = __ldcg(plane + (size_t)(oy + tid) * pitch + ox - 1);
-      if (tid < count) { ((uint4*)s_rec)[tid] = rec0; if (rec0.w != HMR_NO_OFFSET) atomicMin(&s_minoff, rec0.w); }
-      if (tid + IN_THREADS < count) { ((uint4*)s_rec)[tid + IN_THREADS] = rec1; if (rec1.w != HMR_NO_OFFSET) atomicMin(&s_minoff, rec1.w); }
+      uint4* recN = (uint4*)(s_rec + (buf ^ 1) * IN_MAXREC);
+      if (tid < countN) { recN[tid] = rec0; if (rec0.w != HMR_NO_OFFSET) atomicMin(&s_minoff[buf ^ 1], rec0.w); }
+      if (tid + IN_THREADS < countN) { recN[tid + IN_THREADS] = rec1; if (rec1.w != HMR_NO_OFFSET) atomicMin(&s_minoff[buf ^ 1], rec1.w); }
       if (hasTop) T(-1, tid - 1) = (int16_t)top;
       if (hasLeft) T(tid, -1) = (int16_t)left;
     }
-    __syncthreads();
-    // ---- stage 2: residuals of this CTU's TUs, compact layout (one warp per TU, 16-byte async copies) ----
-    const unsigned minoff = s_minoff;
-    for (int k = warp; k < count; k += IN_THREADS / 32)
-    {
-      const uint32_t off = s_rec[k].resid_off;
-      if (off == HMR_NO_OFFSET) continue;
-      const int units = 1 << (2 * s_rec[k].log2_size - 3);   // N*N int16 in 16-byte units
-      const uint32_t rel = off - minoff;
-      if (rel + 8u * units > (uint32_t)IN_MAXRES) continue;  // cannot happen for a well-formed frame (one CTU's levels are contiguous)
-      for (int u = lane; u < units; u += 32) cp_async16(s_res + rel + 8 * u, P.resid + off + 8 * u);
-    }
     cp_async_wait_all();
     __syncthreads();
-    if (tid == 0) s_minoff = 0xffffffffu;                    // everybody holds `minoff`; next use is two barriers away
 
-    // ---- the dependent chain: one warp, one TU after the other, shared memory only ----
     if (warp == 0)
     {
+      // ---- the dependent chain: one warp, one TU after the other, shared memory only ----
+      if (lane == 0) s_minoff[buf] = 0xffffffffu;            // consumed; this buffer is refilled two CTUs from now
+      g.ox = ox;
       for (int k = 0; k < count; k++)
       {
-        const hmr_intra r = s_rec[k];
-        const int lg = r.log2_size, N = 1 << lg, N2 = 2 * N, L = 4 * N + 1;
+        const hmr_intra r = rec[k];
+        const uint16_t* a = addrTab + intra_slot(r, g);
+        const int16_t* res = s_res + (r.resid_off != HMR_NO_OFFSET ? r.resid_off - minoff : 0u);
         const int x0 = r.x - ox, y0 = r.y - oy;
-        // reference samples with substitution (TComPattern.cpp:309-520), unit-granular availability
-        const int nl = N / uh, na = N / uw;
-        unsigned long long M = 0;                             // bit u = unit u available, units in line order
-        M |= (unsigned long long)(__brev((unsigned)r.avail_below_left) >> (32 - nl));
-        M |= (unsigned long long)(__brev((unsigned)r.avail_left) >> (32 - nl)) << nl;
-        if (r.flags & HMR_INTRA_AVAIL_CORNER) M |= 1ull << (2 * nl);
-        M |= (unsigned long long)r.avail_above << (2 * nl + 1);
-        M |= (unsigned long long)r.avail_above_right << (2 * nl + 1 + na);
-        for (int i = lane; i < L; i += 32)
+        switch (r.log2_size)
         {
-          int v;
-          if (M == 0) v = 1 << (bd - 1);
-          else
-          {
-            const int u = i < N2 ? i / uh : (i == N2 ? 2 * nl : 2 * nl + 1 + (i - N2 - 1) / uw);
-            int src = i;
-            if (!((M >> u) & 1))
-            {
-              const unsigned long long lower = M & ((1ull << u) - 1);
-              if (lower)
-              {
-                const int p = 63 - __clzll((long long)lower);                 // nearest available unit before: its LAST sample
-                src = p < 2 * nl ? (p + 1) * uh - 1 : (p == 2 * nl ? N2 : N2 + (p - 2 * nl) * uw);
-              }
-              else
-              {
-                const int q = __ffsll((long long)M) - 1;                      // first available unit after: its FIRST sample
-                src = q < 2 * nl ? q * uh : (q == 2 * nl ? N2 : N2 + 1 + (q - 2 * nl - 1) * uw);
-              }
-            }
-            if (src < N2)       v = T(min(y0 + N2 - 1 - src, CTH - 1), x0 - 1);
-            else if (src == N2) v = T(y0 - 1, x0 - 1);
-            else                v = T(y0 - 1, min(x0 + (src - N2 - 1), CTW + 31));
-          }
-          s_line[i] = v;
+          case 2:  intra_tu<2>(r, a, s_tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
+          case 3:  intra_tu<3>(r, a, s_tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
+          case 4:  intra_tu<4>(r, a, s_tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
+          default: intra_tu<5>(r, a, s_tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
         }
-        __syncwarp();
-        const int* ref = s_line;
-        if (r.flags & HMR_INTRA_FILTER_REFS)
-        {
-          const int bl = s_line[0], tl = s_line[N2], tr = s_line[4 * N];
-          bool strong = (r.flags & HMR_INTRA_LUMA_RULES) && (P.hdr.flags & HMR_FRM_STRONG_INTRA_SMOOTHING) && N >= 32;
-          if (strong)
-          {
-            const int thr = 1 << (bd - 5);
-            strong = abs(bl + tl - 2 * s_line[N]) < thr && abs(tl + tr - 2 * s_line[3 * N]) < thr;
-          }
-          for (int i = lane; i < L; i += 32)
-          {
-            int v;
-            if (i == 0 || i == 4 * N) v = s_line[i];
-            else if (strong)
-            {
-              const int sh = lg + 1;
-              v = i < N2 ? ((N2 - i) * bl + i * tl + N) >> sh : (i == N2 ? tl : ((N2 - (i - N2)) * tl + (i - N2) * tr + N) >> sh);
-            }
-            else v = (s_line[i - 1] + 2 * s_line[i] + s_line[i + 1] + 2) >> 2;
-            s_flt[i] = v;
-          }
-          ref = s_flt;
-          __syncwarp();
-        }
-#define LEFT(y) ref[N2 - 1 - (y)]
-#define TOP(x)  ref[N2 + 1 + (x)]
-        const int mode = r.mode;
-        const bool lumaRules = r.flags & HMR_INTRA_LUMA_RULES;
-        const bool hasRes = r.resid_off != HMR_NO_OFFSET;
-        const int16_t* res = s_res + (hasRes ? r.resid_off - minoff : 0u);
-        int dc = 0, angle = 0;
-        bool ver = true;
-        if (mode == 1)
-        {
-          const int part = lane < N ? TOP(lane) + LEFT(lane) : 0;
-          dc = (__reduce_add_sync(0xffffffffu, part) + N) >> (lg + 1);
-        }
-        else if (mode >= 2)
-        {
-          ver = mode >= 18;
-          const int am = ver ? mode - 26 : -(mode - 10);
-          const int aa = abs(am);
-          angle = am < 0 ? -c_angTab[aa] : c_angTab[aa];
-          const int inv = c_invTab[aa];
-          const int last = (N * angle) >> 5;
-          // main reference rm[-N..2N] (stored at +32): rm[0] = corner, rm[i>0] = main edge, rm[i<0] = projected side edge
-          for (int i = lane - 32; i <= N2; i += 32)
-          {
-            if (i >= 0) { if (angle < 0 && i > N) continue; s_rm[32 + i] = ver ? TOP(i - 1) : LEFT(i - 1); }
-            else if (angle < 0 && i > last)
-            {
-              const int sidx = ((128 + (-i) * inv) >> 8) - 1;
-              s_rm[32 + i] = ver ? LEFT(sidx) : TOP(sidx);
-            }
-          }
-          __syncwarp();
-        }
-        const bool edge = lumaRules && N <= 16 && !(r.flags & HMR_INTRA_NO_EDGE_FLT);
-        for (int i = lane; i < N * N; i += 32)
-        {
-          const int y = i >> lg, x = i & (N - 1);
-          int v;
-          if (mode == 0)
-            v = ((N - 1 - x) * LEFT(y) + (x + 1) * TOP(N) + (N - 1 - y) * TOP(x) + (y + 1) * LEFT(N) + N) >> (lg + 1);
-          else if (mode == 1)
-          {
-            v = dc;
-            if (lumaRules && N <= 16)
-            {
-              if (x == 0 && y == 0) v = (TOP(0) + LEFT(0) + 2 * dc + 2) >> 2;
-              else if (y == 0) v = (TOP(x) + 3 * dc + 2) >> 2;
-              else if (x == 0) v = (LEFT(y) + 3 * dc + 2) >> 2;
-            }
-          }
-          else
-          {
-            const int yy = ver ? y : x, xx = ver ? x : y;       // coordinates in the (possibly transposed) prediction frame
-            const int pos = (yy + 1) * angle, di = pos >> 5, df = pos & 31;
-            const int* rm = s_rm + 32;
-            if (angle == 0)
-            {
-              v = rm[xx + 1];
-              if (edge && xx == 0) v = clip3i(0, maxv, v + (((ver ? LEFT(yy) : TOP(yy)) - ref[N2]) >> 1));
-            }
-            else if (df) v = ((32 - df) * rm[xx + di + 1] + df * rm[xx + di + 2] + 16) >> 5;
-            else v = rm[xx + di + 1];
-          }
-          v = (int16_t)v;
-          const int rr = hasRes ? res[i] : 0;
-          T(y0 + y, x0 + x) = (int16_t)clip3i(0, maxv, v + rr);
-        }
-#undef LEFT
-#undef TOP
-        __syncwarp();        // this TU's samples are in the tile before the next TU builds its reference line
+        __syncwarp();        // this TU's samples are in the tile before the next TU gathers its reference line
       }
+    }
+    else if (cn < ctusW)
+    {
+      // ---- helpers: address tables of the next intra CTU (records were staged above) ----
+      IntraGeom gn = g;
+      gn.ox = cn * CTW;
+      const hmr_intra* recN = s_rec + (buf ^ 1) * IN_MAXREC;
+      uint16_t* addrN = s_addr + (buf ^ 1) * IN_ADDR;
+      const int countN = s_count[cn];
+      for (int k = warp - 1; k < countN; k += IN_THREADS / 32 - 1) intra_addr_table(recN[k], addrN + intra_slot(recN[k], gn), gn, lane);
     }
     __syncthreads();
     // ---- write the CTU back (inter samples are rewritten with the values they had) ----
@@ -322,7 +447,8 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
         *((uint2*)(plane + (size_t)(oy + y) * pitch + ox) + v) = *(const uint2*)&T(y, 4 * v);
       }
     }
-    c = next_intra_ctu(s_count, c + 1, ctusW, lane);
+    c = cn;
+    buf ^= 1;
     __syncthreads();
     if (tid == 0)
     {
@@ -333,10 +459,22 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
 #undef T
 }
 
+static int intra_res_samples(const FrameParams& P)
+{
+  const int ct = 1 << P.hdr.log2_ctu;
+  return ct * ct + 2 * ((ct >> P.csx) * (ct >> P.csy));
+}
+static size_t intra_dyn_smem(int resSamples)
+{
+  return (size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + 2 * IN_MAXREC * sizeof(hmr_intra) + 2 * IN_ADDR * sizeof(uint16_t);
+}
+
 int intra_max_coresident_blocks(int device)
 {
   int perSm = 0, sms = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, intra_kernel, IN_THREADS, 0);
+  const size_t worst = intra_dyn_smem(3 * IN_MAXCT * IN_MAXCT);
+  cudaFuncSetAttribute(intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, intra_kernel, IN_THREADS, worst);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   return perSm * sms;
 }
@@ -345,6 +483,7 @@ cudaError_t launch_intra(const FrameParams& P, cudaStream_t s)
 {
   if (P.hdr.n_intra == 0) return cudaSuccess;
   if (P.ctus_w > IN_MAXCOLS) return cudaErrorInvalidValue;
-  void* args[] = { (void*)&P };
-  return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(3 * P.ctus_h), dim3(IN_THREADS), args, 0, s);
+  int resSamples = intra_res_samples(P);
+  void* args[] = { (void*)&P, (void*)&resSamples };
+  return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(3 * P.ctus_h), dim3(IN_THREADS), args, intra_dyn_smem(resSamples), s);
 }
