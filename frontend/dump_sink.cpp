@@ -19,7 +19,9 @@
 class DumpSink : public HmFrameSink
 {
 public:
-  explicit DumpSink(const char* path) : m_fp(fopen(path, "wb")), m_planes(getenv("HMDUMP_PLANES") != NULL)
+  // HMDUMP_RECORDS_ONLY=1: the product's fast parse path (no HM reconstruction, coefficient hygiene on), records only —
+  // lets a CPU-only test prove that the fast path emits byte-identical records.
+  explicit DumpSink(const char* path) : m_fp(fopen(path, "wb")), m_planes(getenv("HMDUMP_PLANES") != NULL), m_recordsOnly(getenv("HMDUMP_RECORDS_ONLY") != NULL)
   {
     if (!m_fp) { perror(path); abort(); }
     fwrite("HMRDUMP1", 1, 8, m_fp);
@@ -54,10 +56,11 @@ public:
     if (d.bs) section(TAG('B','S',' ',' '), d.bs, nbs);
     section(TAG('Q','P',' ',' '), d.qp, nqp);
     if (d.cu_flags) section(TAG('C','U','F','L'), d.cu_flags, nqp);
+    if (m_recordsOnly) { section(TAG('E','N','D',' '), NULL, 0); fflush(m_fp); }
   }
 
   virtual void fetchPicture(TComPic*) {}
-  virtual bool wantHmRecon() const { return true; }
+  virtual bool wantHmRecon() const { return !m_recordsOnly; }
 
   virtual void hmStage(int stage, TComPic* pic)
   {
@@ -87,7 +90,7 @@ public:
 
 private:
   FILE* m_fp;
-  bool m_planes;
+  bool m_planes, m_recordsOnly;
   unsigned char m_gold[3][48];
 };
 

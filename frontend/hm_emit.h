@@ -45,6 +45,7 @@ public:
   HmFrameSink* sink() { return m_sink; }
   int  slotOf(TComPic* pic);
   const char* unsupported() const { return m_unsupported; }
+  bool cleanCoeffs() const { return m_cleanCoeffs; }
 
 private:
   struct CuCtx;
@@ -80,6 +81,7 @@ private:
   std::vector<int8_t>              m_qp;
   std::vector<uint8_t>             m_cuFlags;
   int m_bsStride, m_qpStride;
+  bool m_cleanCoeffs;                      // hm_fast.cpp: clear coded coefficient blocks after copying them
   double m_tCtu, m_tBs, m_tPic, m_tSink;   // HMDEC_B200_STATS: host time spent emitting records
   int m_nPic;
 };

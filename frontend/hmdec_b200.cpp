@@ -32,6 +32,7 @@
 #include "TLibDecoder/NALread.h"
 #include "libHMDecoder_api.h"
 #include "hm_emit.h"
+#include "hm_fast.h"
 
 // HM keeps the "hash mismatch seen" flag in a global that the application must define (TDecGop.cpp:48).
 bool g_md5_mismatch = false;
@@ -208,6 +209,7 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
   read(nalu, bytes);                                   // NALread.cpp:144-154
 
   hm_emit_set_current(d->emitter);
+  hm_fast_set_clean_coeffs(d->emitter->cleanCoeffs());
   bNewPicture = false;
   if (!(d->maxTemporalLayer >= 0 && (int)nalu.m_temporalId > d->maxTemporalLayer))
   {
@@ -232,6 +234,7 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
     d->loopFilterDone = (nalu.m_nalUnitType == NAL_UNIT_EOS);
   }
   hm_emit_set_current(NULL);
+  hm_fast_set_clean_coeffs(false);
 
   checkOutputPictures = false;
   d->flushing = false;
