@@ -60,8 +60,8 @@ struct HmEmitter::CuCtx
 HmEmitter::HmEmitter(HmFrameSink* sink)
   : m_sink(sink), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0), m_tCtu(0), m_tBs(0), m_tPic(0), m_tSink(0), m_nPic(0)
 {
-  // HMDEC_B200_KEEP_COEFF=1: keep HM's per-picture coefficient storage intact for libHMDEC_get_internal_info(TU_COEFF_ENERGY_*)
-  m_cleanCoeffs = !sink->wantHmRecon() && getenv("HMDEC_B200_KEEP_COEFF") == NULL;
+  // product path: HM's whole-CTU coefficient zero fills are skipped (hm_fast.cpp); verification / golden generation keep them
+  m_cleanCoeffs = !sink->wantHmRecon();
   memset(&m_hdr, 0, sizeof(m_hdr));
 }
 
@@ -271,8 +271,6 @@ uint32_t HmEmitter::emitResidualTU(CuCtx& c, int compIdx, void* pTu, bool intra,
       TCoeff v = src[i];
       dst[i] = (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v));
     }
-    // coefficient hygiene (hm_fast.cpp): HM's per-CTU zero fill is skipped, so leave the block as HM expects to find it
-    if (m_cleanCoeffs) memset((void*)src, 0, sizeof(TCoeff) * N * N);
   }
   else memset(dst, 0, sizeof(int16_t) * N * N);
 

@@ -6,6 +6,8 @@
 #define HM_EMIT_H
 
 #include <stdint.h>
+#include <cstdio>
+#include <string>
 #include <vector>
 #include <map>
 #include "hmr_records.h"
@@ -32,6 +34,17 @@ struct HmFrameSink
   virtual void hmStage(int stage, TComPic* pic) { (void)stage; (void)pic; }
   // SEI hash methods that parallelise (2 = CRC, 3 = checksum) computed where the picture lives; false = not available.
   virtual bool deviceHash(TComPic* pic, int method, uint32_t out[3]) { (void)pic; (void)method; (void)out; return false; }
+  // SEI MD5 checked asynchronously where the picture lives: `expected` = 16 bytes per component, `line` = the status line
+  // up to the hash field.  The sink prints the completed line (unless quiet) and records a mismatch when the digest
+  // arrives; lines keep their order.  false = not available (the caller hashes on the host).
+  virtual bool asyncMd5(TComPic* pic, const unsigned char* expected, int ncomp, const std::string& line, bool quiet) { (void)pic; (void)expected; (void)ncomp; (void)line; (void)quiet; return false; }
+  // A finished status line that must not overtake lines still waiting for their digest.
+  virtual void orderedPrint(const std::string& line) { fputs(line.c_str(), stdout); }
+  // Deliver digests that have arrived (wait = true: all of them).
+  virtual void drainHashes(bool wait) { (void)wait; }
+  virtual bool hashMismatchSeen() const { return false; }
+  // Called before HM's picture buffers are freed (the sink may hold page-locks on them).
+  virtual void releaseHostBuffers() {}
 };
 
 class HmEmitter
@@ -81,7 +94,7 @@ private:
   std::vector<int8_t>              m_qp;
   std::vector<uint8_t>             m_cuFlags;
   int m_bsStride, m_qpStride;
-  bool m_cleanCoeffs;                      // hm_fast.cpp: clear coded coefficient blocks after copying them
+  bool m_cleanCoeffs;                      // hm_fast.cpp: HM's whole-CTU coefficient zero fills are skipped for this decoder
   double m_tCtu, m_tBs, m_tPic, m_tSink;   // HMDEC_B200_STATS: host time spent emitting records
   int m_nPic;
 };

@@ -5,16 +5,20 @@
 // (TComDataCU::create, TComDataCU.cpp:173, and TComDataCU::initCU, :453) — together ~100 MB of cold memset per 2160p
 // picture, about 45 % of the parser's run time.  Neither is needed once reconstruction lives on the GPU:
 //
-//  * hm_fast_memset: frontend/Makefile compiles TComDataCU.cpp with -Dmemset=hm_fast_memset.  While the calling thread
-//    has "coefficient hygiene" on (hm_fast_set_clean_coeffs), zero-fills of >= 4 KB — only the coefficient arrays are
-//    that large — are skipped; the invariant "coefficient storage is all zero between pictures" is kept instead by the
-//    record emitter, which clears each coded TU's levels right after copying them (hm_emit.cpp, cache-warm).
+//  * hm_fast_memset: frontend/Makefile force-includes hm_fast_memset.h into TComDataCU.cpp.  While the calling thread
+//    runs the product path (hm_fast_set_skip_coeff_fill), zero-fills of >= 4 KB — only the coefficient arrays are that
+//    large — are skipped, at creation and per CTU: the pages are never even touched.  What the parser really needs,
+//    "the block I am about to parse is zero" (TDecSbac::parseCoeffNxN writes only the scanned positions), is
+//    provided by a one-line build-time patch of parseCoeffNxN (frontend/Makefile) that zeroes exactly that block.
+//    Coefficient blocks of TUs without coded levels are therefore undefined; every consumer checks the cbf first.
 //  * TDecTop::xGetNewPicBuffer (frontend/Makefile renames HM's own definition): same buffer selection rule as HM, but
 //    a picture buffer of unchanged geometry is RESET (slices, SEIs, flags) instead of destroyed and re-created.  HM's
 //    per-CTU state is fully re-initialised by TComDataCU::initCU for every CTU of every picture anyway.
 //
-// Plane pointers of a DPB entry therefore stay stable for the life of the decoder, which is what lets gpu_sink.cpp
-// page-lock them once and have the GPU DMA finished pictures straight into them.
+//  * sample planes: a sink may install an allocator (hm_fast_set_plane_allocator); the planes of every picture buffer
+//    then come from it instead of malloc.  gpu_sink.cpp hands out page-locked memory from a process-wide pool, so the
+//    GPU DMAs finished pictures straight into the planes libHMDEC_get_image_plane returns, with no per-decoder
+//    registration cost.  Plane pointers of a DPB entry stay stable for the life of the decoder.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -32,6 +36,7 @@
 #include <map>
 #include <set>
 #include <deque>
+#include <mutex>
 #define private public
 #define protected public
 #include "TLibCommon/TComPic.h"
@@ -41,24 +46,122 @@
 #undef protected
 #include "hm_fast.h"
 
-static thread_local bool t_cleanCoeffs = false;    // emitter keeps coefficient storage zero between pictures
-static thread_local bool t_creating = false;       // inside TComPic::create: HM's initial zero-fill must happen
+static thread_local bool t_skipCoeffFill = false;
 
-void hm_fast_set_clean_coeffs(bool on) { t_cleanCoeffs = on; }
-bool hm_fast_clean_coeffs() { return t_cleanCoeffs; }
+void hm_fast_set_skip_coeff_fill(bool on) { t_skipCoeffFill = on; }
 
 extern "C" void* hm_fast_memset(void* p, int v, size_t n)
 {
-  if (v == 0 && n >= 4096 && t_cleanCoeffs && !t_creating) return p;
+  if (v == 0 && n >= 4096 && t_skipCoeffFill) return p;
   return memset(p, v, n);
+}
+
+// ---- sample planes from a caller-provided (page-locked) allocator -------------------------------------------------
+static HmPlaneAlloc g_planeAlloc = NULL;
+static HmPlaneFree  g_planeFree = NULL;
+static std::mutex g_planeLock;
+static std::set<void*> g_planeOwned;       // plane buffers that came from g_planeAlloc (any decoder of the process)
+
+void hm_fast_set_plane_allocator(HmPlaneAlloc a, HmPlaneFree f)
+{
+  std::lock_guard<std::mutex> g(g_planeLock);
+  g_planeAlloc = a; g_planeFree = f;
+}
+
+bool hm_fast_plane_is_pinned(const void* buf)
+{
+  std::lock_guard<std::mutex> g(g_planeLock);
+  return g_planeOwned.count((void*)buf) != 0;
+}
+
+// Swap the malloc'ed planes of a freshly created TComPicYuv for allocator-owned ones (same size, same origin offset).
+static void adoptPlanes(TComPicYuv* yuv)
+{
+  if (!g_planeAlloc || !yuv) return;
+  for (UInt c = 0; c < yuv->getNumberValidComponents(); c++)
+  {
+    const ComponentID id = ComponentID(c);
+    Pel* old = yuv->m_apiPicBuf[c];
+    if (!old) continue;
+    const size_t bytes = (size_t)yuv->getStride(id) * yuv->getTotalHeight(id) * sizeof(Pel);
+    Pel* fresh = (Pel*)g_planeAlloc(bytes);
+    if (!fresh) continue;
+    const ptrdiff_t org = yuv->m_piPicOrg[c] - old;
+    xFree(old);
+    yuv->m_apiPicBuf[c] = fresh;
+    yuv->m_piPicOrg[c] = fresh + org;
+    std::lock_guard<std::mutex> g(g_planeLock);
+    g_planeOwned.insert(fresh);
+  }
+}
+
+// Give allocator-owned planes back before HM frees the picture (TComPicYuv::destroy would free() them).
+static void releasePlanes(TComPicYuv* yuv)
+{
+  if (!yuv) return;
+  for (UInt c = 0; c < MAX_NUM_COMPONENT; c++)
+  {
+    Pel* p = yuv->m_apiPicBuf[c];
+    if (!p) continue;
+    bool owned;
+    { std::lock_guard<std::mutex> g(g_planeLock); owned = g_planeOwned.erase(p) != 0; }
+    if (!owned) continue;
+    if (g_planeFree) g_planeFree(p);
+    yuv->m_apiPicBuf[c] = NULL;
+    yuv->m_piPicOrg[c] = NULL;
+  }
+}
+
+// Every picture buffer a decoder ever created.  The wrapper's flush (like the reference's, libHMDecoder.cpp:329-336) only
+// drops the pointers from the DPB list; without this registry those pictures would be lost and never reused.
+static std::mutex g_createdLock;
+static std::map<TDecTop*, std::vector<TComPic*> > g_created;
+
+static void remember(TDecTop* dec, TComPic* pic)
+{
+  std::lock_guard<std::mutex> g(g_createdLock);
+  g_created[dec].push_back(pic);
+}
+
+// A picture of this decoder that is no longer in its DPB list (dropped by a flush), or NULL.
+static TComPic* findOrphan(TDecTop* dec, TComList<TComPic*>& list)
+{
+  std::lock_guard<std::mutex> g(g_createdLock);
+  std::vector<TComPic*>& v = g_created[dec];
+  for (size_t i = 0; i < v.size(); i++)
+  {
+    bool listed = false;
+    for (TComList<TComPic*>::iterator it = list.begin(); it != list.end() && !listed; ++it) listed = (*it == v[i]);
+    if (!listed) return v[i];
+  }
+  return NULL;
+}
+
+void hm_fast_release_decoder(TDecTop* dec)
+{
+  std::vector<TComPic*> mine;
+  {
+    std::lock_guard<std::mutex> g(g_createdLock);
+    std::map<TDecTop*, std::vector<TComPic*> >::iterator it = g_created.find(dec);
+    if (it == g_created.end()) return;
+    mine.swap(it->second);
+    g_created.erase(it);
+  }
+  for (size_t i = 0; i < mine.size(); i++)
+  {
+    TComPic* pic = mine[i];
+    releasePlanes(pic->getPicYuvRec());
+    bool listed = false;
+    for (TComList<TComPic*>::iterator it = dec->m_cListPic.begin(); it != dec->m_cListPic.end() && !listed; ++it) listed = (*it == pic);
+    if (!listed) { pic->destroy(); delete pic; }           // HM's own teardown only knows the pictures still in its list
+  }
 }
 
 static void createPicture(TComPic* pic, TComSPS* sps, Window& conf, Window& disp, Int* reorder)
 {
-  t_creating = true;
   pic->create(sps->getPicWidthInLumaSamples(), sps->getPicHeightInLumaSamples(), sps->getChromaFormatIdc(),
               g_uiMaxCUWidth, g_uiMaxCUHeight, g_uiMaxCUDepth, conf, disp, reorder, true);
-  t_creating = false;
+  adoptPlanes(pic->getPicYuvRec());
 }
 
 static bool sameGeometry(TComPic* pic, TComSPS* sps)
@@ -98,8 +201,18 @@ Void TDecTop::xGetNewPicBuffer(TComSlice* pcSlice, TComPic*& rpcPic)
   m_iMaxRefPicNum = sps->getMaxDecPicBuffering(pcSlice->getTLayer());   // includes the picture being decoded
   if (m_cListPic.size() < (UInt)m_iMaxRefPicNum)
   {
-    rpcPic = new TComPic();
-    createPicture(rpcPic, sps, conf, disp, reorder);
+    rpcPic = findOrphan(this, m_cListPic);                   // a buffer the last flush dropped from the list
+    if (rpcPic && sameGeometry(rpcPic, sps))
+    {
+      rpcPic->setOutputMark(false); rpcPic->setReconMark(false);
+      resetPicture(rpcPic, conf, disp, reorder);
+    }
+    else
+    {
+      rpcPic = new TComPic();
+      createPicture(rpcPic, sps, conf, disp, reorder);
+      remember(this, rpcPic);
+    }
     m_cListPic.pushBack(rpcPic);
     return;
   }
@@ -119,12 +232,14 @@ Void TDecTop::xGetNewPicBuffer(TComSlice* pcSlice, TComPic*& rpcPic)
     rpcPic = new TComPic();
     m_cListPic.pushBack(rpcPic);
     createPicture(rpcPic, sps, conf, disp, reorder);
+    remember(this, rpcPic);
     return;
   }
   rpcPic = found;
   if (sameGeometry(rpcPic, sps)) resetPicture(rpcPic, conf, disp, reorder);
   else
   {
+    releasePlanes(rpcPic->getPicYuvRec());
     rpcPic->destroy();
     createPicture(rpcPic, sps, conf, disp, reorder);
   }

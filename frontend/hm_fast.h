@@ -1,7 +1,15 @@
 // hm_fast.h — switches of the allocation-/memset-free picture turnover (hm_fast.cpp)
 #ifndef HM_FAST_H
 #define HM_FAST_H
-// Per thread (= per decoder call): the emitter clears coded coefficient blocks after use, so HM's per-CTU zero fills are skipped.
-void hm_fast_set_clean_coeffs(bool on);
-bool hm_fast_clean_coeffs();
+#include <stddef.h>
+class TDecTop;
+// Per thread (= per decoder call): skip HM's whole-CTU coefficient zero fills (parseCoeffNxN zeroes what it parses).
+void hm_fast_set_skip_coeff_fill(bool on);
+// Process-wide: where the sample planes of HM's picture buffers come from (NULL = malloc, HM's default).
+typedef void* (*HmPlaneAlloc)(size_t bytes);
+typedef void  (*HmPlaneFree)(void* p);
+void hm_fast_set_plane_allocator(HmPlaneAlloc a, HmPlaneFree f);
+bool hm_fast_plane_is_pinned(const void* planeBuffer);
+// Must run before TDecTop::destroy: hands allocator-owned planes back and frees picture buffers a flush dropped from the DPB list.
+void hm_fast_release_decoder(TDecTop* dec);
 #endif

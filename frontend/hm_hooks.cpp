@@ -5,6 +5,7 @@
 // (-DdecompressCU=decompressCU_hm, -DfilterPicture=filterPicture_hm); the definitions below take their
 // place at link time.  HM's sources are not modified.
 #include <cstdio>
+#include <cstdarg>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -39,37 +40,52 @@ Void TDecCu::decompressCU(TComDataCU* pcCU)
   if (e->sink()->wantHmRecon()) hm_call_original_decompressCU(this, pcCU);
 }
 
-// Status line + SEI hash check, same text as TDecGop::filterPicture / calcAndPrintHashStatus (TDecGop.cpp:176-289)
+// Status line + SEI hash check, same text as TDecGop::filterPicture / calcAndPrintHashStatus (TDecGop.cpp:176-289).
+// MD5 (the default SEI method) is checked asynchronously on the device when the sink offers it: the line is completed
+// and printed by the sink when the digest arrives (lines keep their order).
+static void appendf(std::string& s, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  s += buf;
+}
+
 static void printStatusAndHash(TComPic* pic, TComSlice* slice, Int hashEnabled, HmEmitter* e, bool quiet)
 {
-#define P(...) do { if (!quiet) printf(__VA_ARGS__); } while (0)
+  std::string line;
   Char c = (slice->isIntra() ? 'I' : slice->isInterP() ? 'P' : 'B');
   if (!slice->isReferenced()) c += 32;
-  P("POC %4d TId: %1d ( %c-SLICE, QP%3d ) ", slice->getPOC(), slice->getTLayer(), c, slice->getSliceQp());
-  P("[DT %6.3f] ", 0.0);
+  appendf(line, "POC %4d TId: %1d ( %c-SLICE, QP%3d ) ", slice->getPOC(), slice->getTLayer(), c, slice->getSliceQp());
+  appendf(line, "[DT %6.3f] ", 0.0);
   for (Int l = 0; l < 2; l++)
   {
-    P("[L%d ", l);
-    for (Int i = 0; i < slice->getNumRefIdx(RefPicList(l)); i++) P("%d ", slice->getRefPOC(RefPicList(l), i));
-    P("] ");
+    appendf(line, "[L%d ", l);
+    for (Int i = 0; i < slice->getNumRefIdx(RefPicList(l)); i++) appendf(line, "%d ", slice->getRefPOC(RefPicList(l), i));
+    appendf(line, "] ");
   }
   if (hashEnabled)
   {
     SEIMessages hashes = getSeisByType(pic->getSEIs(), SEI::DECODED_PICTURE_HASH);
     const SEIDecodedPictureHash* hash = hashes.size() > 0 ? (SEIDecodedPictureHash*)*(hashes.begin()) : NULL;
-    if (hashes.size() > 1) P("Warning: Got multiple decoded picture hash SEI messages. Using first.");
+    if (hashes.size() > 1) appendf(line, "Warning: Got multiple decoded picture hash SEI messages. Using first.");
     TComDigest digest; Int numChar = 0; const Char* type = "\0";
     if (hash)
     {
       uint32_t dv[3];
+      const int ncomp = pic->getNumberValidComponents();
       const int method = hash->method == SEIDecodedPictureHash::CRC ? 2 : (hash->method == SEIDecodedPictureHash::CHECKSUM ? 3 : 1);
+      if (method == 1 && (int)hash->m_digest.hash.size() == 16 * ncomp && e->sink()->asyncMd5(pic, hash->m_digest.hash.data(), ncomp, line, quiet))
+        return;                                                    // the sink finishes the line
       if (method != 1 && e->sink()->deviceHash(pic, method, dv))
       {
         // CRC / checksum are computed on the device (no plane transfer); digest bytes are big-endian (TComPicYuvMD5.cpp:120-121,157-160)
         type = method == 2 ? "CRC" : "Checksum";
         numChar = method == 2 ? 2 : 4;
         digest.hash.clear();
-        for (int c = 0; c < pic->getNumberValidComponents(); c++)
+        for (int c = 0; c < ncomp; c++)
           for (int b = numChar - 1; b >= 0; b--) digest.hash.push_back((UChar)((dv[c] >> (8 * b)) & 0xff));
       }
       else
@@ -87,15 +103,15 @@ static void printStatusAndHash(TComPic* pic, TComSlice* slice, Int hashEnabled, 
     }
     const Char* ok = "(unk)"; Bool mismatch = false;
     if (hash) { ok = "(OK)"; if (digest != hash->m_digest) { ok = "(***ERROR***)"; mismatch = true; } }
-    P("[%s:%s,%s] ", type, digestToString(digest, numChar).c_str(), ok);
+    appendf(line, "[%s:%s,%s] ", type, digestToString(digest, numChar).c_str(), ok);
     if (mismatch)
     {
       g_md5_mismatch = true;
-      P("[rx%s:%s] ", type, digestToString(hash->m_digest, numChar).c_str());
+      appendf(line, "[rx%s:%s] ", type, digestToString(hash->m_digest, numChar).c_str());
     }
   }
-  P("\n");
-#undef P
+  line += "\n";
+  if (!quiet) e->sink()->orderedPrint(line);
 }
 
 Void TDecGop::filterPicture(TComPic*& rpcPic)
@@ -126,6 +142,8 @@ Void TDecGop::filterPicture(TComPic*& rpcPic)
   rpcPic->compressMotion();
   static const bool quiet = getenv("HMDEC_B200_QUIET") != NULL;   // the hash is still verified
   printStatusAndHash(rpcPic, slice, m_decodedPictureHashSEIEnabled, e, quiet);
+  e->sink()->drainHashes(false);
+  if (e->sink()->hashMismatchSeen()) g_md5_mismatch = true;
 
 #if SETTING_PIC_OUTPUT_MARK
   rpcPic->setOutputMark(rpcPic->getSlice(0)->getPicOutputFlag() ? true : false);

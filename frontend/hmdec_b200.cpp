@@ -87,6 +87,9 @@ struct Decoder
         if (it->second == this) g_picOwner.erase(it++); else ++it;
     }
     hm_emit_set_current(emitter);
+    sink->drainHashes(true);
+    sink->releaseHostBuffers();          // nothing may still be DMA-ing into HM's planes
+    hm_fast_release_decoder(&top);       // pooled planes go back; buffers dropped by a flush are freed
     top.destroy();
     hm_emit_set_current(NULL);
     delete emitter;
@@ -186,7 +189,14 @@ void libHMDec_set_max_temporal_layer(libHMDec_context* decCtx, int max_layer)
   if (decCtx) D(decCtx)->maxTemporalLayer = max_layer;
 }
 
-bool libHMDecB200_hash_mismatch(libHMDec_context* decCtx) { return decCtx ? D(decCtx)->hashMismatch : false; }
+bool libHMDecB200_hash_mismatch(libHMDec_context* decCtx)
+{
+  if (!decCtx) return false;
+  Decoder* d = D(decCtx);
+  d->sink->drainHashes(true);            // digests still in flight on the device
+  if (d->sink->hashMismatchSeen()) d->hashMismatch = true;
+  return d->hashMismatch;
+}
 const char* libHMDecB200_unsupported(libHMDec_context* decCtx) { return decCtx ? D(decCtx)->emitter->unsupported() : NULL; }
 
 libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data8, int length, bool eof, bool& bNewPicture, bool& checkOutputPictures)
@@ -209,7 +219,7 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
   read(nalu, bytes);                                   // NALread.cpp:144-154
 
   hm_emit_set_current(d->emitter);
-  hm_fast_set_clean_coeffs(d->emitter->cleanCoeffs());
+  hm_fast_set_skip_coeff_fill(d->emitter->cleanCoeffs());
   bNewPicture = false;
   if (!(d->maxTemporalLayer >= 0 && (int)nalu.m_temporalId > d->maxTemporalLayer))
   {
@@ -234,7 +244,7 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
     d->loopFilterDone = (nalu.m_nalUnitType == NAL_UNIT_EOS);
   }
   hm_emit_set_current(NULL);
-  hm_fast_set_clean_coeffs(false);
+  hm_fast_set_skip_coeff_fill(false);
 
   checkOutputPictures = false;
   d->flushing = false;

@@ -104,9 +104,12 @@ void tuEntries(Out& out, TComDataCU* ctu, UInt part, UInt depth, UInt trDepth, l
       // FIRST w*h (or w/2*h/2) levels of the CTU's coefficient buffer, not the TU's own.
       const ComponentID c = type == LIBHMDEC_TU_COEFF_ENERGY_Y ? COMPONENT_Y : COMPONENT_Cb;
       const int n = type == LIBHMDEC_TU_COEFF_ENERGY_Y ? g.w * g.h : (g.w / 2) * (g.h / 2);
+      // In this build HM's whole-CTU zero fill is skipped (hm_fast.cpp): only blocks with coded levels hold defined
+      // values, every other block counts as the zeros stock HM would have left there.
       const TCoeff* co = ctu->getCoeff(c);
+      const int perPart = 16 >> (ctu->getPic()->getComponentScaleX(c) + ctu->getPic()->getComponentScaleY(c));   // levels per 4x4 partition
       int64_t e = 0;
-      for (int i = 0; i < n; i++) e += (int64_t)(co[i] * co[i]);
+      for (int i = 0; i < n; i++) if (ctu->getCbf((UInt)(i / perPart), c) != 0) e += (int64_t)(co[i] * co[i]);
       b.value = e > MAX_INT ? MAX_INT : (int)e;
       break;
     }

@@ -9,8 +9,9 @@
  *                        (TDecGop::filterPicture, Lib/TLibDecoder/TDecGop.cpp:157-174)
  *   hmr_read_plane       replaces the host-memory plane access of TComPicYuv::getAddr as used by
  *                        libHMDEC_get_image_plane (App/libHMDecoder/libHMDecoder.cpp:402-417)
- *   hmr_picture_hash     replaces calcChecksum / calcCRC (Lib/TLibCommon/TComPicYuvMD5.cpp:127-175); MD5 stays on the
- *                        host (it is a serial chain) over the planes returned by hmr_read_plane
+ *   hmr_picture_hash     replaces calcChecksum / calcCRC (Lib/TLibCommon/TComPicYuvMD5.cpp:127-175)
+ *   hmr_md5_submit/result replace calcMD5 (TComPicYuvMD5.cpp:183-205): one serial chain per plane, run asynchronously on
+ *                        the device (many pictures in flight), so the SEI MD5 check costs the host nothing
  *
  * Plain C: pointers, sizes and the POD records of hmr_records.h; no C++/torch/CUDA types.  All functions return
  * HMR_OK (0) or a negative error code; hmr_error_string() describes the last error of an engine.
@@ -32,7 +33,7 @@ extern "C" {
 typedef struct hmr_engine hmr_engine;
 typedef struct hmr_resident_frame hmr_resident_frame;
 
-enum { HMR_OK = 0, HMR_ERR_CUDA = -1, HMR_ERR_ARG = -2, HMR_ERR_FORMAT = -3, HMR_ERR_NOMEM = -4 };
+enum { HMR_OK = 0, HMR_PENDING = 1, HMR_ERR_CUDA = -1, HMR_ERR_ARG = -2, HMR_ERR_FORMAT = -3, HMR_ERR_NOMEM = -4, HMR_ERR_BUSY = -5 };
 
 /* stage bits for hmr_set_stage_mask (default: all).  Same numbering as the oracle's orc_reconstruct_frame. */
 enum { HMR_STAGE_MC = 1, HMR_STAGE_RESID = 2, HMR_STAGE_INTRA = 4, HMR_STAGE_DEBLOCK_V = 8, HMR_STAGE_DEBLOCK_H = 16, HMR_STAGE_SAO = 32, HMR_STAGE_ALL = 63 };
@@ -64,6 +65,19 @@ int  hmr_write_plane(hmr_engine* e, int slot, int comp, const int16_t* src, size
 
 /* type: 2 = CRC, 3 = checksum (SEI decoded picture hash methods, SEI.h:118-134); out[3] one value per component. */
 int  hmr_picture_hash(hmr_engine* e, int slot, int type, uint32_t out[3]);
+
+/* Asynchronous SEI-MD5 of the picture in `slot` as it is after everything submitted so far.  The engine hashes a private
+ * copy on a side stream; at most 8 jobs may be outstanding (HMR_ERR_BUSY: collect results first).
+ * hmr_md5_result: out = 3 x 16 digest bytes (Y, Cb, Cr); wait = 0 polls (HMR_PENDING while running). */
+int  hmr_md5_submit(hmr_engine* e, int slot, uint64_t* job);
+int  hmr_md5_result(hmr_engine* e, uint64_t job, uint8_t out[48], int wait);
+
+/* Page-lock / unlock caller memory so that hmr_read_plane_async can DMA straight into it (e.g. HM's TComPicYuv planes). */
+int  hmr_host_register(void* p, size_t bytes);
+int  hmr_host_unregister(void* p);
+/* Stream markers: record = "everything enqueued so far"; wait blocks the host until that point has been reached. */
+int  hmr_marker_record(hmr_engine* e, uint64_t* id);
+int  hmr_marker_wait(hmr_engine* e, uint64_t id);
 
 /* ---- measurement / test hooks ---- */
 int  hmr_set_stage_mask(hmr_engine* e, int mask);

@@ -5,10 +5,13 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <mutex>
 #include "common.cuh"
 #include "hmrecon.h"
 
 #define RING 3
+#define MARKERS 64
+#define MD5_RING 8
 #define ALIGN_UP(v, a) (((v) + (a) - 1) / (a) * (a))
 
 struct Section { size_t off, bytes; };
@@ -57,7 +60,53 @@ struct hmr_engine
   int coopLimit;
   cudaEvent_t tBegin, tEnd, tJoin;
   bool timerInit;
+  size_t planeSetBytes;
+  // stream markers (hmr_marker_*)
+  cudaEvent_t markers[MARKERS]; bool markerInit; uint64_t markerNext;
+  // asynchronous MD5 (hmr_md5_*): side stream, ring of scratch pictures
+  bool auxInit;
+  struct Md5Slot { PlaneSet pic; bool alloc; cudaEvent_t copied, done; uint32_t* dOut; uint32_t* hOut; uint64_t job; bool busy; cudaStream_t stream; } md5[MD5_RING];
+  uint64_t md5Next;
 };
+
+// Process-wide caches of device and page-locked host buffers.  cudaMalloc / cudaFree / cudaMallocHost take milliseconds,
+// serialise on the driver and (cudaFree) synchronise the whole device — poison when 16 decoder threads share one GPU and
+// every new bitstream means a new engine.  Buffers of an engine that ends are parked here, keyed by (device, size), and
+// the next engine of the same geometry picks them up; nothing is returned to the driver before the process exits.
+#include <map>
+static std::mutex g_poolLock;
+static std::multimap<std::pair<int, size_t>, void*> g_devPool, g_hostPool;
+
+static cudaError_t pool_malloc(int device, void** p, size_t bytes)
+{
+  {
+    std::lock_guard<std::mutex> g(g_poolLock);
+    auto it = g_devPool.find(std::make_pair(device, bytes));
+    if (it != g_devPool.end()) { *p = it->second; g_devPool.erase(it); return cudaSuccess; }
+  }
+  return cudaMalloc(p, bytes);
+}
+static void pool_free(int device, void* p, size_t bytes)
+{
+  if (!p) return;
+  std::lock_guard<std::mutex> g(g_poolLock);
+  g_devPool.insert(std::make_pair(std::make_pair(device, bytes), p));
+}
+static cudaError_t pool_malloc_host(void** p, size_t bytes)
+{
+  {
+    std::lock_guard<std::mutex> g(g_poolLock);
+    auto it = g_hostPool.find(std::make_pair(0, bytes));
+    if (it != g_hostPool.end()) { *p = it->second; g_hostPool.erase(it); return cudaSuccess; }
+  }
+  return cudaMallocHost(p, bytes);
+}
+static void pool_free_host(void* p, size_t bytes)
+{
+  if (!p) return;
+  std::lock_guard<std::mutex> g(g_poolLock);
+  g_hostPool.insert(std::make_pair(std::make_pair(0, bytes), p));
+}
 
 static int fail(hmr_engine* e, int code, const std::string& msg) { if (e) e->err = msg; return code; }
 #define CK(call) do { cudaError_t _r = (call); if (_r != cudaSuccess) return fail(e, HMR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); } while (0)
@@ -121,17 +170,20 @@ static int alloc_planes(hmr_engine* e, PlaneSet& ps)
   size_t total = 0, offs[3];
   for (int c = 0; c < 3; c++) { offs[c] = total; total += ALIGN_UP((size_t)e->pitch[c] * e->h[c] * sizeof(int16_t), 512); }
   uint8_t* base = nullptr;
-  CK(cudaMalloc(&base, total));
+  CK(pool_malloc(e->device, (void**)&base, total));
   CK(cudaMemsetAsync(base, 0, total, e->stream));
   for (int c = 0; c < 3; c++) { ps.p[c] = (int16_t*)(base + offs[c]); ps.pitch[c] = e->pitch[c]; }
+  e->planeSetBytes = total;
   return HMR_OK;
 }
 
 static void free_geometry(hmr_engine* e)
 {
   cudaStreamSynchronize(e->stream);
-  for (int s = 0; s < HMR_MAX_SLOTS; s++) if (e->slotAlloc[s]) { cudaFree(e->slots[s].p[0]); e->slotAlloc[s] = false; }
-  if (e->workAlloc) { cudaFree(e->work.p[0]); e->workAlloc = false; }
+  for (int s = 0; s < HMR_MAX_SLOTS; s++) if (e->slotAlloc[s]) { pool_free(e->device, e->slots[s].p[0], e->planeSetBytes); e->slotAlloc[s] = false; }
+  if (e->workAlloc) { pool_free(e->device, e->work.p[0], e->planeSetBytes); e->workAlloc = false; }
+  for (int i = 0; i < MD5_RING; i++) if (e->auxInit && e->md5[i].busy) cudaEventSynchronize(e->md5[i].done);
+  for (int i = 0; i < MD5_RING; i++) if (e->md5[i].alloc) { pool_free(e->device, e->md5[i].pic.p[0], e->planeSetBytes); e->md5[i].alloc = false; }
   e->haveGeom = false;
 }
 
@@ -156,8 +208,8 @@ static int ensure_geometry(hmr_engine* e, const hmr_frame_hdr& h)
     const size_t need = (size_t)3 * e->ctusH;
     if (need > e->progressCap)
     {
-      if (e->progress) cudaFree(e->progress);
-      CK(cudaMalloc(&e->progress, need * sizeof(unsigned long long)));
+      pool_free(e->device, e->progress, e->progressCap * sizeof(unsigned long long));
+      CK(pool_malloc(e->device, (void**)&e->progress, need * sizeof(unsigned long long)));
       CK(cudaMemsetAsync(e->progress, 0, need * sizeof(unsigned long long), e->stream));
       e->progressCap = need;
     }
@@ -230,18 +282,18 @@ static int run_frame(hmr_engine* e, FrameParams& P, FrameEvents* fe)
   if (h.n_coef > e->residCap)
   {
     CK(cudaStreamSynchronize(e->stream));
-    if (e->resid) cudaFree(e->resid);
-    e->residCap = ALIGN_UP((size_t)h.n_coef * 3 / 2 + 4096, 4096);
-    CK(cudaMalloc(&e->resid, e->residCap * sizeof(int16_t)));
+    pool_free(e->device, e->resid, e->residCap * sizeof(int16_t));
+    e->residCap = ALIGN_UP((size_t)h.n_coef * 3 / 2 + 4096, 1 << 20);
+    CK(pool_malloc(e->device, (void**)&e->resid, e->residCap * sizeof(int16_t)));
     P.resid = e->resid;
   P.mc_tiles = e->mcTiles;
   }
   if (h.n_mc_tiles > e->mcTilesCap)
   {
     CK(cudaStreamSynchronize(e->stream));
-    if (e->mcTiles) cudaFree(e->mcTiles);
-    e->mcTilesCap = ALIGN_UP((size_t)h.n_mc_tiles * 3 / 2 + 1024, 1024);
-    CK(cudaMalloc(&e->mcTiles, e->mcTilesCap * sizeof(hmr_pu)));
+    pool_free(e->device, e->mcTiles, e->mcTilesCap * sizeof(hmr_pu));
+    e->mcTilesCap = ALIGN_UP((size_t)h.n_mc_tiles * 3 / 2 + 1024, 1 << 16);
+    CK(pool_malloc(e->device, (void**)&e->mcTiles, e->mcTilesCap * sizeof(hmr_pu)));
     P.mc_tiles = e->mcTiles;
   }
   auto mark = [&](int k) { if (fe) { cudaEventRecord(fe->ev[k], e->stream); fe->used[k] = true; } };
@@ -287,6 +339,7 @@ int hmr_engine_create(hmr_engine** out, int device)
 {
   if (!out) return HMR_ERR_ARG;
   *out = nullptr;
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);          // one hardware queue per stream (effective if CUDA is not initialised yet)
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
   {
@@ -302,6 +355,8 @@ int hmr_engine_create(hmr_engine** out, int device)
   e->stageMask = HMR_STAGE_ALL; e->timing = false;
   memset(e->accMs, 0, sizeof(e->accMs)); e->accFrames = e->accLaunches = 0;
   e->timerInit = false;
+  e->planeSetBytes = 0; e->markerInit = false; e->markerNext = 0; e->auxInit = false; e->md5Next = 0;
+  memset(e->md5, 0, sizeof(e->md5));
   e->dHash = nullptr; e->dHashRows = nullptr; e->hashRowsCap = 0; e->flushBuf = nullptr; e->flushCap = 0;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
   {
@@ -325,16 +380,25 @@ void hmr_engine_destroy(hmr_engine* e)
   free_geometry(e);
   for (int i = 0; i < RING; i++)
   {
-    if (e->ring[i].host) cudaFreeHost(e->ring[i].host);
-    if (e->ring[i].dev) cudaFree(e->ring[i].dev);
+    pool_free_host(e->ring[i].host, e->ring[i].cap);
+    pool_free(e->device, e->ring[i].dev, e->ring[i].cap);
     cudaEventDestroy(e->ring[i].done);
   }
-  if (e->resid) cudaFree(e->resid);
-  if (e->mcTiles) cudaFree(e->mcTiles);
-  if (e->progress) cudaFree(e->progress);
+  pool_free(e->device, e->resid, e->residCap * sizeof(int16_t));
+  pool_free(e->device, e->mcTiles, e->mcTilesCap * sizeof(hmr_pu));
+  pool_free(e->device, e->progress, e->progressCap * sizeof(unsigned long long));
   if (e->dHash) cudaFree(e->dHash);
   if (e->dHashRows) cudaFree(e->dHashRows);
   if (e->flushBuf) cudaFree(e->flushBuf);
+  if (e->markerInit) for (int i = 0; i < MARKERS; i++) cudaEventDestroy(e->markers[i]);
+  if (e->auxInit)
+  {
+    for (int i = 0; i < MD5_RING; i++)
+    {
+      cudaEventDestroy(e->md5[i].copied); cudaEventDestroy(e->md5[i].done);
+      pool_free(e->device, e->md5[i].dOut, 24 * sizeof(uint32_t)); pool_free_host(e->md5[i].hOut, 12 * sizeof(uint32_t));
+    }
+  }
   fold_timing(e);
   for (size_t i = 0; i < e->freeEvents.size(); i++) for (int k = 0; k <= HMR_T_COUNT; k++) cudaEventDestroy(e->freeEvents[i].ev[k]);
   cudaStreamDestroy(e->stream);
@@ -360,11 +424,12 @@ int hmr_submit_frame(hmr_engine* e, const hmr_frame_desc* f)
   if (st.inflight) { CK(cudaEventSynchronize(st.done)); st.inflight = false; }
   if (L.total > st.cap)
   {
-    if (st.host) cudaFreeHost(st.host);
-    if (st.dev) cudaFree(st.dev);
-    st.cap = ALIGN_UP(L.total * 3 / 2, 1 << 20);
-    CK(cudaMallocHost(&st.host, st.cap));
-    CK(cudaMalloc(&st.dev, st.cap));
+    pool_free_host(st.host, st.cap);
+    pool_free(e->device, st.dev, st.cap);
+    st.host = nullptr; st.dev = nullptr;
+    st.cap = ALIGN_UP(L.total * 3 / 2, 4 << 20);
+    CK(pool_malloc_host((void**)&st.host, st.cap));
+    CK(pool_malloc(e->device, (void**)&st.dev, st.cap));
   }
   pack(st.host, L, f);
   FrameEvents* fe = grab_events(e);
@@ -579,6 +644,124 @@ void hmr_free_resident(hmr_engine* e, hmr_resident_frame* f)
   if (e) { cudaSetDevice(e->device); cudaStreamSynchronize(e->stream); }
   cudaFree(f->dev);
   delete f;
+}
+
+int hmr_host_register(void* p, size_t bytes)
+{
+  if (!p || !bytes) return HMR_ERR_ARG;
+  return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? HMR_OK : HMR_ERR_CUDA;
+}
+int hmr_host_unregister(void* p) { return (p && cudaHostUnregister(p) == cudaSuccess) ? HMR_OK : HMR_ERR_CUDA; }
+
+int hmr_marker_record(hmr_engine* e, uint64_t* id)
+{
+  if (!e || !id) return HMR_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  if (!e->markerInit)
+  {
+    for (int i = 0; i < MARKERS; i++) CK(cudaEventCreateWithFlags(&e->markers[i], cudaEventDisableTiming));
+    e->markerInit = true;
+  }
+  const uint64_t m = e->markerNext++;
+  cudaEvent_t ev = e->markers[m % MARKERS];
+  if (m >= MARKERS) CK(cudaEventSynchronize(ev));            // the marker this slot held before is MARKERS records old
+  CK(cudaEventRecord(ev, e->stream));
+  *id = m;
+  return HMR_OK;
+}
+
+int hmr_marker_wait(hmr_engine* e, uint64_t id)
+{
+  if (!e || id >= e->markerNext) return HMR_ERR_ARG;
+  if (id + MARKERS < e->markerNext) return HMR_OK;            // overwritten => it completed long ago (see hmr_marker_record)
+  CK(cudaEventSynchronize(e->markers[id % MARKERS]));
+  return HMR_OK;
+}
+
+// MD5 chains are long-running one-warp kernels (~0.1 s).  They live on a small PROCESS-WIDE pool of low-priority streams
+// shared by all engines of a device, so that the number of streams of the process stays below the number of hardware
+// work queues (CUDA_DEVICE_MAX_CONNECTIONS, raised to 32 by hmr_engine_create): a decode stream must never end up queued
+// behind somebody's hash.  Two jobs that draw the same pool stream simply run one after the other.
+static std::mutex g_auxLock;
+static std::vector<cudaStream_t> g_auxPool[64];
+static unsigned g_auxNext[64];
+
+static cudaStream_t aux_stream(int device)
+{
+  std::lock_guard<std::mutex> g(g_auxLock);
+  std::vector<cudaStream_t>& pool = g_auxPool[device & 63];
+  if (pool.empty())
+  {
+    int n = 12;
+    if (const char* v = getenv("HMR_MD5_STREAMS")) n = atoi(v) > 0 ? atoi(v) : n;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);             // lo = lowest priority
+    for (int i = 0; i < n; i++)
+    {
+      cudaStream_t st;
+      if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lo) == cudaSuccess) pool.push_back(st);
+    }
+  }
+  if (pool.empty()) return nullptr;
+  return pool[g_auxNext[device & 63]++ % pool.size()];
+}
+
+static int aux_init(hmr_engine* e)
+{
+  if (e->auxInit) return HMR_OK;
+  for (int i = 0; i < MD5_RING; i++)
+  {
+    CK(cudaEventCreateWithFlags(&e->md5[i].copied, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->md5[i].done, cudaEventDisableTiming));
+    CK(pool_malloc(e->device, (void**)&e->md5[i].dOut, 24 * sizeof(uint32_t)));   // digest + chaining state
+    CK(pool_malloc_host((void**)&e->md5[i].hOut, 12 * sizeof(uint32_t)));
+    e->md5[i].busy = false; e->md5[i].alloc = false;
+  }
+  e->auxInit = true;
+  return HMR_OK;
+}
+
+int hmr_md5_submit(hmr_engine* e, int slot, uint64_t* job)
+{
+  if (!e || !job || slot < 0 || slot >= HMR_MAX_SLOTS || !e->slotAlloc[slot]) return fail(e, HMR_ERR_ARG, "md5_submit: bad argument");
+  CK(cudaSetDevice(e->device));
+  int r = aux_init(e);
+  if (r) return r;
+  hmr_engine::Md5Slot& m = e->md5[e->md5Next % MD5_RING];
+  if (m.busy) return fail(e, HMR_ERR_BUSY, "md5_submit: ring full, collect results first");
+  if (!m.alloc) { if ((r = alloc_planes(e, m.pic))) return r; m.alloc = true; }
+  // private copy: the DPB slot may be overwritten long before the chain has walked the picture
+  CK(cudaMemcpyAsync(m.pic.p[0], e->slots[slot].p[0], e->planeSetBytes, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaEventRecord(m.copied, e->stream));
+  m.stream = aux_stream(e->device);
+  if (!m.stream) return fail(e, HMR_ERR_CUDA, "md5_submit: no side stream");
+  CK(cudaStreamWaitEvent(m.stream, m.copied, 0));
+  const int bd[3] = { e->bdLuma, e->bdChroma, e->bdChroma };
+  launch_md5(m.pic, e->w, e->h, bd, e->fmt == HMR_CHROMA_400 ? 1 : 3, m.dOut, m.stream);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(m.hOut, m.dOut, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, m.stream));
+  CK(cudaEventRecord(m.done, m.stream));
+  m.busy = true;
+  m.job = e->md5Next++;
+  *job = m.job;
+  return HMR_OK;
+}
+
+int hmr_md5_result(hmr_engine* e, uint64_t job, uint8_t out[48], int wait)
+{
+  if (!e || !out || !e->auxInit) return HMR_ERR_ARG;
+  hmr_engine::Md5Slot& m = e->md5[job % MD5_RING];
+  if (!m.busy || m.job != job) return fail(e, HMR_ERR_ARG, "md5_result: unknown or already collected job");
+  if (!wait)
+  {
+    const cudaError_t q = cudaEventQuery(m.done);
+    if (q == cudaErrorNotReady) return HMR_PENDING;
+    if (q != cudaSuccess) return fail(e, HMR_ERR_CUDA, cudaGetErrorString(q));
+  }
+  else CK(cudaEventSynchronize(m.done));
+  memcpy(out, m.hOut, 48);
+  m.busy = false;
+  return HMR_OK;
 }
 
 void* hmr_alloc_pinned(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }

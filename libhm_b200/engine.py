@@ -42,6 +42,8 @@ def load():
                            ("hmr_upload_frame", [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
                            ("hmr_run_resident", [C.c_void_p, C.c_void_p]), ("hmr_free_resident", [C.c_void_p, C.c_void_p]),
                            ("hmr_flush_l2", [C.c_void_p, C.c_size_t]),
+                           ("hmr_md5_submit", [C.c_void_p, C.c_int, C.c_void_p]), ("hmr_md5_result", [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]),
+                           ("hmr_marker_record", [C.c_void_p, C.c_void_p]), ("hmr_marker_wait", [C.c_void_p, C.c_uint64]),
                            ("hmr_run_resident_list", [C.c_void_p, C.c_void_p, C.c_int]), ("hmr_timer_begin", [C.c_void_p]),
                            ("hmr_timer_join", [C.c_void_p, C.c_void_p]), ("hmr_timer_end", [C.c_void_p, C.c_void_p])):
             getattr(lib, name).argtypes = args
@@ -108,6 +110,20 @@ class Engine:
         out = (C.c_uint32 * 3)()
         self._ck(self.lib.hmr_picture_hash(self.h, slot, kind, out), "hmr_picture_hash")
         return [int(v) for v in out]
+
+    def md5_submit(self, slot):
+        job = C.c_uint64()
+        self._ck(self.lib.hmr_md5_submit(self.h, slot, C.byref(job)), "hmr_md5_submit")
+        return job.value
+
+    def md5_result(self, job, wait=True):
+        """3 x 16 digest bytes (uint8 [3][16]) or None while the chain is still running (wait=False)."""
+        out = (C.c_uint8 * 48)()
+        rc = self.lib.hmr_md5_result(self.h, job, out, int(wait))
+        if rc == 1:
+            return None
+        self._ck(rc, "hmr_md5_result")
+        return np.frombuffer(bytes(out), np.uint8).reshape(3, 16).copy()
 
     def set_stage_mask(self, mask):
         self._ck(self.lib.hmr_set_stage_mask(self.h, mask), "hmr_set_stage_mask")

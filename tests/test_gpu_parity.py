@@ -93,3 +93,24 @@ def test_resident_replay_is_deterministic(eng_mod):
             eng.free_resident(h)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("name", ["s_ra8_odd", "s_ra10_240p", "s_rext444_240p"])
+def test_device_md5_matches_hm_golden(name, eng_mod):
+    """Asynchronous device MD5 (hmr_md5_submit/result: one warp per plane chain, private copy of the picture) against the MD5
+    HM itself computed for the final picture (8-bit = 1 byte/sample, 10/12-bit = 2 bytes LE; odd sizes exercise the tail)."""
+    frames = records.read_dump(os.path.join(GOLDEN, name + ".hmr.gz"))
+    eng = eng_mod.Engine(0)
+    try:
+        jobs = []
+        for fr in frames:
+            eng.submit(fr)
+            jobs.append((eng.md5_submit(int(fr.h["out_slot"])), fr))
+            if len(jobs) == 6:                      # several digests in flight while later pictures overwrite the DPB slots
+                for job, f in jobs:
+                    assert (eng.md5_result(job) == f.gold[2]).all(), (name, int(f.h["poc"]))
+                jobs = []
+        for job, f in jobs:
+            assert (eng.md5_result(job) == f.gold[2]).all(), (name, int(f.h["poc"]))
+    finally:
+        eng.close()
