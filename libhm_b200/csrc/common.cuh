@@ -47,4 +47,3 @@ void launch_deblock(const FrameParams& P, int dir, cudaStream_t s);
 void launch_sao(const FrameParams& P, cudaStream_t s);
 void launch_hash(const PlaneSet& pic, const int w[3], const int h[3], const int bd[3], int type, uint32_t* d_out, uint32_t* d_scratch, cudaStream_t s);
 int  intra_max_coresident_blocks(int device);
-void launch_md5(const PlaneSet& pic, const int w[3], const int h[3], const int bd[3], int ncomp, uint32_t* d_out, cudaStream_t s);

@@ -6,7 +6,11 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <atomic>
+#include <thread>
+#include <chrono>
 #include "common.cuh"
+#include "md5_service.h"
 #include "hmrecon.h"
 
 #define RING 3
@@ -65,7 +69,7 @@ struct hmr_engine
   cudaEvent_t markers[MARKERS]; bool markerInit; uint64_t markerNext;
   // asynchronous MD5 (hmr_md5_*): side stream, ring of scratch pictures
   bool auxInit;
-  struct Md5Slot { PlaneSet pic; bool alloc; cudaEvent_t copied, done; uint32_t* dOut; uint32_t* hOut; uint64_t job; bool busy; cudaStream_t stream; } md5[MD5_RING];
+  struct Md5Slot { PlaneSet pic; bool alloc; cudaEvent_t copied; uint32_t* dState; uint32_t* hOut; uint64_t job; bool busy; std::atomic<int> done; } md5[MD5_RING];
   uint64_t md5Next;
 };
 
@@ -182,7 +186,7 @@ static void free_geometry(hmr_engine* e)
   cudaStreamSynchronize(e->stream);
   for (int s = 0; s < HMR_MAX_SLOTS; s++) if (e->slotAlloc[s]) { pool_free(e->device, e->slots[s].p[0], e->planeSetBytes); e->slotAlloc[s] = false; }
   if (e->workAlloc) { pool_free(e->device, e->work.p[0], e->planeSetBytes); e->workAlloc = false; }
-  for (int i = 0; i < MD5_RING; i++) if (e->auxInit && e->md5[i].busy) cudaEventSynchronize(e->md5[i].done);
+  for (int i = 0; i < MD5_RING; i++) while (e->auxInit && e->md5[i].busy && e->md5[i].done.load() == 0) std::this_thread::sleep_for(std::chrono::microseconds(200));
   for (int i = 0; i < MD5_RING; i++) if (e->md5[i].alloc) { pool_free(e->device, e->md5[i].pic.p[0], e->planeSetBytes); e->md5[i].alloc = false; }
   e->haveGeom = false;
 }
@@ -339,7 +343,7 @@ int hmr_engine_create(hmr_engine** out, int device)
 {
   if (!out) return HMR_ERR_ARG;
   *out = nullptr;
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);          // one hardware queue per stream (effective if CUDA is not initialised yet)
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);          // decoder streams should not share hardware queues (effective if CUDA is not initialised yet)
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
   {
@@ -356,7 +360,7 @@ int hmr_engine_create(hmr_engine** out, int device)
   memset(e->accMs, 0, sizeof(e->accMs)); e->accFrames = e->accLaunches = 0;
   e->timerInit = false;
   e->planeSetBytes = 0; e->markerInit = false; e->markerNext = 0; e->auxInit = false; e->md5Next = 0;
-  memset(e->md5, 0, sizeof(e->md5));
+  for (int i = 0; i < MD5_RING; i++) { e->md5[i].alloc = false; e->md5[i].busy = false; e->md5[i].dState = nullptr; e->md5[i].hOut = nullptr; e->md5[i].job = 0; e->md5[i].done.store(0); }
   e->dHash = nullptr; e->dHashRows = nullptr; e->hashRowsCap = 0; e->flushBuf = nullptr; e->flushCap = 0;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
   {
@@ -395,8 +399,8 @@ void hmr_engine_destroy(hmr_engine* e)
   {
     for (int i = 0; i < MD5_RING; i++)
     {
-      cudaEventDestroy(e->md5[i].copied); cudaEventDestroy(e->md5[i].done);
-      pool_free(e->device, e->md5[i].dOut, 24 * sizeof(uint32_t)); pool_free_host(e->md5[i].hOut, 12 * sizeof(uint32_t));
+      cudaEventDestroy(e->md5[i].copied);
+      pool_free(e->device, e->md5[i].dState, 12 * sizeof(uint32_t)); pool_free_host(e->md5[i].hOut, 12 * sizeof(uint32_t));
     }
   }
   fold_timing(e);
@@ -678,43 +682,14 @@ int hmr_marker_wait(hmr_engine* e, uint64_t id)
   return HMR_OK;
 }
 
-// MD5 chains are long-running one-warp kernels (~0.1 s).  They live on a small PROCESS-WIDE pool of low-priority streams
-// shared by all engines of a device, so that the number of streams of the process stays below the number of hardware
-// work queues (CUDA_DEVICE_MAX_CONNECTIONS, raised to 32 by hmr_engine_create): a decode stream must never end up queued
-// behind somebody's hash.  Two jobs that draw the same pool stream simply run one after the other.
-static std::mutex g_auxLock;
-static std::vector<cudaStream_t> g_auxPool[64];
-static unsigned g_auxNext[64];
-
-static cudaStream_t aux_stream(int device)
-{
-  std::lock_guard<std::mutex> g(g_auxLock);
-  std::vector<cudaStream_t>& pool = g_auxPool[device & 63];
-  if (pool.empty())
-  {
-    int n = 12;
-    if (const char* v = getenv("HMR_MD5_STREAMS")) n = atoi(v) > 0 ? atoi(v) : n;
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);             // lo = lowest priority
-    for (int i = 0; i < n; i++)
-    {
-      cudaStream_t st;
-      if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lo) == cudaSuccess) pool.push_back(st);
-    }
-  }
-  if (pool.empty()) return nullptr;
-  return pool[g_auxNext[device & 63]++ % pool.size()];
-}
-
 static int aux_init(hmr_engine* e)
 {
   if (e->auxInit) return HMR_OK;
   for (int i = 0; i < MD5_RING; i++)
   {
     CK(cudaEventCreateWithFlags(&e->md5[i].copied, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->md5[i].done, cudaEventDisableTiming));
-    CK(pool_malloc(e->device, (void**)&e->md5[i].dOut, 24 * sizeof(uint32_t)));   // digest + chaining state
-    CK(pool_malloc_host((void**)&e->md5[i].hOut, 12 * sizeof(uint32_t)));
+    CK(pool_malloc(e->device, (void**)&e->md5[i].dState, 12 * sizeof(uint32_t)));   // chaining state between ticks
+    CK(pool_malloc_host((void**)&e->md5[i].hOut, 12 * sizeof(uint32_t)));           // digest, written by the device
     e->md5[i].busy = false; e->md5[i].alloc = false;
   }
   e->auxInit = true;
@@ -733,14 +708,13 @@ int hmr_md5_submit(hmr_engine* e, int slot, uint64_t* job)
   // private copy: the DPB slot may be overwritten long before the chain has walked the picture
   CK(cudaMemcpyAsync(m.pic.p[0], e->slots[slot].p[0], e->planeSetBytes, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaEventRecord(m.copied, e->stream));
-  m.stream = aux_stream(e->device);
-  if (!m.stream) return fail(e, HMR_ERR_CUDA, "md5_submit: no side stream");
-  CK(cudaStreamWaitEvent(m.stream, m.copied, 0));
+  Md5Job J;
   const int bd[3] = { e->bdLuma, e->bdChroma, e->bdChroma };
-  launch_md5(m.pic, e->w, e->h, bd, e->fmt == HMR_CHROMA_400 ? 1 : 3, m.dOut, m.stream);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(m.hOut, m.dOut, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, m.stream));
-  CK(cudaEventRecord(m.done, m.stream));
+  for (int c = 0; c < 3; c++) { J.plane[c] = m.pic.p[c]; J.pitch[c] = m.pic.pitch[c]; J.w[c] = e->w[c]; J.h[c] = e->h[c]; J.bd[c] = bd[c]; }
+  J.ncomp = e->fmt == HMR_CHROMA_400 ? 1 : 3;
+  J.out = m.hOut;
+  J.state = m.dState;
+  if (!md5_service_submit(e->device, J, m.copied, &m.done)) return fail(e, HMR_ERR_CUDA, "md5_submit: hash service unavailable");
   m.busy = true;
   m.job = e->md5Next++;
   *job = m.job;
@@ -752,15 +726,12 @@ int hmr_md5_result(hmr_engine* e, uint64_t job, uint8_t out[48], int wait)
   if (!e || !out || !e->auxInit) return HMR_ERR_ARG;
   hmr_engine::Md5Slot& m = e->md5[job % MD5_RING];
   if (!m.busy || m.job != job) return fail(e, HMR_ERR_ARG, "md5_result: unknown or already collected job");
-  if (!wait)
-  {
-    const cudaError_t q = cudaEventQuery(m.done);
-    if (q == cudaErrorNotReady) return HMR_PENDING;
-    if (q != cudaSuccess) return fail(e, HMR_ERR_CUDA, cudaGetErrorString(q));
-  }
-  else CK(cudaEventSynchronize(m.done));
-  memcpy(out, m.hOut, 48);
+  int st = m.done.load(std::memory_order_acquire);
+  if (st == 0 && !wait) return HMR_PENDING;
+  while (st == 0) { std::this_thread::sleep_for(std::chrono::microseconds(200)); st = m.done.load(std::memory_order_acquire); }
   m.busy = false;
+  if (st < 0) return fail(e, HMR_ERR_CUDA, "md5_result: the hash service failed");
+  memcpy(out, m.hOut, 48);
   return HMR_OK;
 }
 

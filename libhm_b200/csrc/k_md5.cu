@@ -11,20 +11,13 @@
 // broadcasts.  The chain itself is LOP3 -> IADD3 -> SHF (rotate) -> IADD per step.
 #include <algorithm>
 #include "common.cuh"
+#include "md5_service.h"
 
 __constant__ uint32_t c_md5K[64] = {
   0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501, 0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
   0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8, 0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
   0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70, 0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
   0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1, 0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391 };
-
-struct Md5Job
-{
-  const int16_t* plane[3];
-  int pitch[3], w[3], h[3], bd[3];
-  uint32_t* out;                       // 3 x 4 words (digest A,B,C,D per component, little endian = digest byte order)
-  uint32_t* state;                     // 3 x 4 words: chaining value between the chunk launches
-};
 
 #define MD5_CHUNK 4096                 // 64-byte blocks per launch (~2 ms)
 
@@ -153,23 +146,27 @@ __device__ __forceinline__ void md5_plane(const Md5Job& J, int comp, int chunk, 
   if (lane == 0) { J.out[comp * 4 + 0] = st[0]; J.out[comp * 4 + 1] = st[1]; J.out[comp * 4 + 2] = st[2]; J.out[comp * 4 + 3] = st[3]; }
 }
 
-__global__ void __launch_bounds__(32) md5_kernel(const Md5Job J, const int chunk)
+// One tick of the hash service: every in-flight job advances by one chunk (grid = jobs x 3 planes, one warp each).
+__global__ void __launch_bounds__(32) md5_tick_kernel(const Md5TickJob* __restrict__ jobs)
 {
   __shared__ uint32_t s_msg[32 * 16];
-  const int comp = blockIdx.x, lane = threadIdx.x;
+  const int job = blockIdx.x / 3, comp = blockIdx.x % 3, lane = threadIdx.x;
+  const Md5Job J = jobs[job].J;
+  const int chunk = jobs[job].chunk;
+  if (comp >= J.ncomp) return;
   if (J.bd[comp] > 8) md5_plane<true>(J, comp, chunk, s_msg, lane);
   else                md5_plane<false>(J, comp, chunk, s_msg, lane);
 }
 
-void launch_md5(const PlaneSet& pic, const int w[3], const int h[3], const int bd[3], int ncomp, uint32_t* d_out, cudaStream_t s)
+void launch_md5_tick(const Md5TickJob* jobs, int n, cudaStream_t s)
 {
-  Md5Job J;
-  for (int c = 0; c < 3; c++) { J.plane[c] = pic.p[c]; J.pitch[c] = pic.pitch[c]; J.w[c] = w[c]; J.h[c] = h[c]; J.bd[c] = bd[c]; }
-  J.out = d_out;
-  J.state = d_out + 12;
-  // the plane with the most blocks decides the number of launches; +1 block so that the tail always has a launch
+  if (n > 0) md5_tick_kernel<<<3 * n, 32, 0, s>>>(jobs);
+}
+
+int md5_chunks(const Md5Job& J)
+{
+  // the plane with the most blocks decides the number of ticks; +1 so that the tail always has a tick
   unsigned long long maxBlocks = 0;
-  for (int c = 0; c < ncomp; c++) maxBlocks = std::max(maxBlocks, ((unsigned long long)w[c] * h[c] * (bd[c] > 8 ? 2 : 1)) >> 6);
-  const int launches = (int)(maxBlocks / MD5_CHUNK) + 1;
-  for (int k = 0; k < launches; k++) md5_kernel<<<ncomp, 32, 0, s>>>(J, k);
+  for (int c = 0; c < J.ncomp; c++) maxBlocks = std::max(maxBlocks, ((unsigned long long)J.w[c] * J.h[c] * (J.bd[c] > 8 ? 2 : 1)) >> 6);
+  return (int)(maxBlocks / MD5_CHUNK) + 1;
 }

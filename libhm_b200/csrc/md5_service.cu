@@ -1,0 +1,129 @@
+// md5_service.cu — process-wide asynchronous MD5 service.
+//
+// An MD5 chain is serial (one warp, ~0.1 s for a 2160p luma plane), but chains are independent.  Giving every job its own
+// stream does not scale: a process has at most 32 hardware work queues, so ~15 hashes could run at once — ~100 pictures/s
+// where the decoders deliver 500.  Instead ONE host thread per device drives ONE stream with "ticks": each tick is a
+// single short launch (k_md5.cu: md5_tick_kernel) in which every job in flight advances by MD5_CHUNK blocks, one warp
+// per plane.  The latency of a job is (its number of chunks) x (tick period ~2 ms) whatever the number of jobs, so the
+// throughput is bounded only by how many jobs the engines keep in flight (8 each).  No launch runs longer than a few
+// milliseconds, nothing ever queues behind a hash, and the host thread sleeps when there is no work.
+#include <pthread.h>
+#include <sched.h>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "md5_service.h"
+
+namespace {
+
+struct Active { Md5Job J; int chunk, chunks; std::atomic<int>* done; cudaEvent_t ready; };
+
+struct Service
+{
+  int device;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<Active> pending;
+  bool running;                // a worker thread exists
+  bool failed;
+  Service() : device(0), running(false), failed(false) {}
+};
+
+Service* const g_svc = new Service[16];   // never destroyed: a lingering worker may still hold its mutex at process exit
+
+void worker(Service* sv)
+{
+  // the thread that happened to submit first may be pinned to one core: this worker must not inherit that
+  cpu_set_t all;
+  CPU_ZERO(&all);
+  for (int c = 0; c < CPU_SETSIZE; c++) CPU_SET(c, &all);
+  pthread_setaffinity_np(pthread_self(), sizeof(all), &all);
+  cudaSetDevice(sv->device);
+  cudaStream_t stream = nullptr;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);                   // lo = lowest priority
+  const int MAXJ = 512;
+  Md5TickJob* table[2] = { nullptr, nullptr };
+  cudaEvent_t ev[2];
+  bool ok = cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, lo) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; i++)
+    ok = cudaMallocHost(&table[i], sizeof(Md5TickJob) * MAXJ) == cudaSuccess && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;   // sleep, never spin: the cores belong to the parsers
+  std::vector<Active> active;
+  std::vector<std::atomic<int>*> finishing[2];                  // jobs whose last chunk was in tick t (signalled when tick t completes)
+  unsigned long long t = 0;
+  for (;;)
+  {
+    {
+      std::unique_lock<std::mutex> lk(sv->mu);
+      if (!ok) { sv->failed = true; for (size_t i = 0; i < sv->pending.size(); i++) sv->pending[i].done->store(-1); sv->pending.clear(); sv->running = false; return; }
+      if (active.empty() && sv->pending.empty() && finishing[0].empty() && finishing[1].empty())
+      {
+        // idle: linger a little, then let the thread end (a later submit starts a new one)
+        if (!sv->cv.wait_for(lk, std::chrono::milliseconds(200), [&] { return !sv->pending.empty(); })) { sv->running = false; break; }
+      }
+      while (!sv->pending.empty() && (int)active.size() < MAXJ)
+      {
+        active.push_back(sv->pending.back());
+        sv->pending.pop_back();
+        ok = ok && cudaStreamWaitEvent(stream, active.back().ready, 0) == cudaSuccess;   // the planes are complete before the first tick reads them
+      }
+    }
+    const int cur = (int)(t & 1);
+    if (!active.empty())
+    {
+      for (size_t i = 0; i < active.size(); i++) { table[cur][i].J = active[i].J; table[cur][i].chunk = active[i].chunk; }
+      launch_md5_tick(table[cur], (int)active.size(), stream);
+      ok = ok && cudaGetLastError() == cudaSuccess;
+      size_t keep = 0;
+      for (size_t i = 0; i < active.size(); i++)
+      {
+        if (++active[i].chunk >= active[i].chunks) finishing[cur].push_back(active[i].done);
+        else active[keep++] = active[i];
+      }
+      active.resize(keep);
+    }
+    ok = ok && cudaEventRecord(ev[cur], stream) == cudaSuccess;
+    // tick t-1 has certainly been overtaken once its event fires: publish its digests, and its table may be rewritten next round
+    if (t > 0)
+    {
+      const int prev = cur ^ 1;
+      ok = ok && cudaEventSynchronize(ev[prev]) == cudaSuccess;
+      for (size_t i = 0; i < finishing[prev].size(); i++) finishing[prev][i]->store(ok ? 1 : -1);
+      finishing[prev].clear();
+    }
+    t++;
+  }
+  // drain the last tick before leaving
+  if (t > 0)
+  {
+    const int prev = (int)((t - 1) & 1);
+    const bool fine = cudaEventSynchronize(ev[prev]) == cudaSuccess;
+    for (int k = 0; k < 2; k++) { for (size_t i = 0; i < finishing[k].size(); i++) finishing[k][i]->store(fine ? 1 : -1); finishing[k].clear(); }
+  }
+  for (int i = 0; i < 2; i++) { if (table[i]) cudaFreeHost(table[i]); cudaEventDestroy(ev[i]); }
+  cudaStreamDestroy(stream);
+}
+
+} // namespace
+
+bool md5_service_submit(int device, const Md5Job& J, cudaEvent_t ready, std::atomic<int>* done)
+{
+  if (device < 0 || device >= 16) return false;
+  Service& sv = g_svc[device];
+  Active a;
+  a.J = J; a.chunk = 0; a.chunks = md5_chunks(J); a.done = done; a.ready = ready;
+  done->store(0);
+  std::lock_guard<std::mutex> g(sv.mu);
+  if (sv.failed) return false;
+  sv.device = device;
+  sv.pending.push_back(a);
+  if (!sv.running)
+  {
+    sv.running = true;
+    std::thread(worker, &sv).detach();
+  }
+  sv.cv.notify_one();
+  return true;
+}
