@@ -37,22 +37,23 @@ __device__ __forceinline__ void mc_cp_async16(void* smem, const void* gmem)
 __device__ __forceinline__ void mc_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void mc_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
-// PU records -> one record per 16x16-luma tile (same struct: x, y, w, h describe the tile)
+// PU records -> one record per 16x16-luma tile (same struct: x, y, w, h describe the tile).  16 threads per PU (a PU has at
+// most 4x4 tiles): the record load is a broadcast, the tile records of a PU are written by consecutive lanes.
 __global__ void __launch_bounds__(256) mc_expand_kernel(const __grid_constant__ FrameParams P)
 {
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = gid >> 4;
+  const int k = gid & 15;
   if (p >= P.hdr.n_pu) return;
-  const hmr_pu pu = P.pu[p];
-  const uint32_t base = P.pu_prefix[p];
-  const int tx = (pu.w + 15) >> 4, ty = (pu.h + 15) >> 4;
-  for (int j = 0; j < ty; j++)
-    for (int i = 0; i < tx; i++)
-    {
-      hmr_pu t = pu;
-      t.x = (uint16_t)(pu.x + 16 * i); t.y = (uint16_t)(pu.y + 16 * j);
-      t.w = (uint8_t)min(16, pu.w - 16 * i); t.h = (uint8_t)min(16, pu.h - 16 * j);
-      P.mc_tiles[base + j * tx + i] = t;
-    }
+  const uint4 raw = __ldg((const uint4*)(P.pu + p));
+  hmr_pu t = *(const hmr_pu*)&raw;
+  const int tx = (t.w + 15) >> 4, ty = (t.h + 15) >> 4;
+  if (k >= tx * ty) return;
+  const int j = k / tx, i = k - j * tx;
+  const int w = min(16, t.w - 16 * i), h = min(16, t.h - 16 * j);
+  t.x = (uint16_t)(t.x + 16 * i); t.y = (uint16_t)(t.y + 16 * j);
+  t.w = (uint8_t)w; t.h = (uint8_t)h;
+  *(uint4*)(P.mc_tiles + __ldg(P.pu_prefix + p) + k) = *(const uint4*)&t;
 }
 
 // Stage rows [iy, iy+rows) x columns [xa, xa + 8*nvec) of `ref` into s (pitch MC_PITCH).  Returns nothing; async on the fast path.
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
 void launch_mc(const FrameParams& P, cudaStream_t s)
 {
   if (P.hdr.n_mc_tiles == 0) return;
-  mc_expand_kernel<<<(P.hdr.n_pu + 255) / 256, 256, 0, s>>>(P);
+  mc_expand_kernel<<<(P.hdr.n_pu * 16 + 255) / 256, 256, 0, s>>>(P);
   const int chromaRows = ((16 >> P.csy) + 4) & ~1;
   const int warpBytes = 12 * MC_TMPW * 4 + 2 * 24 * MC_PITCH * 2 + 4 * chromaRows * MC_PITCH * 2;
   mc_kernel<<<(P.hdr.n_mc_tiles + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, MC_WARPS * warpBytes, s>>>(P, warpBytes, chromaRows);
