@@ -112,6 +112,34 @@ static void releasePlanes(TComPicYuv* yuv)
   }
 }
 
+// ---- lazy motion compression ---------------------------------------------------------------------------------
+// TComPic::compressMotion (16x16 motion storage for TMVP) is pure overhead for a picture that is never a reference:
+// nothing will ever read its motion field again — except libHMDEC_get_internal_info, which then compresses on demand
+// so that the API reports exactly what the reference reports.
+static std::mutex g_motionLock;
+static std::set<TComPic*> g_motionPending;
+
+void hm_fast_defer_motion_compression(TComPic* pic)
+{
+  std::lock_guard<std::mutex> g(g_motionLock);
+  g_motionPending.insert(pic);
+}
+
+void hm_fast_ensure_motion_compressed(TComPic* pic)
+{
+  {
+    std::lock_guard<std::mutex> g(g_motionLock);
+    if (!g_motionPending.erase(pic)) return;
+  }
+  pic->compressMotion();
+}
+
+static void forgetMotion(TComPic* pic)
+{
+  std::lock_guard<std::mutex> g(g_motionLock);
+  g_motionPending.erase(pic);
+}
+
 // Every picture buffer a decoder ever created.  The wrapper's flush (like the reference's, libHMDecoder.cpp:329-336) only
 // drops the pointers from the DPB list; without this registry those pictures would be lost and never reused.
 static std::mutex g_createdLock;
@@ -150,6 +178,7 @@ void hm_fast_release_decoder(TDecTop* dec)
   for (size_t i = 0; i < mine.size(); i++)
   {
     TComPic* pic = mine[i];
+    forgetMotion(pic);
     releasePlanes(pic->getPicYuvRec());
     bool listed = false;
     for (TComList<TComPic*>::iterator it = dec->m_cListPic.begin(); it != dec->m_cListPic.end() && !listed; ++it) listed = (*it == pic);
@@ -178,6 +207,7 @@ static bool sameGeometry(TComPic* pic, TComSPS* sps)
 static void resetPicture(TComPic* pic, Window& conf, Window& disp, Int* reorder)
 {
   TComPicSym* sym = pic->m_apcPicSym;
+  forgetMotion(pic);
   sym->clearSliceBuffer();
   delete sym->getSlice(0);
   sym->setSlice(new TComSlice, 0);

@@ -18,6 +18,7 @@
 #include "TLibCommon/TComSampleAdaptiveOffset.h"
 #include "TLibCommon/SEI.h"
 #include "hm_emit.h"
+#include "hm_fast.h"
 
 extern Bool g_md5_mismatch;
 void hm_call_original_decompressCU(TDecCu* dec, TComDataCU* ctu);
@@ -139,7 +140,9 @@ Void TDecGop::filterPicture(TComPic*& rpcPic)
     e->sink()->hmStage(2, rpcPic);
   }
 
-  rpcPic->compressMotion();
+  // TMVP storage (TDecGop.cpp:176): only a picture that can be referenced needs it now (hm_fast.cpp)
+  if (slice->isReferenced() || e->sink()->wantHmRecon()) rpcPic->compressMotion();
+  else hm_fast_defer_motion_compression(rpcPic);
   static const bool quiet = getenv("HMDEC_B200_QUIET") != NULL;   // the hash is still verified
   printStatusAndHash(rpcPic, slice, m_decodedPictureHashSEIEnabled, e, quiet);
   e->sink()->drainHashes(false);

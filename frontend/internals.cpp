@@ -12,6 +12,7 @@
 #include "TLibCommon/TComPic.h"
 #include "TLibCommon/TComRom.h"
 #include "libHMDecoder_api.h"
+#include "hm_fast.h"
 
 namespace {
 
@@ -170,6 +171,7 @@ void cuWalk(Out& out, TComDataCU* ctu, UInt part, UInt depth, libHMDec_info_type
 
 std::vector<libHMDec_BlockValue>* hm_collect_internals(std::vector<libHMDec_BlockValue>& out, TComPic* pic, libHMDec_info_type type)
 {
+  hm_fast_ensure_motion_compressed(pic);     // non-reference pictures postpone compressMotion until somebody looks
   TComPicSym* sym = pic->getPicSym();
   if (!sym) return NULL;
   const int n = sym->getNumberOfCUsInFrame();

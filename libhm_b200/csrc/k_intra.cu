@@ -15,17 +15,19 @@
 // The per-TU chain is the critical path (an I picture at 2160p is ~3300 dependent TU steps; a dataflow simulation over
 // real streams shows TU-level parallelism inside a CTU is < 1.2x, z-order makes every TU depend on its predecessor),
 // so the design minimises the latency of ONE warp walking the TUs:
-//   * all 4 warps stage in shared memory the CTU's current samples plus the row above (x = -1 .. CTU+31) and the
-//     column to the left, and the residuals of the CTU's TUs, with 16-byte cp.async copies all in flight together;
-//   * warps 1-3 ("helpers") turn the NEXT intra CTU's records into reference-address tables while warp 0 runs the
-//     current CTU: for every TU, entry i = shared-memory position of reference sample i AFTER HM's substitution of
-//     unavailable samples (pure function of the record, no sample data) — the whole fillReferenceSamples logic is off
-//     the critical path and double-buffered;
+//   * the CTA is warp-specialised and double-buffered: warps 1-3 ("stagers") do everything that touches global
+//     memory for CTU n+1 while warp 0 ("chain") predicts CTU n — the CTU's current samples plus the row above
+//     (x = -1 .. CTU+31, after waiting for the row above) and the column to the left, the residuals of its TUs
+//     (16-byte cp.async copies all in flight together), the records — then write CTU n back and publish the progress;
+//     hand-over through named barriers (bar.arrive / bar.sync), never a full __syncthreads;
+//   * the stagers also turn the records into reference-address tables: for every TU, entry i = shared-memory position
+//     of reference sample i AFTER HM's substitution of unavailable samples (pure function of the record, no sample
+//     data) — the whole fillReferenceSamples logic is off the critical path;
 //   * warp 0 ("chain") runs size-templated, fully unrolled code per TU: gather the line through the table -> optional
 //     smoothing -> prediction (main-reference projection folded into the index) -> + residual -> back into the tile,
 //     with warp-level synchronisation only;
-//   * the tile is written back once, coalesced, by all warps.  Cross-CTA reads go through L2 (ld.global.cg); the
-//     producer fences before publishing.
+//   * a tile is written back once, coalesced.  Cross-CTA reads go through L2 (ld.global.cg); the producer fences before
+//     publishing.
 #include "common.cuh"
 
 #define IN_THREADS 128
@@ -262,12 +264,21 @@ __device__ __forceinline__ void intra_tu(const hmr_intra r, const uint16_t* __re
 #undef EMIT
 }
 
+// named barriers (id 0 is __syncthreads)
+#define BAR_FULL 1     // +buffer: stagers arrive, chain waits  -> "CTU staged"
+#define BAR_DONE 3     // +buffer: chain arrives, stagers wait  -> "CTU predicted"
+#define BAR_STAGE 5    // the three stager warps among themselves
+#define IN_STAGERS (IN_THREADS - 32)
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+
 __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant__ FrameParams P, const int resSamples)
 {
   extern __shared__ __align__(16) uint8_t s_dyn[];
-  int16_t* s_tile = (int16_t*)s_dyn;                                         // IN_TILE (+ pad to 16 bytes)
-  int16_t* s_res = s_tile + ((IN_TILE + 7) & ~7);                            // residuals of this CTU, compact layout relative to minoff
-  hmr_intra* s_rec = (hmr_intra*)(s_res + resSamples);                       // [2][IN_MAXREC]
+  constexpr int TILE_PAD = (IN_TILE + 7) & ~7;
+  int16_t* s_tileB = (int16_t*)s_dyn;                                        // [2][TILE_PAD]
+  int16_t* s_resB = s_tileB + 2 * TILE_PAD;                                  // [2][resSamples] residuals of a CTU, compact layout relative to minoff
+  hmr_intra* s_rec = (hmr_intra*)(s_resB + 2 * resSamples);                  // [2][IN_MAXREC]
   uint16_t* s_addr = (uint16_t*)(s_rec + 2 * IN_MAXREC);                     // [2][IN_ADDR]
   __shared__ int s_lineBuf[4 * 32 + 8];   // unfiltered reference line: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right
   __shared__ int s_fltBuf[4 * 32 + 8];    // smoothed
@@ -276,6 +287,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   __shared__ uint32_t s_first[IN_MAXCOLS];
   __shared__ uint16_t s_count[IN_MAXCOLS];
   __shared__ unsigned s_minoff[2];
+  __shared__ int16_t s_col[IN_MAXCT];     // right-most column of the CTU the chain just finished (left neighbours of the next one)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int comp = blockIdx.x / P.ctus_h, row = blockIdx.x % P.ctus_h;
   if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) return;
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   const bool strongAllowed = P.hdr.flags & HMR_FRM_STRONG_INTRA_SMOOTHING;
   int16_t* plane = P.work.p[comp];
   const int pitch = P.work.pitch[comp];
-#define T(y, x) s_tile[TIDX(y, x)]
+  const int oy = row * CTH, ch = min(CTH, H - oy);
 
   for (int c = tid; c < ctusW; c += IN_THREADS)
   {
@@ -303,160 +315,191 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
     s_first[c] = rg.first[comp];
     s_count[c] = (uint16_t)min(rg.count[comp], (uint32_t)IN_MAXREC);
   }
-  if (tid == 0) { s_minoff[0] = s_minoff[1] = 0xffffffffu; s_tile[0] = (int16_t)(1 << (bd - 1)); }
+  if (tid == 0) { s_tileB[0] = s_tileB[TILE_PAD] = (int16_t)(1 << (bd - 1)); }
   __syncthreads();
 
-  int c = next_intra_ctu(s_count, 0, ctusW, lane);
-  if (tid == 0) *(volatile unsigned long long*)myProg = base + (unsigned long long)c;   // nothing to do before CTU c
-  if (c >= ctusW) return;
+  const int c0 = next_intra_ctu(s_count, 0, ctusW, lane);
+  if (tid == 0) *(volatile unsigned long long*)myProg = base + (unsigned long long)c0;   // nothing to do before CTU c0
+  if (c0 >= ctusW) return;
 
-  // prologue: records + address tables of the first intra CTU into buffer 0 (all warps)
-  int buf = 0;
+  if (warp == 0)
   {
-    const int count = s_count[c];
-    const uint32_t first = s_first[c];
-    for (int i = tid; i < count; i += IN_THREADS)
+    // ============================ chain warp: TU after TU, shared memory only ============================
+    int prev = -2, n = 0;
+    for (int c = c0; c < ctusW; c = next_intra_ctu(s_count, c + 1, ctusW, lane), n++)
     {
-      const uint4 rec = __ldcg((const uint4*)(P.intra + first) + i);
-      ((uint4*)s_rec)[i] = rec;
-      if (rec.w != HMR_NO_OFFSET) atomicMin(&s_minoff[0], rec.w);
-    }
-    __syncthreads();
-    g.ox = c * CTW;
-    for (int k = warp; k < count; k += IN_THREADS / 32) intra_addr_table(s_rec[k], s_addr + intra_slot(s_rec[k], g), g, lane);
-    __syncthreads();
-  }
-
-  while (c < ctusW)
-  {
-    const int count = s_count[c];
-    hmr_intra* rec = s_rec + buf * IN_MAXREC;
-    uint16_t* addrTab = s_addr + buf * IN_ADDR;
-    const int cn = next_intra_ctu(s_count, c + 1, ctusW, lane);           // next CTU with intra TUs in this row
-    if (upProg)
-    {
-      if (tid == 0)
-      {
-        const unsigned long long need = base + (unsigned long long)min(c + 2, ctusW);
-        while (*upProg < need) { }
-        __threadfence();
-      }
-      __syncthreads();
-    }
-    const int ox = c * CTW, oy = row * CTH;                 // CTU origin in this component
-    const int cw = min(CTW, W - ox), ch = min(CTH, H - oy); // part inside the picture
-
-    // ---- stage: tile interior + residuals (async), row above, column to the left, next CTU's records ----
-    if ((cw & 7) == 0)
-    {
-      const int vecPerRow = cw >> 3;
-      for (int i = tid; i < ch * vecPerRow; i += IN_THREADS)
-      {
-        const int y = i / vecPerRow, v = i - y * vecPerRow;
-        cp_async16(&T(y, 8 * v), plane + (size_t)(oy + y) * pitch + ox + 8 * v);
-      }
-    }
-    else
-    {
-      const int vecPerRow = cw >> 2;                         // widths are multiples of 4
-      for (int i = tid; i < ch * vecPerRow; i += IN_THREADS)
-      {
-        const int y = i / vecPerRow, v = i - y * vecPerRow;
-        cp_async8(&T(y, 4 * v), plane + (size_t)(oy + y) * pitch + ox + 4 * v);
-      }
-    }
-    const unsigned minoff = s_minoff[buf];
-    for (int k = warp; k < count; k += IN_THREADS / 32)
-    {
-      const uint32_t off = rec[k].resid_off;
-      if (off == HMR_NO_OFFSET) continue;
-      const int units = 1 << (2 * rec[k].log2_size - 3);     // N*N int16 in 16-byte units
-      const uint32_t rel = off - minoff;
-      if (rel + 8u * units > (uint32_t)resSamples) continue; // cannot happen for a well-formed frame (one CTU's levels are contiguous)
-      for (int u = lane; u < units; u += 32) cp_async16(s_res + rel + 8 * u, P.resid + off + 8 * u);
-    }
-    {
-      uint4 rec0 = make_uint4(0, 0, 0, 0), rec1 = rec0;
-      int top = 0, left = 0;
-      const int gx = ox + tid - 1;
-      const bool hasTop = oy > 0 && tid < CTW + 33 && gx >= 0 && gx < W;
-      const bool hasLeft = ox > 0 && tid < ch;
-      const int countN = cn < ctusW ? (int)s_count[cn] : 0;
-      const uint32_t firstN = cn < ctusW ? s_first[cn] : 0;
-      if (tid < countN) rec0 = __ldcg((const uint4*)(P.intra + firstN) + tid);
-      if (tid + IN_THREADS < countN) rec1 = __ldcg((const uint4*)(P.intra + firstN) + tid + IN_THREADS);
-      if (hasTop) top = __ldcg(plane + (size_t)(oy - 1) * pitch + gx);
-      if (hasLeft) left = __ldcg(plane + (size_t)(oy + tid) * pitch + ox - 1);
-      uint4* recN = (uint4*)(s_rec + (buf ^ 1) * IN_MAXREC);
-      if (tid < countN) { recN[tid] = rec0; if (rec0.w != HMR_NO_OFFSET) atomicMin(&s_minoff[buf ^ 1], rec0.w); }
-      if (tid + IN_THREADS < countN) { recN[tid + IN_THREADS] = rec1; if (rec1.w != HMR_NO_OFFSET) atomicMin(&s_minoff[buf ^ 1], rec1.w); }
-      if (hasTop) T(-1, tid - 1) = (int16_t)top;
-      if (hasLeft) T(tid, -1) = (int16_t)left;
-    }
-    cp_async_wait_all();
-    __syncthreads();
-
-    if (warp == 0)
-    {
-      // ---- the dependent chain: one warp, one TU after the other, shared memory only ----
-      if (lane == 0) s_minoff[buf] = 0xffffffffu;            // consumed; this buffer is refilled two CTUs from now
+      const int b = n & 1;
+      int16_t* tile = s_tileB + b * TILE_PAD;
+      const hmr_intra* rec = s_rec + b * IN_MAXREC;
+      const uint16_t* addrTab = s_addr + b * IN_ADDR;
+      const int16_t* resB = s_resB + b * resSamples;
+      const int count = s_count[c];
+      const int ox = c * CTW;
+      bar_sync(BAR_FULL + b, IN_THREADS);                    // staged: tile, records, tables, residuals
+      const unsigned minoff = s_minoff[b];
+      if (prev == c - 1)                                     // left neighbours = what this warp produced a moment ago
+        for (int y = lane; y < ch; y += 32) tile[TIDX(y, -1)] = s_col[y];
+      __syncwarp();
       g.ox = ox;
       for (int k = 0; k < count; k++)
       {
         const hmr_intra r = rec[k];
         const uint16_t* a = addrTab + intra_slot(r, g);
-        const int16_t* res = s_res + (r.resid_off != HMR_NO_OFFSET ? r.resid_off - minoff : 0u);
+        const int16_t* res = resB + (r.resid_off != HMR_NO_OFFSET ? r.resid_off - minoff : 0u);
         const int x0 = r.x - ox, y0 = r.y - oy;
         switch (r.log2_size)
         {
-          case 2:  intra_tu<2>(r, a, s_tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
-          case 3:  intra_tu<3>(r, a, s_tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
-          case 4:  intra_tu<4>(r, a, s_tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
-          default: intra_tu<5>(r, a, s_tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
+          case 2:  intra_tu<2>(r, a, tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
+          case 3:  intra_tu<3>(r, a, tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
+          case 4:  intra_tu<4>(r, a, tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
+          default: intra_tu<5>(r, a, tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
         }
         __syncwarp();        // this TU's samples are in the tile before the next TU gathers its reference line
       }
+      const int cwc = min(CTW, W - ox);
+      for (int y = lane; y < ch; y += 32) s_col[y] = tile[TIDX(y, cwc - 1)];
+      prev = c;
+      __syncwarp();
+      __threadfence_block();
+      bar_arrive(BAR_DONE + b, IN_THREADS);                  // predicted: the stagers write it back and publish
     }
-    else if (cn < ctusW)
-    {
-      // ---- helpers: address tables of the next intra CTU (records were staged above) ----
-      IntraGeom gn = g;
-      gn.ox = cn * CTW;
-      const hmr_intra* recN = s_rec + (buf ^ 1) * IN_MAXREC;
-      uint16_t* addrN = s_addr + (buf ^ 1) * IN_ADDR;
-      const int countN = s_count[cn];
-      for (int k = warp - 1; k < countN; k += IN_THREADS / 32 - 1) intra_addr_table(recN[k], addrN + intra_slot(recN[k], gn), gn, lane);
-    }
-    __syncthreads();
-    // ---- write the CTU back (inter samples are rewritten with the values they had) ----
+    return;
+  }
+
+  // ============================ stager warps: everything that touches global memory ============================
+  const int st = tid - 32, swarp = warp - 1;
+  int prev = -2, prevB = 0, n = 0;
+  for (int c = c0; c < ctusW; n++)
+  {
+    const int b = n & 1;
+    int16_t* tile = s_tileB + b * TILE_PAD;
+    hmr_intra* rec = s_rec + b * IN_MAXREC;
+    uint16_t* addrTab = s_addr + b * IN_ADDR;
+    int16_t* resB = s_resB + b * resSamples;
+    const int count = s_count[c];
+    const uint32_t first = s_first[c];
+    const int cn = next_intra_ctu(s_count, c + 1, ctusW, lane);
+    const int ox = c * CTW;
+    const int cw = min(CTW, W - ox);
+
+    // ---- stage CTU c into buffer b (free: its previous tenant was written back in the last iteration) ----
     if ((cw & 7) == 0)
     {
       const int vecPerRow = cw >> 3;
-      for (int i = tid; i < ch * vecPerRow; i += IN_THREADS)
+      for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
       {
         const int y = i / vecPerRow, v = i - y * vecPerRow;
-        *((uint4*)(plane + (size_t)(oy + y) * pitch + ox) + v) = *(const uint4*)&T(y, 8 * v);
+        cp_async16(&tile[TIDX(y, 8 * v)], plane + (size_t)(oy + y) * pitch + ox + 8 * v);
       }
     }
     else
     {
-      const int vecPerRow = cw >> 2;
-      for (int i = tid; i < ch * vecPerRow; i += IN_THREADS)
+      const int vecPerRow = cw >> 2;                         // widths are multiples of 4
+      for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
       {
         const int y = i / vecPerRow, v = i - y * vecPerRow;
-        *((uint2*)(plane + (size_t)(oy + y) * pitch + ox) + v) = *(const uint2*)&T(y, 4 * v);
+        cp_async8(&tile[TIDX(y, 4 * v)], plane + (size_t)(oy + y) * pitch + ox + 4 * v);
       }
     }
+    if (st == 0) s_minoff[b] = 0xffffffffu;
+    bar_sync(BAR_STAGE, IN_STAGERS);
+    for (int i = st; i < count; i += IN_STAGERS)
+    {
+      const uint4 q = __ldcg((const uint4*)(P.intra + first) + i);
+      ((uint4*)rec)[i] = q;
+      if (q.w != HMR_NO_OFFSET) atomicMin(&s_minoff[b], q.w);
+    }
+    if (ox > 0 && prev != c - 1)                             // left CTU has no intra blocks: its samples have been final since the kernel started
+      for (int y = st; y < ch; y += IN_STAGERS) tile[TIDX(y, -1)] = __ldcg(plane + (size_t)(oy + y) * pitch + ox - 1);
+    bar_sync(BAR_STAGE, IN_STAGERS);
+    const unsigned minoff = s_minoff[b];
+    IntraGeom gc = g;
+    gc.ox = ox;
+    for (int k = swarp; k < count; k += IN_STAGERS / 32)
+    {
+      const hmr_intra r = rec[k];
+      if (r.resid_off != HMR_NO_OFFSET)
+      {
+        const int units = 1 << (2 * r.log2_size - 3);        // N*N int16 in 16-byte units
+        const uint32_t rel = r.resid_off - minoff;
+        if (rel + 8u * units <= (uint32_t)resSamples)        // always true for a well-formed frame (one CTU's levels are contiguous)
+          for (int u = lane; u < units; u += 32) cp_async16(resB + rel + 8 * u, P.resid + r.resid_off + 8 * u);
+      }
+      intra_addr_table(r, addrTab + intra_slot(r, gc), gc, lane);
+    }
+    // the row above (x = -1 .. CTW+31) needs the CTU above-right to be final
+    if (upProg)
+    {
+      if (st == 0)
+      {
+        const unsigned long long need = base + (unsigned long long)min(c + 2, ctusW);
+        while (*upProg < need) { }
+        __threadfence();
+      }
+      bar_sync(BAR_STAGE, IN_STAGERS);
+      for (int x = st - 1; x < CTW + 32; x += IN_STAGERS)
+      {
+        const int gx = ox + x;
+        if (gx >= 0 && gx < W) tile[TIDX(-1, x)] = __ldcg(plane + (size_t)(oy - 1) * pitch + gx);
+      }
+    }
+    cp_async_wait_all();
+    __threadfence_block();
+    bar_arrive(BAR_FULL + b, IN_THREADS);
+
+    // ---- write back + publish the CTU the chain is finishing meanwhile ----
+    if (prev >= 0)
+    {
+      bar_sync(BAR_DONE + prevB, IN_THREADS);
+      const int16_t* ptile = s_tileB + prevB * TILE_PAD;
+      const int pox = prev * CTW, pcw = min(CTW, W - pox);
+      if ((pcw & 7) == 0)
+      {
+        const int vecPerRow = pcw >> 3;
+        for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
+        {
+          const int y = i / vecPerRow, v = i - y * vecPerRow;
+          *((uint4*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint4*)&ptile[TIDX(y, 8 * v)];
+        }
+      }
+      else
+      {
+        const int vecPerRow = pcw >> 2;
+        for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
+        {
+          const int y = i / vecPerRow, v = i - y * vecPerRow;
+          *((uint2*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint2*)&ptile[TIDX(y, 4 * v)];
+        }
+      }
+      bar_sync(BAR_STAGE, IN_STAGERS);
+      if (st == 0)
+      {
+        __threadfence();
+        *(volatile unsigned long long*)myProg = base + (unsigned long long)c;    // every CTU before c (the next intra CTU) is final
+      }
+    }
+    prev = c; prevB = b;
     c = cn;
-    buf ^= 1;
-    __syncthreads();
-    if (tid == 0)
+  }
+  // ---- the last CTU of the row ----
+  {
+    bar_sync(BAR_DONE + prevB, IN_THREADS);
+    const int16_t* ptile = s_tileB + prevB * TILE_PAD;
+    const int pox = prev * CTW, pcw = min(CTW, W - pox);
+    const int unit = (pcw & 7) == 0 ? 8 : 4, vecPerRow = pcw / unit;
+    for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
+    {
+      const int y = i / vecPerRow, v = i - y * vecPerRow;
+      if (unit == 8) *((uint4*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint4*)&ptile[TIDX(y, 8 * v)];
+      else           *((uint2*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint2*)&ptile[TIDX(y, 4 * v)];
+    }
+    bar_sync(BAR_STAGE, IN_STAGERS);
+    if (st == 0)
     {
       __threadfence();
-      *(volatile unsigned long long*)myProg = base + (unsigned long long)c;      // every CTU before the next intra CTU is final
+      *(volatile unsigned long long*)myProg = base + (unsigned long long)ctusW;
     }
   }
-#undef T
 }
 
 static int intra_res_samples(const FrameParams& P)
@@ -466,7 +509,7 @@ static int intra_res_samples(const FrameParams& P)
 }
 static size_t intra_dyn_smem(int resSamples)
 {
-  return (size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + 2 * IN_MAXREC * sizeof(hmr_intra) + 2 * IN_ADDR * sizeof(uint16_t);
+  return 2 * ((size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + IN_MAXREC * sizeof(hmr_intra) + IN_ADDR * sizeof(uint16_t));
 }
 
 int intra_max_coresident_blocks(int device)

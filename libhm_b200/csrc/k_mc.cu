@@ -27,8 +27,30 @@
 #define MC_PITCH 40                 // int16 per staged window row: up to 32 loaded + 8 pad (80 B: 16-byte aligned, conflict-free row pairs)
 #define MC_TMPW 16                  // words per row pair of the H-pass output
 
-__constant__ int8_t c_lumaTaps[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
-__constant__ int8_t c_chromaTaps[8][4] = { {0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4}, {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2} };
+// HM's interpolation taps (TComInterpolationFilter.cpp:50-72), packed for dp2a: `e` = byte pairs (t0,t1)(t2,t3).. for an
+// output at an even position, `o` = (0,t0)(t1,t2)..(t7,0) for an odd one.  Filled by launch_mc on first use.
+struct McTapTable { int lumaE[4][4], lumaO[4][5], chromaE[8][2], chromaO[8][3]; };
+__constant__ McTapTable c_taps;
+static const int8_t h_lumaTaps[4][8] = { {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1} };
+static const int8_t h_chromaTaps[8][4] = { {0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4}, {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2} };
+
+template <int NT> static void pack_taps_host(const int8_t* t, int* e, int* o)
+{
+  for (int j = 0; j < NT / 2; j++) e[j] = (t[2 * j] & 0xff) | ((t[2 * j + 1] & 0xff) << 8);
+  for (int j = 0; j <= NT / 2; j++) o[j] = (j > 0 ? (t[2 * j - 1] & 0xff) : 0) | (j < NT / 2 ? ((t[2 * j] & 0xff) << 8) : 0);
+}
+static void upload_taps()
+{
+  static bool done[64] = { false };
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && done[dev]) return;
+  McTapTable T;
+  for (int f = 0; f < 4; f++) pack_taps_host<8>(h_lumaTaps[f], T.lumaE[f], T.lumaO[f]);
+  for (int f = 0; f < 8; f++) pack_taps_host<4>(h_chromaTaps[f], T.chromaE[f], T.chromaO[f]);
+  cudaMemcpyToSymbol(c_taps, &T, sizeof(T));
+  if (dev < 64) done[dev] = true;
+}
 
 __device__ __forceinline__ void mc_cp_async16(void* smem, const void* gmem)
 {
@@ -60,18 +82,13 @@ __global__ void __launch_bounds__(256) mc_expand_kernel(const __grid_constant__ 
 __device__ __forceinline__ void mc_stage(int16_t* s, const int16_t* __restrict__ ref, int rpitch, int Wc, int Hc,
                                          int ix, int iy, int xa, int rows, int cols, int nvec, int lane)
 {
-  const bool inside = iy >= 0 && iy + rows <= Hc && ix >= 0 && ix + cols <= Wc && xa + 8 * nvec <= rpitch;
+  const bool inside = iy >= 0 && iy + rows <= Hc && ix >= 0 && ix + cols <= Wc && xa + 32 <= rpitch;
   if (inside)
   {
-    const int16_t* g = ref + (size_t)iy * rpitch + xa;
-    if (nvec == 4)
-      for (int i = lane; i < rows * 4; i += 32) mc_cp_async16(s + (i >> 2) * MC_PITCH + 8 * (i & 3), g + (size_t)(i >> 2) * rpitch + 8 * (i & 3));
-    else
-      for (int i = lane; i < rows * nvec; i += 32)
-      {
-        const int r = i / nvec, q = i - r * nvec;
-        mc_cp_async16(s + r * MC_PITCH + 8 * q, g + (size_t)r * rpitch + 8 * q);
-      }
+    // always 4 x 16 bytes per row (the row pitch of the window holds them): 8 rows per round, pointers only advance
+    const int16_t* g = ref + (size_t)(iy + (lane >> 2)) * rpitch + xa + 8 * (lane & 3);
+    int16_t* d = s + (lane >> 2) * MC_PITCH + 8 * (lane & 3);
+    for (int r = lane >> 2; r < rows; r += 8, g += 8 * (size_t)rpitch, d += 8 * MC_PITCH) mc_cp_async16(d, g);
   }
   else
   {
@@ -88,13 +105,13 @@ __device__ __forceinline__ void mc_stage(int16_t* s, const int16_t* __restrict__
 template <int NT> struct McTaps { int e[NT / 2]; int o[NT / 2 + 1]; };
 
 template <int NT>
-__device__ __forceinline__ McTaps<NT> mc_pack_taps(const int8_t* t)
+__device__ __forceinline__ McTaps<NT> mc_load_taps(int frac)      // frac: quarter-sample (luma) / eighth-sample (chroma) phase
 {
   McTaps<NT> r;
 #pragma unroll
-  for (int j = 0; j < NT / 2; j++) r.e[j] = (t[2 * j] & 0xff) | ((t[2 * j + 1] & 0xff) << 8);
+  for (int j = 0; j < NT / 2; j++) r.e[j] = NT == 8 ? c_taps.lumaE[frac][j] : c_taps.chromaE[frac][j];
 #pragma unroll
-  for (int j = 0; j <= NT / 2; j++) r.o[j] = (j > 0 ? (t[2 * j - 1] & 0xff) : 0) | (j < NT / 2 ? ((t[2 * j] & 0xff) << 8) : 0);
+  for (int j = 0; j <= NT / 2; j++) r.o[j] = NT == 8 ? c_taps.lumaO[frac][j] : c_taps.chromaO[frac][j];
   return r;
 }
 
@@ -177,8 +194,8 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
     if (!(t.lists & (1 << list))) continue;                  // warp-uniform
     const int mvx = t.mv[list][0], mvy = t.mv[list][1];
     const int fx = mvx & ((4 << cx) - 1), fy = mvy & ((4 << cy) - 1);
-    const McTaps<NT> tx = mc_pack_taps<NT>(NT == 8 ? c_lumaTaps[fx] : c_chromaTaps[fx << (1 - cx)]);
-    const McTaps<NT> ty = mc_pack_taps<NT>(NT == 8 ? c_lumaTaps[fy] : c_chromaTaps[fy << (1 - cy)]);
+    const McTaps<NT> tx = mc_load_taps<NT>(NT == 8 ? fx : fx << (1 - cx));
+    const McTaps<NT> ty = mc_load_taps<NT>(NT == 8 ? fy : fy << (1 - cy));
     mc_hpass<NT>(sref[list], tmp, offs[list], rowPairs, log2ColPairs, tx, s1, o1, lane);
     __syncwarp();
     if (lane < nV)
@@ -277,6 +294,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
 void launch_mc(const FrameParams& P, cudaStream_t s)
 {
   if (P.hdr.n_mc_tiles == 0) return;
+  upload_taps();
   mc_expand_kernel<<<(P.hdr.n_pu * 16 + 255) / 256, 256, 0, s>>>(P);
   const int chromaRows = ((16 >> P.csy) + 4) & ~1;
   const int warpBytes = 12 * MC_TMPW * 4 + 2 * 24 * MC_PITCH * 2 + 4 * chromaRows * MC_PITCH * 2;
