@@ -184,7 +184,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from libhm_b200 import engine, records
+    from libhm_b200 import engine, records, sharding
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the reconstruction engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -229,11 +229,8 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = sum(e.stage_times()[2] for e in engines)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * S * F * a.steps / (ms / 1000.0)
+    frames_total, ms = sharding.reduce_measurement(S * F * a.steps, ms, device="cuda")     # frames summed, time = max over ranks
+    value = sharding.frames_per_second(frames_total, ms)
 
     # ---- per-kernel durations, single stream, CUDA events around every launch (live, same process)
     kern = {}
@@ -269,7 +266,8 @@ def main():
 
     # ---- end to end through libHMDec_* on the bitstream bytes: one decoder process per host core of this rank
     e2e = None
-    cores_rank = max(1, ncores // world)
+    my_cores = sharding.host_cores_of_rank(ncores, world, local_rank)
+    cores_rank = len(my_cores)
     if not a.no_e2e and os.path.exists(CLI) and os.path.exists(bin_path):
         # decoder front ends: ONE process per rank (one CUDA context, process-wide buffer pools and MD5 service), 1.5 decoder
         # threads per host core of this rank: the surplus threads fill the ~0.13 s a finishing decoder waits for its last
@@ -282,7 +280,7 @@ def main():
         if world > 1:
             dist.broadcast(t0, 0)
         start = float(t0.item())
-        first_core = local_rank * cores_rank
+        first_core = my_cores[0]
         cmd = [CLI, "-b", bin_path, "--threads", str(thr), "--repeat", str(passes), "--start-at", f"{start:.3f}"]
         if world > 1:
             cmd = ["taskset", "-c", f"{first_core}-{first_core + cores_rank - 1}"] + cmd
