@@ -107,55 +107,129 @@ __device__ __forceinline__ void intra_addr_table(const hmr_intra& r, uint16_t* _
   }
 }
 
-// One TU on one warp, everything in shared memory.  `line`/`flt` are warp-private scratch (4N+1 ints each).
+// Everything the chain needs to know about a TU, decoded ahead of time by the stagers (16 bytes, one LDS.128).
+// Kept as a plain uint4 (fields by shifts): a struct with narrow members ends up on the local-memory stack, and local memory
+// sits behind the L1 that every __threadfence of the stager warps invalidates.
+//   x: [15:0] org  = tile index of the TU's top-left sample     [31:16] slot = first entry of its reference-address table
+//   y: res  = residual position relative to the CTU's first residual, or HMR_NO_OFFSET
+//   z: [7:0] angle (signed intraPredAngle)  [15:8] log2 size  [23:16] class OP_*  [31:24] flags OPF_*
+//   w: [15:0] inverse angle (negative angles)
+typedef uint4 IntraOp;
+__device__ __forceinline__ int op_org(const IntraOp& o)   { return o.x & 0xffff; }
+__device__ __forceinline__ int op_slot(const IntraOp& o)  { return o.x >> 16; }
+__device__ __forceinline__ int op_angle(const IntraOp& o) { return (int)(int8_t)(o.z & 0xff); }
+__device__ __forceinline__ int op_lg(const IntraOp& o)    { return (o.z >> 8) & 0xff; }
+__device__ __forceinline__ int op_cls(const IntraOp& o)   { return (o.z >> 16) & 0xff; }
+__device__ __forceinline__ int op_flags(const IntraOp& o) { return o.z >> 24; }
+__device__ __forceinline__ int op_inv(const IntraOp& o)   { return o.w & 0xffff; }
+enum { OP_PLANAR = 0, OP_DC = 1, OP_ANG0 = 2, OP_ANGPOS = 3, OP_ANGNEG = 4 };
+enum { OPF_FILTER = 1, OPF_STRONG = 2, OPF_EDGE = 4, OPF_VER = 8, OPF_DCEDGE = 16 };
+
+__device__ __forceinline__ IntraOp intra_make_op(const hmr_intra& r, const IntraGeom& g, unsigned minoff, bool strongAllowed)
+{
+  const int N = 1 << r.log2_size;
+  const bool luma = r.flags & HMR_INTRA_LUMA_RULES;
+  int f = 0, cls, angle = 0, inv = 0;
+  if (r.flags & HMR_INTRA_FILTER_REFS) f |= OPF_FILTER;
+  if (N == 32 && luma && strongAllowed) f |= OPF_STRONG;
+  if (luma && N <= 16) f |= OPF_DCEDGE;
+  if (luma && N <= 16 && !(r.flags & HMR_INTRA_NO_EDGE_FLT)) f |= OPF_EDGE;
+  const int mode = r.mode;
+  if (mode == 0) cls = OP_PLANAR;
+  else if (mode == 1) cls = OP_DC;
+  else
+  {
+    const bool ver = mode >= 18;
+    const int am = ver ? mode - 26 : 10 - mode;
+    const int aa = abs(am);
+    angle = am < 0 ? -c_angTab[aa] : c_angTab[aa];
+    if (ver) f |= OPF_VER;
+    inv = c_invTab[aa];
+    cls = angle == 0 ? OP_ANG0 : (angle > 0 ? OP_ANGPOS : OP_ANGNEG);
+  }
+  IntraOp op;
+  op.x = (uint32_t)TIDX(r.y - g.oy, r.x - g.ox) | ((uint32_t)intra_slot(r, g) << 16);
+  op.y = r.resid_off != HMR_NO_OFFSET ? r.resid_off - minoff : HMR_NO_OFFSET;
+  op.z = (uint32_t)(angle & 0xff) | ((uint32_t)r.log2_size << 8) | ((uint32_t)cls << 16) | ((uint32_t)f << 24);
+  op.w = (uint32_t)inv;
+  return op;
+}
+
+#define IN_NJMAX 5      // (4*32 + 1 + 31) / 32 reference samples per lane at most
+
+// Reference-sample addresses of a TU for this lane (entry lane + 32 j), ahead of the TU's turn.
+__device__ __forceinline__ void intra_fetch_addrs(const IntraOp& op, const uint16_t* __restrict__ addrTab, int lane, int a[IN_NJMAX])
+{
+  const int L = (4 << op_lg(op)) + 1;
+  const uint16_t* t = addrTab + op_slot(op);
+#pragma unroll
+  for (int j = 0; j < IN_NJMAX; j++)
+  {
+    const int i = lane + 32 * j;
+    a[j] = i < L ? (int)t[i] : 0;
+  }
+}
+
+// One TU on one warp, everything in shared memory / registers.  `a` = this lane's reference addresses (prefetched);
+// while the references are being gathered the addresses of the NEXT TU (`opn`) are fetched into `an`.
 template <int LG>
-__device__ __forceinline__ void intra_tu(const hmr_intra r, const uint16_t* __restrict__ addr, int16_t* __restrict__ tile,
-                                         const int16_t* __restrict__ res, int* __restrict__ line, int* __restrict__ flt,
-                                         const int x0, const int y0, const int bd, const bool strongAllowed, const int lane)
+__device__ __forceinline__ void intra_tu(const IntraOp op, const int a[IN_NJMAX], const bool hasNext, const IntraOp opn, int an[IN_NJMAX],
+                                         const uint16_t* __restrict__ addrTab, int16_t* __restrict__ tile, const int16_t* __restrict__ resB,
+                                         int* __restrict__ sref, const int bd, const int lane)
 {
   constexpr int N = 1 << LG, N2 = 2 * N, L = 4 * N + 1, NJ = (L + 31) / 32, S = (N * N + 31) / 32;
   const int maxv = (1 << bd) - 1;
-  // ---- reference line through the address table ----
+  // ---- gather the reference line: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right ----
+  int v[NJ];
 #pragma unroll
-  for (int j = 0; j < NJ; j++)
+  for (int j = 0; j < NJ; j++) v[j] = tile[a[j]];             // a[] is 0 (the constant slot) past the end of the line
+  if (hasNext) intra_fetch_addrs(opn, addrTab, lane, an);      // independent of the samples: overlaps the gather
+  const int flags = op_flags(op);
+  if (flags & OPF_FILTER)
   {
-    const int i = lane + 32 * j;
-    if (i < L) line[i] = tile[addr[i]];
-  }
-  __syncwarp();
-  const int* ref = line;
-  if (r.flags & HMR_INTRA_FILTER_REFS)
-  {
-    const int bl = line[0], tl = line[N2], tr = line[4 * N];
+    // [1 2 1] / 4 smoothing (or the bilinear "strong" variant) of everything but the two end points, neighbours by shuffle
     bool strong = false;
-    if (N == 32 && strongAllowed && (r.flags & HMR_INTRA_LUMA_RULES))
+    int bl = 0, tl = 0, tr = 0;
+    if (N == 32 && (flags & OPF_STRONG))
     {
+      bl = __shfl_sync(0xffffffffu, v[0], 0); tl = __shfl_sync(0xffffffffu, v[2 % NJ], 0); tr = __shfl_sync(0xffffffffu, v[4 % NJ], 0);
+      const int mid0 = __shfl_sync(0xffffffffu, v[1 % NJ], 0), mid1 = __shfl_sync(0xffffffffu, v[3 % NJ], 0);     // line[N], line[3N]
       const int thr = 1 << (bd - 5);
-      strong = abs(bl + tl - 2 * line[N]) < thr && abs(tl + tr - 2 * line[3 * N]) < thr;
+      strong = abs(bl + tl - 2 * mid0) < thr && abs(tl + tr - 2 * mid1) < thr;
     }
+    int f[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; j++)
     {
       const int i = lane + 32 * j;
-      if (i < L)
-      {
-        int v;
-        if (i == 0 || i == 4 * N) v = line[i];
-        else if (strong) v = i < N2 ? ((N2 - i) * bl + i * tl + N) >> (LG + 1) : (i == N2 ? tl : ((N2 - (i - N2)) * tl + (i - N2) * tr + N) >> (LG + 1));
-        else v = (line[i - 1] + 2 * line[i] + line[i + 1] + 2) >> 2;
-        flt[i] = v;
-      }
+      int up = __shfl_up_sync(0xffffffffu, v[j], 1), dn = __shfl_down_sync(0xffffffffu, v[j], 1);
+      if (j > 0)      { const int w = __shfl_sync(0xffffffffu, v[j - 1], 31); if (lane == 0) up = w; }
+      if (j + 1 < NJ) { const int w = __shfl_sync(0xffffffffu, v[j + 1], 0);  if (lane == 31) dn = w; }
+      int r;
+      if (i == 0 || i >= 4 * N) r = v[j];
+      else if (strong) r = i < N2 ? ((N2 - i) * bl + i * tl + N) >> (LG + 1) : (i == N2 ? tl : ((N2 - (i - N2)) * tl + (i - N2) * tr + N) >> (LG + 1));
+      else r = (up + 2 * v[j] + dn + 2) >> 2;
+      f[j] = r;
     }
-    ref = flt;
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NJ; j++) v[j] = f[j];
   }
+#pragma unroll
+  for (int j = 0; j < NJ; j++)
+  {
+    const int i = lane + 32 * j;
+    if (i < L) sref[i] = v[j];
+  }
+  __syncwarp();
+  const int* ref = sref;
 #define LEFT(y) ref[N2 - 1 - (y)]
 #define TOP(x)  ref[N2 + 1 + (x)]
-#define EMIT(i, y, x, v) tile[TIDX(y0 + (y), x0 + (x))] = (int16_t)clip3i(0, maxv, (int)(int16_t)(v) + (hasRes ? (int)res[i] : 0))
-  const int mode = r.mode;
-  const bool lumaRules = r.flags & HMR_INTRA_LUMA_RULES;
-  const bool hasRes = r.resid_off != HMR_NO_OFFSET;
-  if (mode == 0)
+#define EMIT(i, y, x, v) dst[(y) * IN_LD + (x)] = (int16_t)clip3i(0, maxv, (int)(int16_t)(v) + (hasRes ? (int)res[i] : 0))
+  const bool hasRes = op.y != HMR_NO_OFFSET;
+  const int16_t* res = resB + (hasRes ? op.y : 0u);
+  int16_t* dst = tile + op_org(op);
+  const int cls = op_cls(op);
+  if (cls == OP_PLANAR)
   {
     const int tn = TOP(N), ln = LEFT(N);
 #pragma unroll
@@ -165,16 +239,16 @@ __device__ __forceinline__ void intra_tu(const hmr_intra r, const uint16_t* __re
       if (N * N >= 32 || i < N * N)
       {
         const int y = i >> LG, x = i & (N - 1);
-        const int v = ((N - 1 - x) * LEFT(y) + (x + 1) * tn + (N - 1 - y) * TOP(x) + (y + 1) * ln + N) >> (LG + 1);
-        EMIT(i, y, x, v);
+        const int p = ((N - 1 - x) * LEFT(y) + (x + 1) * tn + (N - 1 - y) * TOP(x) + (y + 1) * ln + N) >> (LG + 1);
+        EMIT(i, y, x, p);
       }
     }
   }
-  else if (mode == 1)
+  else if (cls == OP_DC)
   {
     const int part = lane < N ? TOP(lane) + LEFT(lane) : 0;
     const int dc = (__reduce_add_sync(0xffffffffu, part) + N) >> (LG + 1);
-    const bool edge = lumaRules && N <= 16;
+    const bool edge = flags & OPF_DCEDGE;
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
@@ -182,27 +256,25 @@ __device__ __forceinline__ void intra_tu(const hmr_intra r, const uint16_t* __re
       if (N * N >= 32 || i < N * N)
       {
         const int y = i >> LG, x = i & (N - 1);
-        int v = dc;
+        int p = dc;
         if (edge)
         {
-          if (x == 0 && y == 0) v = (TOP(0) + LEFT(0) + 2 * dc + 2) >> 2;
-          else if (y == 0) v = (TOP(x) + 3 * dc + 2) >> 2;
-          else if (x == 0) v = (LEFT(y) + 3 * dc + 2) >> 2;
+          if (x == 0 && y == 0) p = (TOP(0) + LEFT(0) + 2 * dc + 2) >> 2;
+          else if (y == 0) p = (TOP(x) + 3 * dc + 2) >> 2;
+          else if (x == 0) p = (LEFT(y) + 3 * dc + 2) >> 2;
         }
-        EMIT(i, y, x, v);
+        EMIT(i, y, x, p);
       }
     }
   }
   else
   {
-    const bool ver = mode >= 18;
-    const int am = ver ? mode - 26 : 10 - mode;
-    const int aa = abs(am);
-    const int angle = am < 0 ? -c_angTab[aa] : c_angTab[aa];
+    const bool ver = flags & OPF_VER;
+    const int angle = op_angle(op);
     const int sgn = ver ? 1 : -1;                          // main reference rm[j >= 0] = ref[N2 + sgn*j]
-    if (angle == 0)
+    if (cls == OP_ANG0)
     {
-      const bool edge = lumaRules && N <= 16 && !(r.flags & HMR_INTRA_NO_EDGE_FLT);
+      const bool edge = flags & OPF_EDGE;
       const int corner = ref[N2];
 #pragma unroll
       for (int j = 0; j < S; j++)
@@ -212,13 +284,13 @@ __device__ __forceinline__ void intra_tu(const hmr_intra r, const uint16_t* __re
         {
           const int y = i >> LG, x = i & (N - 1);
           const int yy = ver ? y : x, xx = ver ? x : y;
-          int v = ref[N2 + sgn * (xx + 1)];
-          if (edge && xx == 0) v = clip3i(0, maxv, v + ((ref[N2 - sgn * (yy + 1)] - corner) >> 1));
-          EMIT(i, y, x, v);
+          int p = ref[N2 + sgn * (xx + 1)];
+          if (edge && xx == 0) p = clip3i(0, maxv, p + ((ref[N2 - sgn * (yy + 1)] - corner) >> 1));
+          EMIT(i, y, x, p);
         }
       }
     }
-    else if (angle > 0)
+    else if (cls == OP_ANGPOS)
     {
 #pragma unroll
       for (int j = 0; j < S; j++)
@@ -230,15 +302,15 @@ __device__ __forceinline__ void intra_tu(const hmr_intra r, const uint16_t* __re
           const int yy = ver ? y : x, xx = ver ? x : y;
           const int pos = (yy + 1) * angle, di = pos >> 5, df = pos & 31;
           const int k = xx + di + 1;
-          const int a = ref[N2 + sgn * k], b = ref[N2 + sgn * (k + 1)];     // df == 0: b has weight 0 (index <= 2N+... stays inside the line)
-          const int v = ((32 - df) * a + df * b + 16) >> 5;
-          EMIT(i, y, x, v);
+          const int pa = ref[N2 + sgn * k], pb = ref[N2 + sgn * (k + 1)];   // df == 0: pb has weight 0 (the index stays inside the padded line)
+          const int p = ((32 - df) * pa + df * pb + 16) >> 5;
+          EMIT(i, y, x, p);
         }
       }
     }
     else
     {
-      const int inv = c_invTab[aa];
+      const int inv = op_inv(op);
       // negative angle: rm[k < 0] is the side edge projected onto the main edge: side sample ((128 - k*inv) >> 8) - 1  (TComPrediction.cpp:396-404)
 #pragma unroll
       for (int j = 0; j < S; j++)
@@ -252,9 +324,9 @@ __device__ __forceinline__ void intra_tu(const hmr_intra r, const uint16_t* __re
           const int k0 = xx + di + 1, k1 = k0 + 1;
           const int i0 = k0 >= 0 ? N2 + sgn * k0 : N2 - sgn * ((128 - k0 * inv) >> 8);
           const int i1 = k1 >= 0 ? N2 + sgn * k1 : N2 - sgn * ((128 - k1 * inv) >> 8);
-          const int a = ref[i0], b = ref[i1];
-          const int v = ((32 - df) * a + df * b + 16) >> 5;
-          EMIT(i, y, x, v);
+          const int pa = ref[i0], pb = ref[i1];
+          const int p = ((32 - df) * pa + df * pb + 16) >> 5;
+          EMIT(i, y, x, p);
         }
       }
     }
@@ -278,12 +350,11 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   constexpr int TILE_PAD = (IN_TILE + 7) & ~7;
   int16_t* s_tileB = (int16_t*)s_dyn;                                        // [2][TILE_PAD]
   int16_t* s_resB = s_tileB + 2 * TILE_PAD;                                  // [2][resSamples] residuals of a CTU, compact layout relative to minoff
-  hmr_intra* s_rec = (hmr_intra*)(s_resB + 2 * resSamples);                  // [2][IN_MAXREC]
-  uint16_t* s_addr = (uint16_t*)(s_rec + 2 * IN_MAXREC);                     // [2][IN_ADDR]
-  __shared__ int s_lineBuf[4 * 32 + 8];   // unfiltered reference line: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right
-  __shared__ int s_fltBuf[4 * 32 + 8];    // smoothed
-  int* const s_line = s_lineBuf + 2;      // indices -1 and 4N+1 are touched (with weight 0) by the 45-degree modes
-  int* const s_flt = s_fltBuf + 2;
+  IntraOp* s_ops = (IntraOp*)(s_resB + 2 * resSamples);                      // [2][IN_MAXREC] decoded TUs of a CTU (chain's view)
+  hmr_intra* s_rec = (hmr_intra*)(s_ops + 2 * IN_MAXREC);                    // [IN_MAXREC] raw records (stagers only)
+  uint16_t* s_addr = (uint16_t*)(s_rec + IN_MAXREC);                         // [2][IN_ADDR]
+  __shared__ int s_refBuf[2][4 * 32 + 8]; // reference line of a TU: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right
+                                          // (two copies, alternating per TU: the next TU may write while a slow lane still reads)
   __shared__ uint32_t s_first[IN_MAXCOLS];
   __shared__ uint16_t s_count[IN_MAXCOLS];
   __shared__ unsigned s_minoff[2];
@@ -330,31 +401,32 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
     {
       const int b = n & 1;
       int16_t* tile = s_tileB + b * TILE_PAD;
-      const hmr_intra* rec = s_rec + b * IN_MAXREC;
+      const IntraOp* ops = s_ops + b * IN_MAXREC;
       const uint16_t* addrTab = s_addr + b * IN_ADDR;
       const int16_t* resB = s_resB + b * resSamples;
       const int count = s_count[c];
       const int ox = c * CTW;
-      bar_sync(BAR_FULL + b, IN_THREADS);                    // staged: tile, records, tables, residuals
-      const unsigned minoff = s_minoff[b];
+      bar_sync(BAR_FULL + b, IN_THREADS);                    // staged: tile, decoded TUs, tables, residuals
       if (prev == c - 1)                                     // left neighbours = what this warp produced a moment ago
         for (int y = lane; y < ch; y += 32) tile[TIDX(y, -1)] = s_col[y];
+      IntraOp op = ops[0];
+      int a[IN_NJMAX], an[IN_NJMAX];
+      intra_fetch_addrs(op, addrTab, lane, a);
       __syncwarp();
-      g.ox = ox;
       for (int k = 0; k < count; k++)
       {
-        const hmr_intra r = rec[k];
-        const uint16_t* a = addrTab + intra_slot(r, g);
-        const int16_t* res = resB + (r.resid_off != HMR_NO_OFFSET ? r.resid_off - minoff : 0u);
-        const int x0 = r.x - ox, y0 = r.y - oy;
-        switch (r.log2_size)
-        {
-          case 2:  intra_tu<2>(r, a, tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
-          case 3:  intra_tu<3>(r, a, tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
-          case 4:  intra_tu<4>(r, a, tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
-          default: intra_tu<5>(r, a, tile, res, s_line, s_flt, x0, y0, bd, strongAllowed, lane); break;
-        }
+        const bool hasNext = k + 1 < count;
+        const IntraOp opn = ops[hasNext ? k + 1 : k];
+        int* sref = &s_refBuf[0][2] + (k & 1) * (4 * 32 + 8);   // indices -1 and 4N+1 are touched (with weight 0) by the 45-degree modes
+        const int lg = op_lg(op);                            // compare chain, most frequent first (a jump table costs an indirect branch per TU)
+        if (lg == 3)      intra_tu<3>(op, a, hasNext, opn, an, addrTab, tile, resB, sref, bd, lane);
+        else if (lg == 2) intra_tu<2>(op, a, hasNext, opn, an, addrTab, tile, resB, sref, bd, lane);
+        else if (lg == 4) intra_tu<4>(op, a, hasNext, opn, an, addrTab, tile, resB, sref, bd, lane);
+        else              intra_tu<5>(op, a, hasNext, opn, an, addrTab, tile, resB, sref, bd, lane);
         __syncwarp();        // this TU's samples are in the tile before the next TU gathers its reference line
+        op = opn;
+#pragma unroll
+        for (int j = 0; j < IN_NJMAX; j++) a[j] = an[j];
       }
       const int cwc = min(CTW, W - ox);
       for (int y = lane; y < ch; y += 32) s_col[y] = tile[TIDX(y, cwc - 1)];
@@ -373,7 +445,8 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   {
     const int b = n & 1;
     int16_t* tile = s_tileB + b * TILE_PAD;
-    hmr_intra* rec = s_rec + b * IN_MAXREC;
+    hmr_intra* rec = s_rec;
+    IntraOp* ops = s_ops + b * IN_MAXREC;
     uint16_t* addrTab = s_addr + b * IN_ADDR;
     int16_t* resB = s_resB + b * resSamples;
     const int count = s_count[c];
@@ -426,6 +499,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
           for (int u = lane; u < units; u += 32) cp_async16(resB + rel + 8 * u, P.resid + r.resid_off + 8 * u);
       }
       intra_addr_table(r, addrTab + intra_slot(r, gc), gc, lane);
+      if (lane == 0) ops[k] = intra_make_op(r, gc, minoff, strongAllowed);
     }
     // the row above (x = -1 .. CTW+31) needs the CTU above-right to be final
     if (upProg)
@@ -509,7 +583,7 @@ static int intra_res_samples(const FrameParams& P)
 }
 static size_t intra_dyn_smem(int resSamples)
 {
-  return 2 * ((size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + IN_MAXREC * sizeof(hmr_intra) + IN_ADDR * sizeof(uint16_t));
+  return 2 * ((size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + IN_MAXREC * 16 + IN_ADDR * sizeof(uint16_t)) + IN_MAXREC * sizeof(hmr_intra);
 }
 
 int intra_max_coresident_blocks(int device)
