@@ -33,6 +33,9 @@ struct FrameParams
   const uint8_t*             bs;
   const int8_t*              qp;
   const uint8_t*             cu_flags;
+  uint4*                     intra_ops;       // [n_intra] decoded intra TUs           } scratch written by k_intra.cu's pre-pass
+  uint16_t*                  intra_tab;       // [3][n_ctu][4352] reference-address tables }
+  uint4*                     intra_prep;      // [3][n_ctu] residual span / table length   }
   unsigned long long*        intra_progress;  // [3][ctus_h], (epoch << 32) | CTUs finished in that row
   unsigned long long         epoch;
 };
@@ -47,3 +50,4 @@ void launch_deblock(const FrameParams& P, int dir, cudaStream_t s);
 void launch_sao(const FrameParams& P, cudaStream_t s);
 void launch_hash(const PlaneSet& pic, const int w[3], const int h[3], const int bd[3], int type, uint32_t* d_out, uint32_t* d_scratch, cudaStream_t s);
 int  intra_max_coresident_blocks(int device);
+size_t intra_table_bytes(int nctu);

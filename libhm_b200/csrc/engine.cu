@@ -53,6 +53,7 @@ struct hmr_engine
   int16_t* resid; size_t residCap;
   hmr_pu* mcTiles; size_t mcTilesCap;
   unsigned long long* progress; size_t progressCap;
+  uint4* intraOps; size_t intraOpsCap; uint16_t* intraTab; size_t intraTabBytes; uint4* intraPrep; size_t intraPrepBytes;
   unsigned long long epoch;
   int stageMask;
   bool timing;
@@ -217,6 +218,15 @@ static int ensure_geometry(hmr_engine* e, const hmr_frame_hdr& h)
       CK(cudaMemsetAsync(e->progress, 0, need * sizeof(unsigned long long), e->stream));
       e->progressCap = need;
     }
+    {
+      const size_t nctu = (size_t)e->ctusW * e->ctusH;
+      pool_free(e->device, e->intraTab, e->intraTabBytes);
+      pool_free(e->device, e->intraPrep, e->intraPrepBytes);
+      e->intraTabBytes = intra_table_bytes((int)nctu);
+      e->intraPrepBytes = 3 * nctu * sizeof(uint4);
+      CK(pool_malloc(e->device, (void**)&e->intraTab, e->intraTabBytes));
+      CK(pool_malloc(e->device, (void**)&e->intraPrep, e->intraPrepBytes));
+    }
     int r = alloc_planes(e, e->work);
     if (r) return r;
     e->workAlloc = true;
@@ -257,6 +267,7 @@ static void fill_params(hmr_engine* e, FrameParams& P, const hmr_frame_hdr& h, c
   P.qp = (const int8_t*)(dev + L.qp.off);
   P.cu_flags = hasCuf ? dev + L.cuf.off : nullptr;
   P.intra_progress = e->progress;
+  P.intra_ops = e->intraOps; P.intra_tab = e->intraTab; P.intra_prep = e->intraPrep;
   P.epoch = e->epoch;
 }
 
@@ -292,6 +303,14 @@ static int run_frame(hmr_engine* e, FrameParams& P, FrameEvents* fe)
     P.resid = e->resid;
   P.mc_tiles = e->mcTiles;
   }
+  if (h.n_intra > e->intraOpsCap)
+  {
+    CK(cudaStreamSynchronize(e->stream));
+    pool_free(e->device, e->intraOps, e->intraOpsCap * sizeof(uint4));
+    e->intraOpsCap = ALIGN_UP((size_t)h.n_intra * 3 / 2 + 1024, 1 << 16);
+    CK(pool_malloc(e->device, (void**)&e->intraOps, e->intraOpsCap * sizeof(uint4)));
+    P.intra_ops = e->intraOps;
+  }
   if (h.n_mc_tiles > e->mcTilesCap)
   {
     CK(cudaStreamSynchronize(e->stream));
@@ -308,7 +327,7 @@ static int run_frame(hmr_engine* e, FrameParams& P, FrameEvents* fe)
   mark(HMR_T_RESID);
   if ((m & HMR_STAGE_RESID) && h.n_tu) launches += launch_resid(P, e->stream);
   mark(HMR_T_INTRA);
-  if ((m & HMR_STAGE_INTRA) && h.n_intra) { CK(launch_intra(P, e->stream)); launches++; }
+  if ((m & HMR_STAGE_INTRA) && h.n_intra) { CK(launch_intra(P, e->stream)); launches += 2; }
   mark(HMR_T_DEBLOCK_V);
   if ((m & HMR_STAGE_DEBLOCK_V) && (h.flags & HMR_FRM_DEBLOCK)) { launch_deblock(P, 0, e->stream); launches++; }
   mark(HMR_T_DEBLOCK_H);
@@ -356,6 +375,7 @@ int hmr_engine_create(hmr_engine** out, int device)
   memset(e->slotAlloc, 0, sizeof(e->slotAlloc));
   memset(e->ring, 0, sizeof(e->ring));
   e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->mcTiles = nullptr; e->mcTilesCap = 0; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
+  e->intraOps = nullptr; e->intraOpsCap = 0; e->intraTab = nullptr; e->intraTabBytes = 0; e->intraPrep = nullptr; e->intraPrepBytes = 0;
   e->stageMask = HMR_STAGE_ALL; e->timing = false;
   memset(e->accMs, 0, sizeof(e->accMs)); e->accFrames = e->accLaunches = 0;
   e->timerInit = false;
@@ -391,6 +411,9 @@ void hmr_engine_destroy(hmr_engine* e)
   pool_free(e->device, e->resid, e->residCap * sizeof(int16_t));
   pool_free(e->device, e->mcTiles, e->mcTilesCap * sizeof(hmr_pu));
   pool_free(e->device, e->progress, e->progressCap * sizeof(unsigned long long));
+  pool_free(e->device, e->intraOps, e->intraOpsCap * sizeof(uint4));
+  pool_free(e->device, e->intraTab, e->intraTabBytes);
+  pool_free(e->device, e->intraPrep, e->intraPrepBytes);
   if (e->dHash) cudaFree(e->dHash);
   if (e->dHashRows) cudaFree(e->dHashRows);
   if (e->flushBuf) cudaFree(e->flushBuf);

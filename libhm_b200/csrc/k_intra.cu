@@ -20,9 +20,10 @@
 //     (x = -1 .. CTU+31, after waiting for the row above) and the column to the left, the residuals of its TUs
 //     (16-byte cp.async copies all in flight together), the records — then write CTU n back and publish the progress;
 //     hand-over through named barriers (bar.arrive / bar.sync), never a full __syncthreads;
-//   * the stagers also turn the records into reference-address tables: for every TU, entry i = shared-memory position
-//     of reference sample i AFTER HM's substitution of unavailable samples (pure function of the record, no sample
-//     data) — the whole fillReferenceSamples logic is off the critical path;
+//   * a pre-pass kernel (intra_prep_kernel, fully parallel over the picture) turns the records into reference-address
+//     tables — for every TU, entry i = shared-memory position of reference sample i AFTER HM's substitution of
+//     unavailable samples (pure function of the record, no sample data) — and into decoded 16-byte micro-ops; the
+//     whole fillReferenceSamples logic and all mode decoding are off the critical path, the stagers only copy;
 //   * warp 0 ("chain") runs size-templated, fully unrolled code per TU: gather the line through the table -> optional
 //     smoothing -> prediction (main-reference projection folded into the index) -> + residual -> back into the tile,
 //     with warp-level synchronisation only;
@@ -125,7 +126,7 @@ __device__ __forceinline__ int op_inv(const IntraOp& o)   { return o.w & 0xffff;
 enum { OP_PLANAR = 0, OP_DC = 1, OP_ANG0 = 2, OP_ANGPOS = 3, OP_ANGNEG = 4 };
 enum { OPF_FILTER = 1, OPF_STRONG = 2, OPF_EDGE = 4, OPF_VER = 8, OPF_DCEDGE = 16 };
 
-__device__ __forceinline__ IntraOp intra_make_op(const hmr_intra& r, const IntraGeom& g, unsigned minoff, bool strongAllowed)
+__device__ __forceinline__ IntraOp intra_make_op(const hmr_intra& r, const IntraGeom& g, unsigned minoff, bool strongAllowed, int slot)
 {
   const int N = 1 << r.log2_size;
   const bool luma = r.flags & HMR_INTRA_LUMA_RULES;
@@ -148,7 +149,7 @@ __device__ __forceinline__ IntraOp intra_make_op(const hmr_intra& r, const Intra
     cls = angle == 0 ? OP_ANG0 : (angle > 0 ? OP_ANGPOS : OP_ANGNEG);
   }
   IntraOp op;
-  op.x = (uint32_t)TIDX(r.y - g.oy, r.x - g.ox) | ((uint32_t)intra_slot(r, g) << 16);
+  op.x = (uint32_t)TIDX(r.y - g.oy, r.x - g.ox) | ((uint32_t)slot << 16);
   op.y = r.resid_off != HMR_NO_OFFSET ? r.resid_off - minoff : HMR_NO_OFFSET;
   op.z = (uint32_t)(angle & 0xff) | ((uint32_t)r.log2_size << 8) | ((uint32_t)cls << 16) | ((uint32_t)f << 24);
   op.w = (uint32_t)inv;
@@ -336,6 +337,49 @@ __device__ __forceinline__ void intra_tu(const IntraOp op, const int a[IN_NJMAX]
 #undef EMIT
 }
 
+// ---- pre-pass: everything about the intra TUs that does not depend on sample data, for the whole picture at once ----
+// One CTA per (component, CTU): reference-address tables (compact, TU after TU), decoded micro-ops, and the CTU's
+// residual span.  The wavefront kernel below only copies these into shared memory.
+__global__ void __launch_bounds__(128) intra_prep_kernel(const __grid_constant__ FrameParams P)
+{
+  __shared__ int s_off[IN_MAXREC + 1];
+  __shared__ unsigned s_mn, s_mx;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nctu = P.ctus_w * P.ctus_h;
+  const int comp = blockIdx.x / nctu, ctu = blockIdx.x - comp * nctu;
+  if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) return;
+  const hmr_ctu_intra_range rg = P.irange[ctu];
+  const uint32_t first = rg.first[comp];
+  const int count = (int)min(rg.count[comp], (uint32_t)IN_MAXREC);
+  if (count == 0) { if (tid == 0) P.intra_prep[blockIdx.x] = make_uint4(0, 0, 0, 0); return; }
+  const int csx = comp ? P.csx : 0, csy = comp ? P.csy : 0;
+  IntraGeom g;
+  g.CTW = (1 << P.hdr.log2_ctu) >> csx; g.CTH = (1 << P.hdr.log2_ctu) >> csy;
+  g.uws = 2 - csx; g.uhs = 2 - csy; g.gw = g.CTW >> 2;
+  g.ox = (ctu % P.ctus_w) * g.CTW; g.oy = (ctu / P.ctus_w) * g.CTH;
+  if (tid == 0) { s_mn = 0xffffffffu; s_mx = 0; s_off[0] = 0; }
+  __syncthreads();
+  for (int k = tid; k < count; k += 128)
+  {
+    const hmr_intra r = P.intra[first + k];
+    s_off[k + 1] = (4 << r.log2_size) + 1;
+    if (r.resid_off != HMR_NO_OFFSET) { atomicMin(&s_mn, r.resid_off); atomicMax(&s_mx, r.resid_off + (1u << (2 * r.log2_size))); }
+  }
+  __syncthreads();
+  if (tid == 0) for (int k = 0; k < count; k++) s_off[k + 1] += s_off[k];     // <= 256 short steps; everything else is parallel
+  __syncthreads();
+  const unsigned mn = s_mn;
+  const bool strongAllowed = P.hdr.flags & HMR_FRM_STRONG_INTRA_SMOOTHING;
+  uint16_t* tab = P.intra_tab + (size_t)blockIdx.x * IN_ADDR;
+  for (int k = warp; k < count; k += 4)
+  {
+    const hmr_intra r = P.intra[first + k];
+    intra_addr_table(r, tab + s_off[k], g, lane);
+    if (lane == 0) P.intra_ops[first + k] = intra_make_op(r, g, mn, strongAllowed, s_off[k]);
+  }
+  if (tid == 0) P.intra_prep[blockIdx.x] = make_uint4(mn, s_mx > mn ? s_mx - mn : 0u, (unsigned)s_off[count], 0u);
+}
+
 // named barriers (id 0 is __syncthreads)
 #define BAR_FULL 1     // +buffer: stagers arrive, chain waits  -> "CTU staged"
 #define BAR_DONE 3     // +buffer: chain arrives, stagers wait  -> "CTU predicted"
@@ -350,14 +394,13 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   constexpr int TILE_PAD = (IN_TILE + 7) & ~7;
   int16_t* s_tileB = (int16_t*)s_dyn;                                        // [2][TILE_PAD]
   int16_t* s_resB = s_tileB + 2 * TILE_PAD;                                  // [2][resSamples] residuals of a CTU, compact layout relative to minoff
-  IntraOp* s_ops = (IntraOp*)(s_resB + 2 * resSamples);                      // [2][IN_MAXREC] decoded TUs of a CTU (chain's view)
-  hmr_intra* s_rec = (hmr_intra*)(s_ops + 2 * IN_MAXREC);                    // [IN_MAXREC] raw records (stagers only)
-  uint16_t* s_addr = (uint16_t*)(s_rec + IN_MAXREC);                         // [2][IN_ADDR]
+  IntraOp* s_ops = (IntraOp*)(s_resB + 2 * resSamples);                      // [2][IN_MAXREC] decoded TUs of a CTU
+  uint16_t* s_addr = (uint16_t*)(s_ops + 2 * IN_MAXREC);                     // [2][IN_ADDR]
   __shared__ int s_refBuf[2][4 * 32 + 8]; // reference line of a TU: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right
                                           // (two copies, alternating per TU: the next TU may write while a slow lane still reads)
   __shared__ uint32_t s_first[IN_MAXCOLS];
   __shared__ uint16_t s_count[IN_MAXCOLS];
-  __shared__ unsigned s_minoff[2];
+  __shared__ uint4 s_prep[IN_MAXCOLS];    // per CTU of this row: x = first residual, y = residual span, z = table entries
   __shared__ int16_t s_col[IN_MAXCT];     // right-most column of the CTU the chain just finished (left neighbours of the next one)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int comp = blockIdx.x / P.ctus_h, row = blockIdx.x % P.ctus_h;
@@ -385,6 +428,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
     const hmr_ctu_intra_range rg = P.irange[row * ctusW + c];
     s_first[c] = rg.first[comp];
     s_count[c] = (uint16_t)min(rg.count[comp], (uint32_t)IN_MAXREC);
+    s_prep[c] = P.intra_prep[(size_t)comp * ctusW * P.ctus_h + (size_t)row * ctusW + c];
   }
   if (tid == 0) { s_tileB[0] = s_tileB[TILE_PAD] = (int16_t)(1 << (bd - 1)); }
   __syncthreads();
@@ -445,7 +489,6 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   {
     const int b = n & 1;
     int16_t* tile = s_tileB + b * TILE_PAD;
-    hmr_intra* rec = s_rec;
     IntraOp* ops = s_ops + b * IN_MAXREC;
     uint16_t* addrTab = s_addr + b * IN_ADDR;
     int16_t* resB = s_resB + b * resSamples;
@@ -474,33 +517,19 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
         cp_async8(&tile[TIDX(y, 4 * v)], plane + (size_t)(oy + y) * pitch + ox + 4 * v);
       }
     }
-    if (st == 0) s_minoff[b] = 0xffffffffu;
-    bar_sync(BAR_STAGE, IN_STAGERS);
-    for (int i = st; i < count; i += IN_STAGERS)
     {
-      const uint4 q = __ldcg((const uint4*)(P.intra + first) + i);
-      ((uint4*)rec)[i] = q;
-      if (q.w != HMR_NO_OFFSET) atomicMin(&s_minoff[b], q.w);
+      const uint4 prep = s_prep[c];
+      const uint4* gops = P.intra_ops + first;                                   // decoded TUs
+      for (int i = st; i < count; i += IN_STAGERS) cp_async16(ops + i, gops + i);
+      const uint16_t* gtab = P.intra_tab + ((size_t)comp * ctusW * P.ctus_h + (size_t)row * ctusW + c) * IN_ADDR;
+      const int tabVec = ((int)prep.z + 7) >> 3;                                 // reference-address tables, 8 entries per copy
+      for (int i = st; i < tabVec; i += IN_STAGERS) cp_async16(addrTab + 8 * i, gtab + 8 * i);
+      const int resVec = (int)(min(prep.y, (unsigned)resSamples) >> 3);          // the CTU's residual span (a multiple of 16 samples)
+      const int16_t* gres = P.resid + prep.x;
+      for (int i = st; i < resVec; i += IN_STAGERS) cp_async16(resB + 8 * i, gres + 8 * i);
     }
     if (ox > 0 && prev != c - 1)                             // left CTU has no intra blocks: its samples have been final since the kernel started
       for (int y = st; y < ch; y += IN_STAGERS) tile[TIDX(y, -1)] = __ldcg(plane + (size_t)(oy + y) * pitch + ox - 1);
-    bar_sync(BAR_STAGE, IN_STAGERS);
-    const unsigned minoff = s_minoff[b];
-    IntraGeom gc = g;
-    gc.ox = ox;
-    for (int k = swarp; k < count; k += IN_STAGERS / 32)
-    {
-      const hmr_intra r = rec[k];
-      if (r.resid_off != HMR_NO_OFFSET)
-      {
-        const int units = 1 << (2 * r.log2_size - 3);        // N*N int16 in 16-byte units
-        const uint32_t rel = r.resid_off - minoff;
-        if (rel + 8u * units <= (uint32_t)resSamples)        // always true for a well-formed frame (one CTU's levels are contiguous)
-          for (int u = lane; u < units; u += 32) cp_async16(resB + rel + 8 * u, P.resid + r.resid_off + 8 * u);
-      }
-      intra_addr_table(r, addrTab + intra_slot(r, gc), gc, lane);
-      if (lane == 0) ops[k] = intra_make_op(r, gc, minoff, strongAllowed);
-    }
     // the row above (x = -1 .. CTW+31) needs the CTU above-right to be final
     if (upProg)
     {
@@ -583,8 +612,10 @@ static int intra_res_samples(const FrameParams& P)
 }
 static size_t intra_dyn_smem(int resSamples)
 {
-  return 2 * ((size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + IN_MAXREC * 16 + IN_ADDR * sizeof(uint16_t)) + IN_MAXREC * sizeof(hmr_intra);
+  return 2 * ((size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + IN_MAXREC * 16 + IN_ADDR * sizeof(uint16_t));
 }
+
+size_t intra_table_bytes(int nctu) { return (size_t)3 * nctu * IN_ADDR * sizeof(uint16_t); }
 
 int intra_max_coresident_blocks(int device)
 {
@@ -601,6 +632,7 @@ cudaError_t launch_intra(const FrameParams& P, cudaStream_t s)
   if (P.hdr.n_intra == 0) return cudaSuccess;
   if (P.ctus_w > IN_MAXCOLS) return cudaErrorInvalidValue;
   int resSamples = intra_res_samples(P);
+  intra_prep_kernel<<<3 * P.ctus_w * P.ctus_h, 128, 0, s>>>(P);
   void* args[] = { (void*)&P, (void*)&resSamples };
   return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(3 * P.ctus_h), dim3(IN_THREADS), args, intra_dyn_smem(resSamples), s);
 }
