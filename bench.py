@@ -189,6 +189,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the reconstruction engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     frames = records.read_dump(rec_path)
     F = len(frames)
