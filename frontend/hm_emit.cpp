@@ -60,6 +60,7 @@ struct HmEmitter::CuCtx
 HmEmitter::HmEmitter(HmFrameSink* sink)
   : m_sink(sink), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0), m_tCtu(0), m_tBs(0), m_tPic(0), m_tSink(0), m_nPic(0)
 {
+  m_in422SubTu = false;
   // product path: HM's whole-CTU coefficient zero fills are skipped (hm_fast.cpp); verification / golden generation keep them
   m_cleanCoeffs = !sink->wantHmRecon();
   memset(&m_hdr, 0, sizeof(m_hdr));
@@ -374,8 +375,14 @@ void HmEmitter::interResidual(CuCtx& c, int compIdx, void* pTu)
     if (rect.width != rect.height)
     {
       // 4:2:2 chroma: two square halves, both run through the transform (TComTrQuant.cpp:1437-1464)
+      // Each half has its own cbf one level down (TDecSbac::parseQtCbf); HM runs both through invTransformNxN, the one
+      // without coded levels on an all-zero block — which only exists if the storage was zero-filled (hm_fast.cpp), so say so.
       TComTURecurse sub(rTu, false, TComTU::VERTICAL_SPLIT, true, compID);
-      do { emitResidualTU(c, compIdx, &sub, false, coded, alpha); } while (sub.nextSection(rTu));
+      do
+      {
+        const bool subCoded = coded && ctu->getCbf(sub.GetAbsPartIdxTU(compID), compID, trMode + 1) != 0;
+        emitResidualTU(c, compIdx, &sub, false, subCoded, alpha);
+      } while (sub.nextSection(rTu));
     }
     else emitResidualTU(c, compIdx, &rTu, false, coded, alpha);
   }
@@ -443,7 +450,9 @@ void HmEmitter::intraBlk(CuCtx& c, int compIdx, void* pTu)
   if (W != Hh)
   {
     TComTURecurse sub(rTu, false, TComTU::VERTICAL_SPLIT, true, compID);
+    m_in422SubTu = true;
     do { intraBlk(c, compIdx, &sub); } while (sub.nextSection(rTu));
+    m_in422SubTu = false;
     return;
   }
   const UInt chPredMode  = ctu->getIntraDir(toChannelType(compID), absPartIdx);
@@ -494,7 +503,11 @@ void HmEmitter::intraBlk(CuCtx& c, int compIdx, void* pTu)
   }
 
   // residual (TDecCu.cpp:560-586) + cross-component prediction (TDecCu.cpp:600-625)
-  const bool coded = ctu->getCbf(absPartIdx, compID, rTu.GetTransformDepthRel()) != 0;
+  // HM tests the cbf at the TU's own level (TDecCu.cpp:560); for the two halves of a 4:2:2 chroma TU that is the COMBINED
+  // flag, and the half without levels is inverse-transformed from an all-zero block — which only exists if the storage
+  // was zero-filled (hm_fast.cpp).  Each half has its own flag one level down (TDecSbac::parseQtCbf): use it.
+  bool coded = ctu->getCbf(absPartIdx, compID, rTu.GetTransformDepthRel()) != 0;
+  if (coded && m_in422SubTu) coded = ctu->getCbf(rTu.GetAbsPartIdxTU(compID), compID, rTu.GetTransformDepthRel() + 1) != 0;
   const int alpha = isChroma(compID) ? ctu->getCrossComponentPredictionAlpha(absPartIdx, compID) : 0;
   const bool keepLuma = bIsLuma && (m_hdr.flags & HMR_FRM_HAS_CCP); // chroma CCP may read a zero luma residual
   r.resid_off = HMR_NO_OFFSET;

@@ -94,6 +94,7 @@ private:
   std::vector<int8_t>              m_qp;
   std::vector<uint8_t>             m_cuFlags;
   int m_bsStride, m_qpStride;
+  bool m_in422SubTu;                       // inside the two square halves of a 4:2:2 chroma TU
   bool m_cleanCoeffs;                      // hm_fast.cpp: HM's whole-CTU coefficient zero fills are skipped for this decoder
   double m_tCtu, m_tBs, m_tPic, m_tSink;   // HMDEC_B200_STATS: host time spent emitting records
   int m_nPic;
