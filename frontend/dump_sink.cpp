@@ -56,6 +56,7 @@ public:
     if (d.bs) section(TAG('B','S',' ',' '), d.bs, nbs);
     section(TAG('Q','P',' ',' '), d.qp, nqp);
     if (d.cu_flags) section(TAG('C','U','F','L'), d.cu_flags, nqp);
+    if (d.scaling) section(TAG('S','C','A','L'), d.scaling, HMR_SCALING_BYTES);
     if (m_recordsOnly) { section(TAG('E','N','D',' '), NULL, 0); fflush(m_fp); }
   }
 

@@ -117,7 +117,26 @@ void HmEmitter::beginFrame(TComPic* pic, TComDataCU* ctu)
   if (sps->getUseStrongIntraSmoothing())     m_hdr.flags |= HMR_FRM_STRONG_INTRA_SMOOTHING;
   if (pps->getUseCrossComponentPrediction()) m_hdr.flags |= HMR_FRM_HAS_CCP;
   if (sps->getUseExtendedPrecision())        fail("extended_precision_processing");
-  if (sps->getScalingListFlag())             fail("scaling lists");
+  if (sps->getScalingListFlag())
+  {
+    // the list TDecTop installs for this slice (TDecTop.cpp: SPS list, overridden by the PPS list, else the default one),
+    // expanded per transform size exactly like TComTrQuant::xSetScalingListDec / processScalingListDec
+    m_hdr.flags |= HMR_FRM_SCALING_LIST;
+    TComScalingList* sl = slice->getScalingList();
+    m_scaling.assign(HMR_SCALING_BYTES, 16);
+    for (UInt sizeId = 0; sizeId < SCALING_LIST_SIZE_NUM; sizeId++)
+    {
+      const int N = (int)g_scalingListSizeX[sizeId];
+      const int stored = N < MAX_MATRIX_SIZE_NUM ? N : MAX_MATRIX_SIZE_NUM, ratio = N / stored;
+      for (UInt listId = 0; listId < SCALING_LIST_NUM; listId++)
+      {
+        const Int* coeff = sl->getScalingListAddress(sizeId, listId);
+        uint8_t* dst = &m_scaling[HMR_SCALING_OFFSET(sizeId) + listId * N * N];
+        for (int j = 0; j < N; j++) for (int i = 0; i < N; i++) dst[j * N + i] = (uint8_t)coeff[stored * (j / ratio) + i / ratio];
+        if (ratio > 1) dst[0] = (uint8_t)sl->getScalingListDC(sizeId, listId);
+      }
+    }
+  }
   if (g_uiMaxCUWidth != g_uiMaxCUHeight)     fail("non-square CTU");
   if ((g_uiMaxCUWidth >> g_uiMaxCUDepth) != 4) fail("minimum partition size != 4");
   if (pic->getChromaFormat() == CHROMA_400)  fail("4:0:0");
@@ -678,6 +697,7 @@ void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdap
   d.intra = m_intra.data(); d.intra_range = m_range.data();
   d.pu = m_pu.data(); d.pu_tile_prefix = m_puPrefix.data();
   d.ctu = m_ctu.data();
+  d.scaling = (m_hdr.flags & HMR_FRM_SCALING_LIST) ? m_scaling.data() : NULL;
   d.bs = (m_hdr.flags & HMR_FRM_DEBLOCK) ? m_bs.data() : NULL;
   d.qp = m_qp.data();
   d.cu_flags = (m_hdr.flags & HMR_FRM_HAS_NOFILTER) ? m_cuFlags.data() : NULL;

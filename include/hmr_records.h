@@ -36,7 +36,15 @@ enum {
   HMR_FRM_HAS_CCP               = 1u << 4, /* PPS cross_component_prediction (4:4:4): luma residuals are kept for chroma TUs */
   HMR_FRM_IS_REFERENCE          = 1u << 5, /* informational */
   HMR_FRM_INTRA_ONLY            = 1u << 6, /* informational: no PU records */
+  HMR_FRM_SCALING_LIST          = 1u << 7, /* scaling lists in use: hmr_frame_desc.scaling is valid (TComTrQuant.cpp:1230-1276) */
 };
+
+/* Scaling factors m[y][x] (1..255) of the active scaling list, expanded to the transform size the way
+ * TComTrQuant::processScalingListDec does (TComTrQuant.cpp:3092-3106: 16x16/32x32 replicate the 8x8 list, DC replaced):
+ * for size s = log2(N)-2 and list l = 3*(inter) + component: N*N bytes at HMR_SCALING_OFFSET(s) + l*N*N, raster like the levels.
+ * The dequantiser multiplies by g_invQuantScales[qp%6] * m instead of g_invQuantScales[qp%6] << 4. */
+#define HMR_SCALING_OFFSET(s) ((s) == 0 ? 0 : (s) == 1 ? 96 : (s) == 2 ? 480 : 2016)
+#define HMR_SCALING_BYTES     8160
 
 typedef struct hmr_frame_hdr {
   uint32_t magic;            /* HMR_MAGIC */
@@ -168,6 +176,7 @@ typedef struct hmr_frame_desc {
   const uint8_t*             bs;              /* [(W/4)*(H/4)] or NULL when !HMR_FRM_DEBLOCK */
   const int8_t*              qp;              /* [(W/8)*(H/8)] */
   const uint8_t*             cu_flags;        /* [(W/8)*(H/8)] or NULL when !HMR_FRM_HAS_NOFILTER */
+  const uint8_t*             scaling;         /* [HMR_SCALING_BYTES] or NULL when !HMR_FRM_SCALING_LIST */
 } hmr_frame_desc;
 
 #ifdef __cplusplus

@@ -33,6 +33,7 @@ struct FrameParams
   const uint8_t*             bs;
   const int8_t*              qp;
   const uint8_t*             cu_flags;
+  const uint8_t*             scaling;         // scaling factors (hmr_records.h: HMR_SCALING_OFFSET) or nullptr
   uint4*                     intra_ops;       // [n_intra] decoded intra TUs           } scratch written by k_intra.cu's pre-pass
   uint16_t*                  intra_tab;       // [3][n_ctu][4352] reference-address tables }
   uint4*                     intra_prep;      // [3][n_ctu] residual span / table length   }

@@ -21,7 +21,7 @@
 struct Section { size_t off, bytes; };
 struct Layout
 {
-  Section hdr, tu, coef, intra, irange, pu, prefix, ctu, bs, qp, cuf;
+  Section hdr, tu, coef, intra, irange, pu, prefix, ctu, bs, qp, cuf, scal;
   size_t total;
 };
 
@@ -116,7 +116,7 @@ static void pool_free_host(void* p, size_t bytes)
 static int fail(hmr_engine* e, int code, const std::string& msg) { if (e) e->err = msg; return code; }
 #define CK(call) do { cudaError_t _r = (call); if (_r != cudaSuccess) return fail(e, HMR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); } while (0)
 
-static Layout make_layout(const hmr_frame_hdr& h, bool hasBs, bool hasCuf)
+static Layout make_layout(const hmr_frame_hdr& h, bool hasBs, bool hasCuf, bool hasScal = false)
 {
   Layout L;
   size_t off = 0;
@@ -134,6 +134,7 @@ static Layout make_layout(const hmr_frame_hdr& h, bool hasBs, bool hasCuf)
   put(L.bs, hasBs ? nbs : 0);
   put(L.qp, nqp);
   put(L.cuf, hasCuf ? nqp : 0);
+  put(L.scal, hasScal ? HMR_SCALING_BYTES : 0);
   L.total = off;
   return L;
 }
@@ -151,6 +152,7 @@ static void pack(uint8_t* dst, const Layout& L, const hmr_frame_desc* f)
   if (L.bs.bytes)     memcpy(dst + L.bs.off, f->bs, L.bs.bytes);
   if (L.qp.bytes)     memcpy(dst + L.qp.off, f->qp, L.qp.bytes);
   if (L.cuf.bytes)    memcpy(dst + L.cuf.off, f->cu_flags, L.cuf.bytes);
+  if (L.scal.bytes)   memcpy(dst + L.scal.off, f->scaling, L.scal.bytes);
 }
 
 static int validate(hmr_engine* e, const hmr_frame_desc* f)
@@ -167,6 +169,7 @@ static int validate(hmr_engine* e, const hmr_frame_desc* f)
   if ((h.n_tu && (!f->tu || !f->coef)) || (h.n_intra && !f->intra) || (h.n_pu && !f->pu) || !f->pu_tile_prefix || !f->ctu || !f->intra_range || !f->qp)
     return fail(e, HMR_ERR_ARG, "missing record array");
   if ((h.flags & HMR_FRM_DEBLOCK) && !f->bs) return fail(e, HMR_ERR_ARG, "HMR_FRM_DEBLOCK without a BS map");
+  if ((h.flags & HMR_FRM_SCALING_LIST) && !f->scaling) return fail(e, HMR_ERR_ARG, "HMR_FRM_SCALING_LIST without scaling factors");
   return HMR_OK;
 }
 
@@ -266,6 +269,7 @@ static void fill_params(hmr_engine* e, FrameParams& P, const hmr_frame_hdr& h, c
   P.bs = hasBs ? dev + L.bs.off : nullptr;
   P.qp = (const int8_t*)(dev + L.qp.off);
   P.cu_flags = hasCuf ? dev + L.cuf.off : nullptr;
+  P.scaling = L.scal.bytes ? dev + L.scal.off : nullptr;
   P.intra_progress = e->progress;
   P.intra_ops = e->intraOps; P.intra_tab = e->intraTab; P.intra_prep = e->intraPrep;
   P.epoch = e->epoch;
@@ -444,7 +448,7 @@ int hmr_submit_frame(hmr_engine* e, const hmr_frame_desc* f)
   if ((r = ensure_geometry(e, h))) return r;
   if ((r = ensure_slot(e, h.out_slot))) return r;
   const bool hasBs = f->bs != nullptr, hasCuf = f->cu_flags != nullptr;
-  const Layout L = make_layout(h, hasBs, hasCuf);
+  const Layout L = make_layout(h, hasBs, hasCuf, (h.flags & HMR_FRM_SCALING_LIST) != 0);
 
   hmr_engine::Stage& st = e->ring[e->ringPos];
   e->ringPos = (e->ringPos + 1) % RING;
@@ -598,7 +602,7 @@ int hmr_upload_frame(hmr_engine* e, const hmr_frame_desc* f, hmr_resident_frame*
   hmr_resident_frame* rf = new hmr_resident_frame();
   rf->hdr = *f->hdr;
   rf->hasBs = f->bs != nullptr; rf->hasCuf = f->cu_flags != nullptr;
-  rf->lay = make_layout(rf->hdr, rf->hasBs, rf->hasCuf);
+  rf->lay = make_layout(rf->hdr, rf->hasBs, rf->hasCuf, (rf->hdr.flags & HMR_FRM_SCALING_LIST) != 0);
   std::vector<uint8_t> tmp(rf->lay.total);
   pack(tmp.data(), rf->lay, f);
   cudaError_t ce = cudaMalloc(&rf->dev, rf->lay.total);

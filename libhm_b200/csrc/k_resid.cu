@@ -68,8 +68,10 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
   if (plainTransform)
   {
     const int per = t.qp / 6, rem = t.qp - per * 6, scale = c_invq[rem];
-    const int rshift = 6 - ((15 - bd - LOG2N) + per);
-    const int inBits = min(16, 32 + rshift - 7);
+    // scaling lists (xDeQuant, TComTrQuant.cpp:1230-1276): per-coefficient factor, 4 more bits of right shift
+    const uint8_t* __restrict__ sl = P.scaling ? P.scaling + HMR_SCALING_OFFSET(LOG2N - 2) + (((t.flags & HMR_TU_INTRA) ? 0 : 3) + t.comp) * NN : nullptr;
+    const int rshift = 6 - ((15 - bd - LOG2N) + per) + (sl ? 4 : 0);
+    const int inBits = min(16, 32 + rshift - (sl ? 15 : 7));
     const int inMin = -(1 << (inBits - 1)), inMax = (1 << (inBits - 1)) - 1;
     const bool dst = (LOG2N == 2) && (t.flags & HMR_TU_DST);
 #pragma unroll
@@ -83,7 +85,8 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
       const int q = lv[n];
       if (q == 0) continue;
       const int qc = clip3i(inMin, inMax, q);
-      int c = rshift > 0 ? (qc * scale + (1 << (rshift - 1))) >> rshift : (int)((unsigned)(qc * scale) << (-rshift));
+      const int sc = sl ? scale * (int)__ldg(sl + n * N + j) : scale;
+      int c = rshift > 0 ? (qc * sc + (1 << (rshift - 1))) >> rshift : (int)((unsigned)(qc * sc) << (-rshift));
       c = clip3i(-32768, 32767, c);
 #pragma unroll
       for (int k = 0; k < N; k++)
@@ -138,14 +141,18 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
     {
       const int per = t.qp / 6, rem = t.qp - per * 6, scale = c_invq[rem];
       const int trShift = 15 - bd - LOG2N;
-      const int rshift = 6 - (trShift + per);
-      const int inBits = min(16, 32 + rshift - 7);
+      // getUseScalingList: a transform-skipped block uses the lists only when it is 4x4
+      const uint8_t* __restrict__ sl = (P.scaling && LOG2N == 2) ? P.scaling + HMR_SCALING_OFFSET(0) + (((t.flags & HMR_TU_INTRA) ? 0 : 3) + t.comp) * NN : nullptr;
+      const int rshift = 6 - (trShift + per) + (sl ? 4 : 0);
+      const int inBits = min(16, 32 + rshift - (sl ? 15 : 7));
       const int inMin = -(1 << (inBits - 1)), inMax = (1 << (inBits - 1)) - 1;
       for (int y = 0; y < N; y++)
       {
         const int i = y * N + j;
-        const int qc = clip3i(inMin, inMax, (int)lev[(t.flags & HMR_TU_ROTATE) ? NN - 1 - i : i]);
-        int c = rshift > 0 ? (qc * scale + (1 << (rshift - 1))) >> rshift : (int)((unsigned)(qc * scale) << (-rshift));
+        const int src = (t.flags & HMR_TU_ROTATE) ? NN - 1 - i : i;
+        const int qc = clip3i(inMin, inMax, (int)lev[src]);
+        const int sc = sl ? scale * (int)sl[src] : scale;
+        int c = rshift > 0 ? (qc * sc + (1 << (rshift - 1))) >> rshift : (int)((unsigned)(qc * sc) << (-rshift));
         c = clip3i(-32768, 32767, c);
         const int r = trShift >= 0 ? (c + (trShift == 0 ? 0 : (1 << (trShift - 1)))) >> trShift : c << (-trShift);
         sb[y * LD + j] = (int16_t)r;

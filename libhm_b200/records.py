@@ -11,7 +11,7 @@ HMR_MAGIC = 0x52524D48
 HMR_VERSION = 4
 HMR_NO_OFFSET = 0xFFFFFFFF
 
-FRM_STRONG_INTRA_SMOOTHING, FRM_DEBLOCK, FRM_SAO, FRM_HAS_NOFILTER, FRM_HAS_CCP, FRM_IS_REFERENCE, FRM_INTRA_ONLY = (1 << i for i in range(7))
+FRM_STRONG_INTRA_SMOOTHING, FRM_DEBLOCK, FRM_SAO, FRM_HAS_NOFILTER, FRM_HAS_CCP, FRM_IS_REFERENCE, FRM_INTRA_ONLY, FRM_SCALING_LIST = (1 << i for i in range(8))
 TU_CODED, TU_INTRA, TU_DST, TU_TSKIP, TU_BYPASS, TU_ROTATE, TU_RDPCM_H, TU_RDPCM_V = (1 << i for i in range(8))
 
 HDR_DT = np.dtype([("magic", "<u4"), ("version", "<u4"), ("width", "<i4"), ("height", "<i4"), ("poc", "<i4"),
@@ -33,17 +33,17 @@ assert (HDR_DT.itemsize, TU_DT.itemsize, INTRA_DT.itemsize, IRNG_DT.itemsize, PU
 
 class FrameDesc(C.Structure):
     """struct hmr_frame_desc"""
-    _fields_ = [(n, C.c_void_p) for n in ("hdr", "tu", "coef", "intra", "intra_range", "pu", "pu_tile_prefix", "ctu", "bs", "qp", "cu_flags")]
+    _fields_ = [(n, C.c_void_p) for n in ("hdr", "tu", "coef", "intra", "intra_range", "pu", "pu_tile_prefix", "ctu", "bs", "qp", "cu_flags", "scaling")]
 
 
 _SECTIONS = {b"HDR ": ("hdr", HDR_DT), b"TU  ": ("tu", TU_DT), b"COEF": ("coef", np.dtype("<i2")), b"INTR": ("intra", INTRA_DT),
              b"IRNG": ("intra_range", IRNG_DT), b"PU  ": ("pu", PU_DT), b"PUPF": ("pu_tile_prefix", np.dtype("<u4")),
-             b"CTU ": ("ctu", CTU_DT), b"BS  ": ("bs", np.dtype("u1")), b"QP  ": ("qp", np.dtype("i1")), b"CUFL": ("cu_flags", np.dtype("u1"))}
+             b"CTU ": ("ctu", CTU_DT), b"BS  ": ("bs", np.dtype("u1")), b"QP  ": ("qp", np.dtype("i1")), b"CUFL": ("cu_flags", np.dtype("u1")), b"SCAL": ("scaling", np.dtype("u1"))}
 
 
 class Frame:
     """One picture's records (+ optional golden data recorded from HM's own CPU reconstruction)."""
-    FIELDS = ("hdr", "tu", "coef", "intra", "intra_range", "pu", "pu_tile_prefix", "ctu", "bs", "qp", "cu_flags")
+    FIELDS = ("hdr", "tu", "coef", "intra", "intra_range", "pu", "pu_tile_prefix", "ctu", "bs", "qp", "cu_flags", "scaling")
 
     def __init__(self):
         for f in self.FIELDS:
@@ -70,7 +70,7 @@ class Frame:
         keep = []
         for f in self.FIELDS:
             a = getattr(self, f)
-            if a is None or (f in ("bs", "cu_flags") and a.size == 0):
+            if a is None or (f in ("bs", "cu_flags", "scaling") and a.size == 0):
                 setattr(d, f, None)
                 continue
             a = np.ascontiguousarray(a)

@@ -78,7 +78,8 @@ static void inv_stage(const int32_t* src, int32_t* dst, int N, int use_dst, int 
 
 /* Residual of one TU: TComTrQuant::invTransformNxN (TComTrQuant.cpp:1423-1548) = xDeQuant (:1203-1313, flat scaling)
  * + xIT / xITransformSkip (:1836-1866, :1920-1959) or bypass copy (:1475-1487) + invRdpcmNxN (:1737-1792). */
-void orc_tu_residual(const hmr_tu* t, const int16_t* level, int bit_depth, int16_t* resi /* N*N, stride N */)
+/* `scaling` = hmr_frame_desc.scaling or NULL: xDeQuant's scaling-list branch (TComTrQuant.cpp:1230-1276) */
+void orc_tu_residual(const hmr_tu* t, const int16_t* level, int bit_depth, const uint8_t* scaling, int16_t* resi /* N*N, stride N */)
 {
   static const int invq[6] = { 40, 45, 51, 57, 64, 72 };             /* g_invQuantScales, TComRom.cpp:326 */
   const int log2n = t->log2_size, N = 1 << log2n, NN = N * N;
@@ -93,13 +94,17 @@ void orc_tu_residual(const hmr_tu* t, const int16_t* level, int bit_depth, int16
     int32_t coef[ORC_MAX_TU * ORC_MAX_TU], tmp[ORC_MAX_TU * ORC_MAX_TU], blk[ORC_MAX_TU * ORC_MAX_TU];
     const int per = t->qp / 6, rem = t->qp % 6, scale = invq[rem];
     const int tr_shift = 15 - bit_depth - log2n;                       /* getTransformShift, TComChromaFormat.h:166 */
-    const int rshift = 6 - (tr_shift + per);                           /* IQUANT_SHIFT = 6 */
-    int in_bits = 32 + rshift - 7; if (in_bits > 16) in_bits = 16;     /* targetInputBitDepth, :1284 */
+    /* getUseScalingList (TComTrQuant.h): enabled, and not a transform-skipped block other than 4x4 */
+    const int use_sl = scaling != NULL && (!(t->flags & HMR_TU_TSKIP) || N == 4);
+    const uint8_t* m = use_sl ? scaling + HMR_SCALING_OFFSET(log2n - 2) + ((t->flags & HMR_TU_INTRA) ? 0 : 3) * NN + t->comp * NN : NULL;
+    const int rshift = 6 - (tr_shift + per) + (use_sl ? 4 : 0);        /* IQUANT_SHIFT = 6, LOG2_SCALING_LIST_NEUTRAL_VALUE = 4 */
+    int in_bits = 32 + rshift - (use_sl ? 15 : 7); if (in_bits > 16) in_bits = 16;   /* targetInputBitDepth, :1243 / :1284 */
     const int in_min = -(1 << (in_bits - 1)), in_max = (1 << (in_bits - 1)) - 1;
     for (int i = 0; i < NN; i++)
     {
       const int q = clip3(in_min, in_max, level[i]);
-      const int32_t v = rshift > 0 ? (q * scale + (1 << (rshift - 1))) >> rshift : (int32_t)((uint32_t)(q * scale) << (-rshift));
+      const int sc = use_sl ? scale * m[i] : scale;
+      const int32_t v = rshift > 0 ? (q * sc + (1 << (rshift - 1))) >> rshift : (int32_t)((uint32_t)(q * sc) << (-rshift));
       coef[i] = clip3(-32768, 32767, v);
     }
     if (t->flags & HMR_TU_TSKIP)
@@ -563,7 +568,7 @@ int orc_reconstruct_frame(const hmr_frame_desc* f, orc_pic* dpb, orc_pic* work, 
     {
       const hmr_tu* t = &f->tu[i];
       const int c = t->comp, N = 1 << t->log2_size, bd = c ? h->bit_depth_chroma : h->bit_depth_luma;
-      orc_tu_residual(t, f->coef + t->coef_off, bd, blk);
+      orc_tu_residual(t, f->coef + t->coef_off, bd, (h->flags & HMR_FRM_SCALING_LIST) ? f->scaling : NULL, blk);
       if (t->ccp_alpha && t->luma_off != HMR_NO_OFFSET)
         ccp_apply(blk, resid + t->luma_off, N * N, t->ccp_alpha, h->bit_depth_luma - h->bit_depth_chroma);
       const int keep = (t->flags & HMR_TU_INTRA) || (c == 0 && (h->flags & HMR_FRM_HAS_CCP));

@@ -24,6 +24,7 @@ JOBS=(
  "s_rext444_240p     encoder_intra_high_throughput_rext.cfg 416 240  3  12 444 17 --InternalBitDepth=12"
  "s_ra8_odd          encoder_randomaccess_main.cfg         200  136  9  8  420 18 -q 27"
  "s_ra422_240p       encoder_randomaccess_main_rext.cfg    416  240  9  10 422 19 --InternalBitDepth=10 -q 27"
+ "s_sl8_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 20 --ScalingList=1 -q 27"
  "c2_ra8_1080p       encoder_randomaccess_main.cfg         1920 1080 64 8  420 2"
  "c3_ra10_2160p      encoder_randomaccess_main10.cfg       3840 2160 33 10 420 3"
  "c4_rext444_1080p   encoder_intra_high_throughput_rext.cfg 1920 1080 8 12 444 4 --InternalBitDepth=12"
