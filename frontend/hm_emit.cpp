@@ -211,7 +211,6 @@ void HmEmitter::walkCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth)
     case MODE_INTRA: emitIntraCU(ctu, absPartIdx, depth, lx, ty); break;
     default: fail("CU with no prediction mode"); break;
   }
-  if (ctu->isLosslessCoded(absPartIdx)) fail("lossless CU (post-filter restoration not implemented)");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -416,7 +415,7 @@ void HmEmitter::interResidual(CuCtx& c, int compIdx, void* pTu)
 // intra CU: TDecCu::xReconIntraQT / xIntraRecQT / xIntraRecBlk (TDecCu.cpp:662-732, 483-659)
 void HmEmitter::emitIntraCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, int cuX, int cuY)
 {
-  if (ctu->getIPCMFlag(absPartIdx)) { fail("IPCM CU"); return; }
+  if (ctu->getIPCMFlag(absPartIdx)) { emitPcmCU(ctu, absPartIdx, depth, cuX, cuY); return; }
   CuCtx c;
   c.ctu = ctu; c.absPartIdx = absPartIdx; c.depth = depth; c.cuX = cuX; c.cuY = cuY;
   for (int i = 0; i < 256; i++) c.lumaOff[i] = HMR_NO_OFFSET;
@@ -429,6 +428,44 @@ void HmEmitter::emitIntraCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth
     TComTURecurse tuCU(ctu, absPartIdx);
     TComTURecurse tuPU(tuCU, false, (initTrDepth == 0) ? TComTU::DONT_SPLIT : TComTU::QUAD_SPLIT);
     do { intraQT(c, chType, &tuPU); } while (tuPU.nextSection(tuCU));
+  }
+}
+
+// I_PCM CU: TDecCu::xReconPCM / xDecodePCMTexture (TDecCu.cpp:771-842).  Per component one (4:2:2 chroma: two) square
+// block(s): a bypass residual record whose "levels" are the PCM samples at the internal bit depth, and an intra record
+// with the PCM pseudo mode (prediction 0), so that the samples land in decode order like any other intra block.
+void HmEmitter::emitPcmCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, int cuX, int cuY)
+{
+  TComPic* pic = ctu->getPic();
+  const int cuSize = g_uiMaxCUWidth >> depth;
+  const UInt minArea = (g_uiMaxCUWidth >> g_uiMaxCUDepth) * (g_uiMaxCUHeight >> g_uiMaxCUDepth);
+  for (UInt ch = 0; ch < pic->getNumberValidComponents(); ch++)
+  {
+    const ComponentID compID = ComponentID(ch);
+    const int csx = pic->getComponentScaleX(compID), csy = pic->getComponentScaleY(compID);
+    const int w = cuSize >> csx, h = cuSize >> csy;
+    const Pel* pcm = ctu->getPCMSample(compID) + ((minArea * absPartIdx) >> (csx + csy));
+    const int shift = g_bitDepth[toChannelType(compID)] - ctu->getSlice()->getSPS()->getPCMBitDepth(toChannelType(compID));
+    for (int part = 0; part < h / w; part++)                 // 4:2:2 chroma: w x 2w -> two squares
+    {
+      int lg = 0; while ((1 << lg) < w) lg++;
+      hmr_tu t; memset(&t, 0, sizeof(t));
+      t.x = (uint16_t)(cuX >> csx); t.y = (uint16_t)((cuY >> csy) + part * w);
+      t.comp = (uint8_t)ch; t.log2_size = (uint8_t)lg;
+      t.flags = HMR_TU_CODED | HMR_TU_INTRA | HMR_TU_BYPASS;
+      t.luma_off = HMR_NO_OFFSET;
+      t.coef_off = (uint32_t)m_coef.size();
+      m_coef.resize(m_coef.size() + (size_t)w * w);
+      int16_t* dst = &m_coef[t.coef_off];
+      const Pel* src = pcm + (size_t)part * w * w;
+      for (int i = 0; i < w * w; i++) dst[i] = (int16_t)(src[i] << shift);
+      m_tu.push_back(t);
+      hmr_intra r; memset(&r, 0, sizeof(r));
+      r.x = t.x; r.y = t.y; r.comp = t.comp; r.log2_size = t.log2_size;
+      r.mode = HMR_INTRA_MODE_PCM;
+      r.resid_off = t.coef_off;
+      m_intraTmp[ch].push_back(r);
+    }
   }
 }
 

@@ -66,6 +66,7 @@ private:
   void walkCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth);
   void emitInterCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, int cuX, int cuY, int cuSize);
   void emitIntraCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, int cuX, int cuY);
+  void emitPcmCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, int cuX, int cuY);
   void interResidual(CuCtx& c, int compID, void* rTu);
   void intraQT(CuCtx& c, int chType, void* rTu);
   void intraBlk(CuCtx& c, int compID, void* rTu);

@@ -105,11 +105,15 @@ enum {
   HMR_INTRA_LUMA_RULES   = 1u << 3, /* channel is luma: DC/edge filters and strong smoothing may apply */
 };
 
+/* I_PCM block (TDecCu::xReconPCM / xDecodePCMTexture, TDecCu.cpp:771-842): "prediction" 0, and the block's residual record
+ * (HMR_TU_BYPASS) carries the PCM samples already shifted to the internal bit depth.  Keeps PCM inside the decode order. */
+#define HMR_INTRA_MODE_PCM 35
+
 typedef struct hmr_intra {
   uint16_t x, y;        /* top-left, component samples */
   uint8_t  comp;
   uint8_t  log2_size;   /* 2..5 */
-  uint8_t  mode;        /* final prediction mode 0..34 after DM / 4:2:2 mapping (TDecCu.cpp:524-526) */
+  uint8_t  mode;        /* final prediction mode 0..34 after DM / 4:2:2 mapping (TDecCu.cpp:524-526), or HMR_INTRA_MODE_PCM */
   uint8_t  flags;       /* HMR_INTRA_* */
   /* Neighbour availability per "unit" (= 4 luma samples = 4>>csx chroma samples, TComPattern.cpp:119-127),
      bit i = unit i counted AWAY from the top-left corner: left/below-left downwards, above/above-right rightwards. */

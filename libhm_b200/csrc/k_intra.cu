@@ -123,7 +123,7 @@ __device__ __forceinline__ int op_lg(const IntraOp& o)    { return (o.z >> 8) & 
 __device__ __forceinline__ int op_cls(const IntraOp& o)   { return (o.z >> 16) & 0xff; }
 __device__ __forceinline__ int op_flags(const IntraOp& o) { return o.z >> 24; }
 __device__ __forceinline__ int op_inv(const IntraOp& o)   { return o.w & 0xffff; }
-enum { OP_PLANAR = 0, OP_DC = 1, OP_ANG0 = 2, OP_ANGPOS = 3, OP_ANGNEG = 4 };
+enum { OP_PLANAR = 0, OP_DC = 1, OP_ANG0 = 2, OP_ANGPOS = 3, OP_ANGNEG = 4, OP_PCM = 5 };
 enum { OPF_FILTER = 1, OPF_STRONG = 2, OPF_EDGE = 4, OPF_VER = 8, OPF_DCEDGE = 16 };
 
 __device__ __forceinline__ IntraOp intra_make_op(const hmr_intra& r, const IntraGeom& g, unsigned minoff, bool strongAllowed, int slot)
@@ -138,6 +138,7 @@ __device__ __forceinline__ IntraOp intra_make_op(const hmr_intra& r, const Intra
   const int mode = r.mode;
   if (mode == 0) cls = OP_PLANAR;
   else if (mode == 1) cls = OP_DC;
+  else if (mode == HMR_INTRA_MODE_PCM) cls = OP_PCM;       // I_PCM: prediction 0, the samples arrive as the residual
   else
   {
     const bool ver = mode >= 18;
@@ -243,6 +244,15 @@ __device__ __forceinline__ void intra_tu(const IntraOp op, const int a[IN_NJMAX]
         const int p = ((N - 1 - x) * LEFT(y) + (x + 1) * tn + (N - 1 - y) * TOP(x) + (y + 1) * ln + N) >> (LG + 1);
         EMIT(i, y, x, p);
       }
+    }
+  }
+  else if (cls == OP_PCM)
+  {
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      const int i = lane + 32 * j;
+      if (N * N >= 32 || i < N * N) { const int y = i >> LG, x = i & (N - 1); EMIT(i, y, x, 0); }
     }
   }
   else if (cls == OP_DC)

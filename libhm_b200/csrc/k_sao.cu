@@ -126,6 +126,14 @@ __global__ void __launch_bounds__(256) sao_kernel(const __grid_constant__ FrameP
           out[j] = (ok && e != 0 && j < nvalid) ? clip3i(0, maxv, v[j] + o) : v[j];
         }
       }
+      if (P.cu_flags)
+      {
+        // PCMLFDisableProcess / xPCMRestoration (TComSampleAdaptiveOffset.cpp:743-843): I_PCM (pcm_loop_filter_disabled) and
+        // lossless CUs get their pre-filter samples back — SAO never applies to them (deblocking skipped them already)
+        const uint8_t* frow = P.cu_flags + (size_t)((y << cy) >> 3) * P.w8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (frow[((x + j) << cx) >> 3] & HMR_CU_NOFILTER) out[j] = v[j];
+      }
       q.x = (uint32_t)(out[0] & 0xffff) | ((uint32_t)out[1] << 16);
       q.y = (uint32_t)(out[2] & 0xffff) | ((uint32_t)out[3] << 16);
       q.z = (uint32_t)(out[4] & 0xffff) | ((uint32_t)out[5] << 16);

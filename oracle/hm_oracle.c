@@ -257,6 +257,7 @@ void orc_intra_predict(const hmr_frame_hdr* h, const hmr_intra* r, const orc_pic
   const int x0 = r->x, y0 = r->y;
   int line[4 * ORC_MAX_TU + 1], flt[4 * ORC_MAX_TU + 1];
   uint8_t av[4 * ORC_MAX_TU + 1];
+  if (r->mode == HMR_INTRA_MODE_PCM) { memset(pred, 0, sizeof(int16_t) * N * N); return; }   /* xReconPCM: the samples arrive as the residual */
 
   /* line[0] = bottom-most below-left ... line[2N-1] = left y=0, line[2N] = corner, line[2N+1+x] = above x */
   int any = 0;
@@ -509,7 +510,10 @@ void orc_sao(const hmr_frame_desc* f, const orc_pic* src, orc_pic* dst)
         const int16_t* p = src->plane[c] + (size_t)(by + y) * st + bx + x;
         const int v = *p;
         int out = v;
-        if (s->type == HMR_SAO_BO)
+        /* TComSampleAdaptiveOffset::PCMLFDisableProcess / xPCMRestoration (:743-843): I_PCM (with pcm_loop_filter_disabled)
+           and lossless CUs get their pre-filter samples back, i.e. SAO never applies to them */
+        if (f->cu_flags && (f->cu_flags[(size_t)(((by + y) << cy) >> 3) * ((h->width + 7) >> 3) + (((bx + x) << cx) >> 3)] & HMR_CU_NOFILTER)) { }
+        else if (s->type == HMR_SAO_BO)
         {
           const int k = ((v >> (bd - 5)) - s->band) & 31;
           if (k < 4) out = clip3(0, maxv, v + s->off[k]);

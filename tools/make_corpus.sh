@@ -25,6 +25,8 @@ JOBS=(
  "s_ra8_odd          encoder_randomaccess_main.cfg         200  136  9  8  420 18 -q 27"
  "s_ra422_240p       encoder_randomaccess_main_rext.cfg    416  240  9  10 422 19 --InternalBitDepth=10 -q 27"
  "s_sl8_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 20 --ScalingList=1 -q 27"
+ "s_pcm_240p         encoder_randomaccess_main10.cfg       416  240  5  8  420 21 --InternalBitDepth=10 --PCMEnabledFlag=1 --PCMFilterDisableFlag=1 -q 1"
+ "s_lossless_240p    encoder_randomaccess_main.cfg         208  120  5  8  420 22 --TransquantBypassEnableFlag=1 --CUTransquantBypassFlagForce=1 -q 30"
  "c2_ra8_1080p       encoder_randomaccess_main.cfg         1920 1080 64 8  420 2"
  "c3_ra10_2160p      encoder_randomaccess_main10.cfg       3840 2160 33 10 420 3"
  "c4_rext444_1080p   encoder_intra_high_throughput_rext.cfg 1920 1080 8 12 444 4 --InternalBitDepth=12"
@@ -47,7 +49,8 @@ for j in "${JOBS[@]}"; do
   out=$ROOT/corpus/$name
   [ -s "$out.bin" ] && [ -s "$out.yuvmd5" ] && { echo "$name: exists"; exit 0; }
   yuv=$TMP_YUV/$name.yuv
-  python "$ROOT/tools/gen_yuv.py" "$yuv" --width $W --height $H --frames $F --bitdepth $BD --seed $SEED --chroma $CH
+  if [ "$name" == "s_pcm_240p" ]; then python "$ROOT/tools/gen_pcm_yuv.py" "$yuv" --width $W --height $H --frames $F --seed $SEED   # noise: makes the encoder choose I_PCM
+  else python "$ROOT/tools/gen_yuv.py" "$yuv" --width $W --height $H --frames $F --bitdepth $BD --seed $SEED --chroma $CH; fi
   CF=""; [ "$CH" != "420" ] && CF="--InputChromaFormat=$CH"
   "$ENC" -c "$REF/cfg/$cfg" -i "$yuv" -wdt $W -hgt $H -f $F -fr 30 --InputBitDepth=$BD $CF \
       --SEIDecodedPictureHash=1 $EXTRA -b "$out.bin.tmp" -o "$TMP_YUV/$name.rec.yuv" > "$out.enc.log" 2>&1
