@@ -57,6 +57,7 @@ public:
     section(TAG('Q','P',' ',' '), d.qp, nqp);
     if (d.cu_flags) section(TAG('C','U','F','L'), d.cu_flags, nqp);
     if (d.scaling) section(TAG('S','C','A','L'), d.scaling, HMR_SCALING_BYTES);
+    if (d.wp) { section(TAG('W','P',' ',' '), d.wp, sizeof(hmr_wp) * HMR_WP_ENTRIES); section(TAG('P','U','R','I'), d.pu_refidx, h.n_pu); }
     if (m_recordsOnly) { section(TAG('E','N','D',' '), NULL, 0); fflush(m_fp); }
   }
 

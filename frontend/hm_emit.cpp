@@ -141,7 +141,7 @@ void HmEmitter::beginFrame(TComPic* pic, TComDataCU* ctu)
   if ((g_uiMaxCUWidth >> g_uiMaxCUDepth) != 4) fail("minimum partition size != 4");
   if (pic->getChromaFormat() == CHROMA_400)  fail("4:0:0");
 
-  m_tu.clear(); m_coef.clear(); m_intra.clear(); m_pu.clear(); m_puPrefix.clear();
+  m_tu.clear(); m_coef.clear(); m_intra.clear(); m_pu.clear(); m_puPrefix.clear(); m_puRefIdx.clear();
   m_puPrefix.push_back(0);
   m_range.assign(m_hdr.n_ctu, hmr_ctu_intra_range());
   memset(m_range.data(), 0, m_range.size() * sizeof(hmr_ctu_intra_range));
@@ -306,8 +306,31 @@ void HmEmitter::emitInterCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth
 {
   TComSlice* slice = ctu->getSlice();
   TComPic*   pic   = ctu->getPic();
-  if (slice->getPPS()->getUseWP() && slice->getSliceType() == P_SLICE) fail("explicit weighted prediction (P)");
-  if (slice->getPPS()->getWPBiPred() && slice->getSliceType() == B_SLICE) fail("explicit weighted prediction (B)");
+  // explicit weighted prediction (TComSlice::applyWP): table per (list, refIdx, component), once per picture
+  const bool applyWP = (slice->getPPS()->getUseWP() && slice->getSliceType() == P_SLICE) || (slice->getPPS()->getWPBiPred() && slice->getSliceType() == B_SLICE);
+  if (applyWP && !(m_hdr.flags & HMR_FRM_WEIGHTED_PRED))
+  {
+    if (!m_pu.empty()) fail("slices with and without weighted prediction in one picture");
+    m_hdr.flags |= HMR_FRM_WEIGHTED_PRED;
+    m_wp.assign(HMR_WP_ENTRIES, hmr_wp());
+    memset(m_wp.data(), 0, sizeof(hmr_wp) * m_wp.size());
+    const bool highPrec = slice->getSPS()->getUseHighPrecisionPredictionWeighting();
+    for (int l = 0; l < 2; l++)
+      for (int r = 0; r < slice->getNumRefIdx(RefPicList(l)) && r < 16; r++)
+      {
+        WPScalingParam* wp = NULL;
+        slice->getWpScaling(RefPicList(l), r, wp);
+        for (UInt c = 0; c < pic->getNumberValidComponents(); c++)
+        {
+          hmr_wp& o = m_wp[(l * 16 + r) * 3 + c];
+          const int bd = g_bitDepth[toChannelType(ComponentID(c))];
+          o.weight = (int16_t)wp[c].iWeight;
+          o.offset = (int16_t)(wp[c].iOffset * (highPrec ? 1 : (1 << (bd - 8))));
+          o.log2_denom = (uint8_t)wp[c].uiLog2WeightDenom;
+        }
+      }
+  }
+  else if (!applyWP && (m_hdr.flags & HMR_FRM_WEIGHTED_PRED)) fail("slices with and without weighted prediction in one picture");
 
   // PU geometry: TComDataCU::getPartIndexAndSize (TComDataCU.cpp:2178-2230)
   int n = 1, px[4] = {0, 0, 0, 0}, py[4] = {0, 0, 0, 0}, pw[4], ph[4];
@@ -359,6 +382,7 @@ void HmEmitter::emitInterCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth
     }
     p.slots = (uint8_t)(slot[0] | (slot[1] << 4));
     m_pu.push_back(p);
+    m_puRefIdx.push_back((uint8_t)((use0 ? (refIdx[0] & 15) : 0) | ((use1 ? (refIdx[1] & 15) : 0) << 4)));
     m_puPrefix.push_back(m_puPrefix.back() + ((pw[i] + 15) >> 4) * ((ph[i] + 15) >> 4));
   }
 
@@ -735,6 +759,8 @@ void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdap
   d.pu = m_pu.data(); d.pu_tile_prefix = m_puPrefix.data();
   d.ctu = m_ctu.data();
   d.scaling = (m_hdr.flags & HMR_FRM_SCALING_LIST) ? m_scaling.data() : NULL;
+  d.wp = (m_hdr.flags & HMR_FRM_WEIGHTED_PRED) ? m_wp.data() : NULL;
+  d.pu_refidx = (m_hdr.flags & HMR_FRM_WEIGHTED_PRED) ? m_puRefIdx.data() : NULL;
   d.bs = (m_hdr.flags & HMR_FRM_DEBLOCK) ? m_bs.data() : NULL;
   d.qp = m_qp.data();
   d.cu_flags = (m_hdr.flags & HMR_FRM_HAS_NOFILTER) ? m_cuFlags.data() : NULL;

@@ -95,6 +95,8 @@ private:
   std::vector<int8_t>              m_qp;
   std::vector<uint8_t>             m_cuFlags;
   std::vector<uint8_t>             m_scaling;
+  std::vector<hmr_wp>              m_wp;
+  std::vector<uint8_t>             m_puRefIdx;
   int m_bsStride, m_qpStride;
   bool m_in422SubTu;                       // inside the two square halves of a 4:2:2 chroma TU
   bool m_cleanCoeffs;                      // hm_fast.cpp: HM's whole-CTU coefficient zero fills are skipped for this decoder

@@ -37,6 +37,8 @@ enum {
   HMR_FRM_IS_REFERENCE          = 1u << 5, /* informational */
   HMR_FRM_INTRA_ONLY            = 1u << 6, /* informational: no PU records */
   HMR_FRM_SCALING_LIST          = 1u << 7, /* scaling lists in use: hmr_frame_desc.scaling is valid (TComTrQuant.cpp:1230-1276) */
+  HMR_FRM_WEIGHTED_PRED         = 1u << 8, /* explicit weighted prediction applies to this picture's slices (TComSlice::applyWP):
+                                              hmr_frame_desc.wp and .pu_refidx are valid */
 };
 
 /* Scaling factors m[y][x] (1..255) of the active scaling list, expanded to the transform size the way
@@ -138,6 +140,17 @@ typedef struct hmr_pu {
   int16_t  mv[2][2];    /* [list][x,y] quarter-luma-sample, ALREADY clipped by TComDataCU::clipMv (TComDataCU.cpp:3102-3114) */
 } hmr_pu;               /* 16 bytes */
 
+/* ---- explicit weighted prediction: TComWeightPrediction::getWpScaling / addWeightUni / addWeightBi
+ *      (TComWeightPrediction.cpp:44-53,75-196,211-286).  One entry per (list, refIdx, component); a PU finds its entries
+ *      through pu_refidx[pu] = refIdx of list 0 in bits 0-3, of list 1 in bits 4-7. */
+typedef struct hmr_wp {
+  int16_t  weight;      /* iWeight */
+  int16_t  offset;      /* iOffset already multiplied by the offset scaling factor (1 << (bitDepth-8) unless high_precision_offsets) */
+  uint8_t  log2_denom;  /* uiLog2WeightDenom */
+  uint8_t  pad;
+} hmr_wp;               /* 6 bytes; table = hmr_wp[2][16][3] */
+#define HMR_WP_ENTRIES (2 * 16 * 3)
+
 /* ---- per-CTU side info: SAO (TComSampleAdaptiveOffset.cpp:375-714) and slice-level deblock offsets ---- */
 enum { HMR_SAO_OFF = 0, HMR_SAO_EO_0 = 1, HMR_SAO_EO_90 = 2, HMR_SAO_EO_135 = 3, HMR_SAO_EO_45 = 4, HMR_SAO_BO = 5 };
 /* hmr_ctu.avail bits: TComPicSym::deriveLoopFilterBoundaryAvailibility (TComPicSym.cpp:365-460) */
@@ -181,6 +194,8 @@ typedef struct hmr_frame_desc {
   const int8_t*              qp;              /* [(W/8)*(H/8)] */
   const uint8_t*             cu_flags;        /* [(W/8)*(H/8)] or NULL when !HMR_FRM_HAS_NOFILTER */
   const uint8_t*             scaling;         /* [HMR_SCALING_BYTES] or NULL when !HMR_FRM_SCALING_LIST */
+  const hmr_wp*              wp;              /* [HMR_WP_ENTRIES] or NULL when !HMR_FRM_WEIGHTED_PRED */
+  const uint8_t*             pu_refidx;       /* [n_pu] or NULL when !HMR_FRM_WEIGHTED_PRED */
 } hmr_frame_desc;
 
 #ifdef __cplusplus

@@ -34,6 +34,9 @@ struct FrameParams
   const int8_t*              qp;
   const uint8_t*             cu_flags;
   const uint8_t*             scaling;         // scaling factors (hmr_records.h: HMR_SCALING_OFFSET) or nullptr
+  const hmr_wp*              wp;              // explicit weighted prediction table [2][16][3] or nullptr
+  const uint8_t*             pu_refidx;       // [n_pu] refIdx L0 | L1 << 4 (weighted prediction only)
+  uint8_t*                   mc_tile_refidx;  // [n_mc_tiles] scratch: the same per tile
   uint4*                     intra_ops;       // [n_intra] decoded intra TUs           } scratch written by k_intra.cu's pre-pass
   uint16_t*                  intra_tab;       // [3][n_ctu][4352] reference-address tables }
   uint4*                     intra_prep;      // [3][n_ctu] residual span / table length   }

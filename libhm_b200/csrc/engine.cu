@@ -21,7 +21,7 @@
 struct Section { size_t off, bytes; };
 struct Layout
 {
-  Section hdr, tu, coef, intra, irange, pu, prefix, ctu, bs, qp, cuf, scal;
+  Section hdr, tu, coef, intra, irange, pu, prefix, ctu, bs, qp, cuf, scal, wp, puri;
   size_t total;
 };
 
@@ -51,7 +51,7 @@ struct hmr_engine
   struct Stage { uint8_t* host; uint8_t* dev; size_t cap; cudaEvent_t done; bool inflight; } ring[RING];
   int ringPos;
   int16_t* resid; size_t residCap;
-  hmr_pu* mcTiles; size_t mcTilesCap;
+  hmr_pu* mcTiles; size_t mcTilesCap; uint8_t* mcTileRef;
   unsigned long long* progress; size_t progressCap;
   uint4* intraOps; size_t intraOpsCap; uint16_t* intraTab; size_t intraTabBytes; uint4* intraPrep; size_t intraPrepBytes;
   unsigned long long epoch;
@@ -135,6 +135,9 @@ static Layout make_layout(const hmr_frame_hdr& h, bool hasBs, bool hasCuf, bool 
   put(L.qp, nqp);
   put(L.cuf, hasCuf ? nqp : 0);
   put(L.scal, hasScal ? HMR_SCALING_BYTES : 0);
+  const bool hasWp = (h.flags & HMR_FRM_WEIGHTED_PRED) != 0;
+  put(L.wp, hasWp ? sizeof(hmr_wp) * HMR_WP_ENTRIES : 0);
+  put(L.puri, hasWp ? h.n_pu : 0);
   L.total = off;
   return L;
 }
@@ -153,6 +156,8 @@ static void pack(uint8_t* dst, const Layout& L, const hmr_frame_desc* f)
   if (L.qp.bytes)     memcpy(dst + L.qp.off, f->qp, L.qp.bytes);
   if (L.cuf.bytes)    memcpy(dst + L.cuf.off, f->cu_flags, L.cuf.bytes);
   if (L.scal.bytes)   memcpy(dst + L.scal.off, f->scaling, L.scal.bytes);
+  if (L.wp.bytes)     memcpy(dst + L.wp.off, f->wp, L.wp.bytes);
+  if (L.puri.bytes)   memcpy(dst + L.puri.off, f->pu_refidx, L.puri.bytes);
 }
 
 static int validate(hmr_engine* e, const hmr_frame_desc* f)
@@ -170,6 +175,7 @@ static int validate(hmr_engine* e, const hmr_frame_desc* f)
     return fail(e, HMR_ERR_ARG, "missing record array");
   if ((h.flags & HMR_FRM_DEBLOCK) && !f->bs) return fail(e, HMR_ERR_ARG, "HMR_FRM_DEBLOCK without a BS map");
   if ((h.flags & HMR_FRM_SCALING_LIST) && !f->scaling) return fail(e, HMR_ERR_ARG, "HMR_FRM_SCALING_LIST without scaling factors");
+  if ((h.flags & HMR_FRM_WEIGHTED_PRED) && (!f->wp || (h.n_pu && !f->pu_refidx))) return fail(e, HMR_ERR_ARG, "HMR_FRM_WEIGHTED_PRED without weights");
   return HMR_OK;
 }
 
@@ -270,6 +276,9 @@ static void fill_params(hmr_engine* e, FrameParams& P, const hmr_frame_hdr& h, c
   P.qp = (const int8_t*)(dev + L.qp.off);
   P.cu_flags = hasCuf ? dev + L.cuf.off : nullptr;
   P.scaling = L.scal.bytes ? dev + L.scal.off : nullptr;
+  P.wp = L.wp.bytes ? (const hmr_wp*)(dev + L.wp.off) : nullptr;
+  P.pu_refidx = L.puri.bytes ? dev + L.puri.off : nullptr;
+  P.mc_tile_refidx = e->mcTileRef;
   P.intra_progress = e->progress;
   P.intra_ops = e->intraOps; P.intra_tab = e->intraTab; P.intra_prep = e->intraPrep;
   P.epoch = e->epoch;
@@ -319,9 +328,12 @@ static int run_frame(hmr_engine* e, FrameParams& P, FrameEvents* fe)
   {
     CK(cudaStreamSynchronize(e->stream));
     pool_free(e->device, e->mcTiles, e->mcTilesCap * sizeof(hmr_pu));
+    pool_free(e->device, e->mcTileRef, e->mcTilesCap);
     e->mcTilesCap = ALIGN_UP((size_t)h.n_mc_tiles * 3 / 2 + 1024, 1 << 16);
     CK(pool_malloc(e->device, (void**)&e->mcTiles, e->mcTilesCap * sizeof(hmr_pu)));
+    CK(pool_malloc(e->device, (void**)&e->mcTileRef, e->mcTilesCap));
     P.mc_tiles = e->mcTiles;
+    P.mc_tile_refidx = e->mcTileRef;
   }
   auto mark = [&](int k) { if (fe) { cudaEventRecord(fe->ev[k], e->stream); fe->used[k] = true; } };
   const int m = e->stageMask;
@@ -378,7 +390,7 @@ int hmr_engine_create(hmr_engine** out, int device)
   e->haveGeom = false; e->workAlloc = false;
   memset(e->slotAlloc, 0, sizeof(e->slotAlloc));
   memset(e->ring, 0, sizeof(e->ring));
-  e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->mcTiles = nullptr; e->mcTilesCap = 0; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
+  e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->mcTiles = nullptr; e->mcTilesCap = 0; e->mcTileRef = nullptr; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
   e->intraOps = nullptr; e->intraOpsCap = 0; e->intraTab = nullptr; e->intraTabBytes = 0; e->intraPrep = nullptr; e->intraPrepBytes = 0;
   e->stageMask = HMR_STAGE_ALL; e->timing = false;
   memset(e->accMs, 0, sizeof(e->accMs)); e->accFrames = e->accLaunches = 0;
@@ -414,6 +426,7 @@ void hmr_engine_destroy(hmr_engine* e)
   }
   pool_free(e->device, e->resid, e->residCap * sizeof(int16_t));
   pool_free(e->device, e->mcTiles, e->mcTilesCap * sizeof(hmr_pu));
+  pool_free(e->device, e->mcTileRef, e->mcTilesCap);
   pool_free(e->device, e->progress, e->progressCap * sizeof(unsigned long long));
   pool_free(e->device, e->intraOps, e->intraOpsCap * sizeof(uint4));
   pool_free(e->device, e->intraTab, e->intraTabBytes);

@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) mc_expand_kernel(const __grid_constant__ 
   const int w = min(16, t.w - 16 * i), h = min(16, t.h - 16 * j);
   t.x = (uint16_t)(t.x + 16 * i); t.y = (uint16_t)(t.y + 16 * j);
   t.w = (uint8_t)w; t.h = (uint8_t)h;
-  *(uint4*)(P.mc_tiles + __ldg(P.pu_prefix + p) + k) = *(const uint4*)&t;
+  const uint32_t dstIdx = __ldg(P.pu_prefix + p) + k;
+  *(uint4*)(P.mc_tiles + dstIdx) = *(const uint4*)&t;
+  if (P.pu_refidx) P.mc_tile_refidx[dstIdx] = P.pu_refidx[p];
 }
 
 // Stage rows [iy, iy+rows) x columns [xa, xa + 8*nvec) of `ref` into s (pitch MC_PITCH).  Returns nothing; async on the fast path.
@@ -171,9 +173,11 @@ __device__ __forceinline__ void mc_vpass(const uint32_t* tmp, int x4, int yg, co
   for (int c = 0; c < 4; c++) { v[c] = mc_even<NT>(w[c], ty); v[4 + c] = mc_odd<NT>(w[c], ty); }
 }
 
+// refIdx = refIdx of list 0 | list 1 << 4 (explicit weighted prediction only: TComWeightPrediction::addWeightUni / addWeightBi,
+// TComWeightPrediction.cpp:44-53,75-196 — both cases start from the 14-bit intermediates, like bi-prediction)
 template <int NT>
 __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu& t, int comp, int cx, int cy, int16_t* const sref[2],
-                                             const int offs[2], uint32_t* tmp, int lane)
+                                             const int offs[2], uint32_t* tmp, int lane, int refIdx)
 {
   const int tw = 16 >> cx, th = 16 >> cy;                    // full tile in this component
   const int x0 = t.x >> cx, y0 = t.y >> cy, w = t.w >> cx, h = t.h >> cy;
@@ -181,6 +185,18 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
   const int headroom = max(2, 14 - bd), maxv = (1 << bd) - 1;
   const int s1 = 6 - headroom, o1 = -(8192 << s1);
   const bool bi = t.lists == (HMR_PU_L0 | HMR_PU_L1);
+  const bool wpOn = P.wp != nullptr;
+  int wpW[2] = {0, 0}, wpO[2] = {0, 0}, wpD = 0;
+  if (wpOn)
+  {
+    for (int l = 0; l < 2; l++)
+    {
+      if (!(t.lists & (1 << l))) continue;
+      const hmr_wp q = P.wp[(l * 16 + ((refIdx >> (4 * l)) & 15)) * 3 + comp];
+      wpW[l] = q.weight; wpO[l] = q.offset;
+      if (l == 0 || !(t.lists & HMR_PU_L0)) wpD = q.log2_denom;          // bi uses the list-0 denominator (getWpScaling)
+    }
+  }
   const int rowPairs = (th + NT) >> 1;                       // th + NT - 1 rows, rounded up to even
   const int log2ColPairs = tw == 16 ? 3 : 2;
   const int nV = (tw >> 2) * (th >> 1);                      // V items: 4 columns x 2 rows each (<= 32)
@@ -202,7 +218,12 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
     {
       int v[8];
       mc_vpass<NT>(tmp, x4, yg, ty, v);
-      if (bi)
+      if (wpOn)
+      {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] += wpW[list] * ((int)(int16_t)(v[i] >> 6) + 8192);
+      }
+      else if (bi)
       {
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[i] += (int)(int16_t)(v[i] >> 6);       // xPredInterBlk, !isLast: Pel result
@@ -217,7 +238,22 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
     __syncwarp();                                            // tmp is reused by the next list / component
   }
   if (lane >= nV) return;
-  if (bi)
+  if (wpOn)
+  {
+    if (bi)
+    {
+      const int sh = wpD + 1 + headroom, add = (1 << (sh - 1)) + ((wpO[0] + wpO[1]) << (sh - 1));
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] = clip3i(0, maxv, (acc[i] + add) >> sh);
+    }
+    else
+    {
+      const int sh = wpD + headroom, rnd = sh > 0 ? 1 << (sh - 1) : 0, o = (t.lists & HMR_PU_L0) ? wpO[0] : wpO[1];
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] = clip3i(0, maxv, ((acc[i] + rnd) >> sh) + o);
+    }
+  }
+  else if (bi)
   {
     const int sh = headroom + 1, off = (1 << (sh - 1)) + 2 * 8192;             // TComYuv::addAvg
 #pragma unroll
@@ -283,12 +319,13 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
   }
   if (chroma) mc_cp_async_wait<1>(); else mc_cp_async_wait<0>();
   __syncwarp();
-  mc_component<8>(P, t, 0, 0, 0, sref[0], offs[0], tmp, lane);
+  const int refIdx = P.wp ? (int)P.mc_tile_refidx[tile] : 0;
+  mc_component<8>(P, t, 0, 0, 0, sref[0], offs[0], tmp, lane, refIdx);
   if (!chroma) return;
   mc_cp_async_wait<0>();
   __syncwarp();
-  mc_component<4>(P, t, 1, P.csx, P.csy, sref[1], offs[1], tmp, lane);
-  mc_component<4>(P, t, 2, P.csx, P.csy, sref[2], offs[2], tmp, lane);
+  mc_component<4>(P, t, 1, P.csx, P.csy, sref[1], offs[1], tmp, lane, refIdx);
+  mc_component<4>(P, t, 2, P.csx, P.csy, sref[2], offs[2], tmp, lane, refIdx);
 }
 
 void launch_mc(const FrameParams& P, cudaStream_t s)

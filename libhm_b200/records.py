@@ -11,7 +11,7 @@ HMR_MAGIC = 0x52524D48
 HMR_VERSION = 4
 HMR_NO_OFFSET = 0xFFFFFFFF
 
-FRM_STRONG_INTRA_SMOOTHING, FRM_DEBLOCK, FRM_SAO, FRM_HAS_NOFILTER, FRM_HAS_CCP, FRM_IS_REFERENCE, FRM_INTRA_ONLY, FRM_SCALING_LIST = (1 << i for i in range(8))
+FRM_STRONG_INTRA_SMOOTHING, FRM_DEBLOCK, FRM_SAO, FRM_HAS_NOFILTER, FRM_HAS_CCP, FRM_IS_REFERENCE, FRM_INTRA_ONLY, FRM_SCALING_LIST, FRM_WEIGHTED_PRED = (1 << i for i in range(9))
 TU_CODED, TU_INTRA, TU_DST, TU_TSKIP, TU_BYPASS, TU_ROTATE, TU_RDPCM_H, TU_RDPCM_V = (1 << i for i in range(8))
 
 HDR_DT = np.dtype([("magic", "<u4"), ("version", "<u4"), ("width", "<i4"), ("height", "<i4"), ("poc", "<i4"),
@@ -27,23 +27,24 @@ INTRA_DT = np.dtype([("x", "<u2"), ("y", "<u2"), ("comp", "u1"), ("log2_size", "
 IRNG_DT = np.dtype([("first", "<u4", (3,)), ("count", "<u4", (3,))])
 PU_DT = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("lists", "u1"), ("slots", "u1"), ("mv", "<i2", (2, 2))])
 SAO_DT = np.dtype([("type", "u1"), ("band", "u1"), ("off", "<i2", (4,))])
+WP_DT = np.dtype([("weight", "<i2"), ("offset", "<i2"), ("log2_denom", "u1"), ("pad", "u1")])
 CTU_DT = np.dtype([("sao", SAO_DT, (3,)), ("avail", "u1"), ("beta_offset_div2", "i1"), ("tc_offset_div2", "i1"), ("pad", "u1", (3,))])
 assert (HDR_DT.itemsize, TU_DT.itemsize, INTRA_DT.itemsize, IRNG_DT.itemsize, PU_DT.itemsize, SAO_DT.itemsize, CTU_DT.itemsize) == (80, 20, 16, 24, 16, 10, 36)
 
 
 class FrameDesc(C.Structure):
     """struct hmr_frame_desc"""
-    _fields_ = [(n, C.c_void_p) for n in ("hdr", "tu", "coef", "intra", "intra_range", "pu", "pu_tile_prefix", "ctu", "bs", "qp", "cu_flags", "scaling")]
+    _fields_ = [(n, C.c_void_p) for n in ("hdr", "tu", "coef", "intra", "intra_range", "pu", "pu_tile_prefix", "ctu", "bs", "qp", "cu_flags", "scaling", "wp", "pu_refidx")]
 
 
 _SECTIONS = {b"HDR ": ("hdr", HDR_DT), b"TU  ": ("tu", TU_DT), b"COEF": ("coef", np.dtype("<i2")), b"INTR": ("intra", INTRA_DT),
              b"IRNG": ("intra_range", IRNG_DT), b"PU  ": ("pu", PU_DT), b"PUPF": ("pu_tile_prefix", np.dtype("<u4")),
-             b"CTU ": ("ctu", CTU_DT), b"BS  ": ("bs", np.dtype("u1")), b"QP  ": ("qp", np.dtype("i1")), b"CUFL": ("cu_flags", np.dtype("u1")), b"SCAL": ("scaling", np.dtype("u1"))}
+             b"CTU ": ("ctu", CTU_DT), b"BS  ": ("bs", np.dtype("u1")), b"QP  ": ("qp", np.dtype("i1")), b"CUFL": ("cu_flags", np.dtype("u1")), b"SCAL": ("scaling", np.dtype("u1")), b"WP  ": ("wp", WP_DT), b"PURI": ("pu_refidx", np.dtype("u1"))}
 
 
 class Frame:
     """One picture's records (+ optional golden data recorded from HM's own CPU reconstruction)."""
-    FIELDS = ("hdr", "tu", "coef", "intra", "intra_range", "pu", "pu_tile_prefix", "ctu", "bs", "qp", "cu_flags", "scaling")
+    FIELDS = ("hdr", "tu", "coef", "intra", "intra_range", "pu", "pu_tile_prefix", "ctu", "bs", "qp", "cu_flags", "scaling", "wp", "pu_refidx")
 
     def __init__(self):
         for f in self.FIELDS:
@@ -70,7 +71,7 @@ class Frame:
         keep = []
         for f in self.FIELDS:
             a = getattr(self, f)
-            if a is None or (f in ("bs", "cu_flags", "scaling") and a.size == 0):
+            if a is None or (f in ("bs", "cu_flags", "scaling", "wp", "pu_refidx") and a.size == 0):
                 setattr(d, f, None)
                 continue
             a = np.ascontiguousarray(a)

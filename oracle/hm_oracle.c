@@ -221,7 +221,10 @@ static void mc_block(const orc_pic* ref, int c, int fmt, int bd, int x0, int y0,
 }
 
 /* One PU, all components, into dst: motionCompensation / xPredInterUni / xPredInterBi (TComPrediction.cpp:514-644) */
-void orc_predict_pu(const hmr_frame_hdr* h, const hmr_pu* p, const orc_pic* dpb, orc_pic* dst)
+/* wp = hmr_frame_desc.wp or NULL; refidx = pu_refidx[pu].  With explicit weighted prediction both the uni and the bi case go
+ * through the 14-bit intermediates (xPredInterUni(..., bi = true), TComPrediction.cpp:596-644) and then
+ * TComWeightPrediction::addWeightUni / addWeightBi (TComWeightPrediction.cpp:44-53,75-196). */
+void orc_predict_pu(const hmr_frame_hdr* h, const hmr_pu* p, const hmr_wp* wp, int refidx, const orc_pic* dpb, orc_pic* dst)
 {
   int16_t a[64 * 64], b[64 * 64];
   const int fmt = h->chroma_format;
@@ -231,13 +234,28 @@ void orc_predict_pu(const hmr_frame_hdr* h, const hmr_pu* p, const orc_pic* dpb,
     const int bd = c ? h->bit_depth_chroma : h->bit_depth_luma;
     const int x0 = p->x >> cx, y0 = p->y >> cy, w = p->w >> cx, hh = p->h >> cy;
     const int bi = (p->lists == (HMR_PU_L0 | HMR_PU_L1));
-    if (p->lists & HMR_PU_L0) mc_block(&dpb[p->slots & 15], c, fmt, bd, x0, y0, w, hh, p->mv[0][0], p->mv[0][1], bi, a);
-    if (p->lists & HMR_PU_L1) mc_block(&dpb[p->slots >> 4], c, fmt, bd, x0, y0, w, hh, p->mv[1][0], p->mv[1][1], bi, bi ? b : a);
+    const int inter = bi || wp != NULL;                      /* keep the 14-bit intermediate */
+    if (p->lists & HMR_PU_L0) mc_block(&dpb[p->slots & 15], c, fmt, bd, x0, y0, w, hh, p->mv[0][0], p->mv[0][1], inter, a);
+    if (p->lists & HMR_PU_L1) mc_block(&dpb[p->slots >> 4], c, fmt, bd, x0, y0, w, hh, p->mv[1][0], p->mv[1][1], inter, bi ? b : a);
     const int headroom = (14 - bd) > 2 ? (14 - bd) : 2;
     const int sh = headroom + 1, off = (1 << (sh - 1)) + 2 * 8192, maxv = (1 << bd) - 1;
+    const hmr_wp* w0 = wp ? &wp[(0 * 16 + (refidx & 15)) * 3 + c] : NULL;
+    const hmr_wp* w1 = wp ? &wp[(1 * 16 + (refidx >> 4)) * 3 + c] : NULL;
     for (int y = 0; y < hh; y++) for (int x = 0; x < w; x++)
     {
-      int v = bi ? clip3(0, maxv, (a[y * w + x] + b[y * w + x] + off) >> sh) : a[y * w + x];
+      int v;
+      if (!wp) v = bi ? clip3(0, maxv, (a[y * w + x] + b[y * w + x] + off) >> sh) : a[y * w + x];
+      else if (bi)
+      {
+        const int shift = w0->log2_denom + 1 + headroom, round = 1 << (shift - 1), offset = w0->offset + w1->offset;
+        v = clip3(0, maxv, (w0->weight * (a[y * w + x] + 8192) + w1->weight * (b[y * w + x] + 8192) + round + (offset << (shift - 1))) >> shift);
+      }
+      else
+      {
+        const hmr_wp* q = (p->lists & HMR_PU_L0) ? w0 : w1;
+        const int shift = q->log2_denom + headroom, round = shift > 0 ? 1 << (shift - 1) : 0;
+        v = clip3(0, maxv, ((q->weight * (a[y * w + x] + 8192) + round) >> shift) + q->offset);
+      }
       dst->plane[c][(size_t)(y0 + y) * dst->stride[c] + x0 + x] = (int16_t)v;
     }
   }
@@ -563,7 +581,8 @@ int orc_reconstruct_frame(const hmr_frame_desc* f, orc_pic* dpb, orc_pic* work, 
   if (h->magic != HMR_MAGIC || h->version != HMR_VERSION) return -1;
 
   if (stage_mask & 1)
-    for (uint32_t i = 0; i < h->n_pu; i++) orc_predict_pu(h, &f->pu[i], dpb, work);
+    for (uint32_t i = 0; i < h->n_pu; i++)
+      orc_predict_pu(h, &f->pu[i], (h->flags & HMR_FRM_WEIGHTED_PRED) ? f->wp : NULL, (h->flags & HMR_FRM_WEIGHTED_PRED) ? f->pu_refidx[i] : 0, dpb, work);
 
   if (stage_mask & 2)
   {

@@ -30,9 +30,9 @@ def test_record_struct_sizes_match_header(tmp_path):
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)]).decode().split()
-    assert out == ["80", "20", "16", "24", "16", "10", "36", "96"]
+    assert out == ["80", "20", "16", "24", "16", "10", "36", "112"]
     from libhm_b200 import records
-    assert records.HDR_DT.itemsize == 80 and C.sizeof(records.FrameDesc) == 96
+    assert records.HDR_DT.itemsize == 80 and C.sizeof(records.FrameDesc) == 112
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -27,6 +27,8 @@ JOBS=(
  "s_sl8_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 20 --ScalingList=1 -q 27"
  "s_pcm_240p         encoder_randomaccess_main10.cfg       416  240  5  8  420 21 --InternalBitDepth=10 --PCMEnabledFlag=1 --PCMFilterDisableFlag=1 -q 1"
  "s_lossless_240p    encoder_randomaccess_main.cfg         208  120  5  8  420 22 --TransquantBypassEnableFlag=1 --CUTransquantBypassFlagForce=1 -q 30"
+ "s_wpp_240p         encoder_lowdelay_P_main.cfg           416  240  9  8  420 23 --WeightedPredP=1 -q 30"
+ "s_wpb_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 24 --WeightedPredB=1 --WeightedPredP=1 -q 30"
  "c2_ra8_1080p       encoder_randomaccess_main.cfg         1920 1080 64 8  420 2"
  "c3_ra10_2160p      encoder_randomaccess_main10.cfg       3840 2160 33 10 420 3"
  "c4_rext444_1080p   encoder_intra_high_throughput_rext.cfg 1920 1080 8 12 444 4 --InternalBitDepth=12"
@@ -49,7 +51,8 @@ for j in "${JOBS[@]}"; do
   out=$ROOT/corpus/$name
   [ -s "$out.bin" ] && [ -s "$out.yuvmd5" ] && { echo "$name: exists"; exit 0; }
   yuv=$TMP_YUV/$name.yuv
-  if [ "$name" == "s_pcm_240p" ]; then python "$ROOT/tools/gen_pcm_yuv.py" "$yuv" --width $W --height $H --frames $F --seed $SEED   # noise: makes the encoder choose I_PCM
+  if [ "$name" == "s_wpp_240p" ] || [ "$name" == "s_wpb_240p" ]; then python "$ROOT/tools/gen_fade_yuv.py" "$yuv" --width $W --height $H --frames $F --seed $SEED   # fade: non-trivial WP weights
+  elif [ "$name" == "s_pcm_240p" ]; then python "$ROOT/tools/gen_pcm_yuv.py" "$yuv" --width $W --height $H --frames $F --seed $SEED   # noise: makes the encoder choose I_PCM
   else python "$ROOT/tools/gen_yuv.py" "$yuv" --width $W --height $H --frames $F --bitdepth $BD --seed $SEED --chroma $CH; fi
   CF=""; [ "$CH" != "420" ] && CF="--InputChromaFormat=$CH"
   "$ENC" -c "$REF/cfg/$cfg" -i "$yuv" -wdt $W -hgt $H -f $F -fr 30 --InputBitDepth=$BD $CF \
