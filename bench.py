@@ -80,6 +80,28 @@ class ClockSampler:
                 "samples": len(rows), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/*_full_raw.csv,
+    produced by tools/profile_run.sh); None when no capture is shipped.  Returns (bytes, file name)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kernel}_kernel_full_raw.csv")))
+    if not files:
+        return None, None
+    rows = list(csv.reader(open(files[-1])))
+    if len(rows) < 3:
+        return None, None
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        if name not in hdr:
+            return None, None
+        i = hdr.index(name)
+        total += float(vals[i].replace(",", "")) * scale.get(units[i], 1.0)
+    return total, os.path.basename(files[-1])
+
+
 def algorithmic_bytes(fr):
     """Algorithmic bytes one launch of each kernel moves for this picture (definitions: DESIGN.md §d / SURVEY.md §8d)."""
     import numpy as np
@@ -258,8 +280,10 @@ def main():
             kern[k] = {"us_per_picture": round(1000 * dur_ms / F, 2), "share": round(t[k] / tot, 4), "alg_MB_per_picture": round(alg[k] / F / 1e6, 3),
                        "achieved_GBs": round(gbs, 1), "frac": round(gbs / peak, 4)}
         top = max(kern, key=lambda k: kern[k]["share"])
+        traffic, traffic_src = ncu_traffic({"deblock_v": "deblock", "deblock_h": "deblock"}.get(top, top))
         roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": kern[top]["frac"],
-                "traffic": None, "peak_source": peak_src, "note": "algorithmic bytes / CUDA-event duration, single-stream pass; all kernels in `kernels`"}
+                "traffic": traffic, "traffic_source": (traffic_src + ": ncu --set full, the launch of the I picture (the heaviest launch of the pass; `achieved` averages all pictures)") if traffic_src else None,
+                "peak_source": peak_src, "note": "algorithmic bytes / CUDA-event duration, single-stream pass; all kernels in `kernels`; intra is bounded by its dependency chain, not by HBM (DESIGN.md K3)"}
     for e, hs in zip(engines, handles):
         for h in hs:
             e.free_resident(h)
