@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=4, help="independent bitstreams reconstructed concurrently per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="independent bitstreams reconstructed concurrently per GPU")
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

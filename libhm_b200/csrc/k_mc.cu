@@ -210,6 +210,23 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
     if (!(t.lists & (1 << list))) continue;                  // warp-uniform
     const int mvx = t.mv[list][0], mvy = t.mv[list][1];
     const int fx = mvx & ((4 << cx) - 1), fy = mvy & ((4 << cy) - 1);
+    if ((fx | fy) == 0)
+    {
+      // TComInterpolationFilter::filterCopy (TComInterpolationFilter.cpp:94-148): the staged window IS the block
+      if (lane < nV)
+      {
+        const int16_t* src = sref[list] + 2 * yg * MC_PITCH + offs[list] + 4 * x4;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+          const int smp = src[(i >> 2) * MC_PITCH + (i & 3)];
+          if (wpOn)    acc[i] += wpW[list] * (smp << headroom);                     // (P + IF_INTERNAL_OFFS), P = (s << headroom) - 8192
+          else if (bi) acc[i] += (int)(int16_t)((smp << headroom) - 8192);
+          else         acc[i] = smp;
+        }
+      }
+      continue;
+    }
     const McTaps<NT> tx = mc_load_taps<NT>(NT == 8 ? fx : fx << (1 - cx));
     const McTaps<NT> ty = mc_load_taps<NT>(NT == 8 ? fy : fy << (1 - cy));
     mc_hpass<NT>(sref[list], tmp, offs[list], rowPairs, log2ColPairs, tx, s1, o1, lane);
@@ -310,10 +327,13 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
       offs[comp][list] = 0;
       if (!(t.lists & (1 << list))) continue;
       const int slot = list ? (t.slots >> 4) : (t.slots & 15);
-      const int ix = (t.x >> cx) + (t.mv[list][0] >> (2 + cx)) - half, iy = (t.y >> cy) + (t.mv[list][1] >> (2 + cy)) - half;
+      // integer-sample motion (HM's filterCopy case): only the block itself is needed, no filter support around it
+      const bool whole = ((t.mv[list][0] & ((4 << cx) - 1)) | (t.mv[list][1] & ((4 << cy) - 1))) == 0;
+      const int ix = (t.x >> cx) + (t.mv[list][0] >> (2 + cx)) - (whole ? 0 : half), iy = (t.y >> cy) + (t.mv[list][1] >> (2 + cy)) - (whole ? 0 : half);
       const int xa = ix & ~7, off = ix - xa;
       offs[comp][list] = off;
-      mc_stage(s, P.dpb[slot].p[comp], P.dpb[slot].pitch[comp], P.w[comp], P.h[comp], ix, iy, xa, rows, cols, (off + cols + 7) >> 3, lane);
+      const int wrows = whole ? th : rows, wcols = whole ? tw : cols;
+      mc_stage(s, P.dpb[slot].p[comp], P.dpb[slot].pitch[comp], P.w[comp], P.h[comp], ix, iy, xa, wrows, wcols, (off + wcols + 7) >> 3, lane);
     }
     if (comp == 0 || comp == 2) mc_cp_async_commit();
   }
