@@ -134,6 +134,13 @@ public:
 
   virtual bool wantHmRecon() const { return m_verify; }
 
+  virtual bool readPacked(TComPic* pic, const int outBitDepth[2], const int crop[4], void* dst, size_t capacity, size_t* bytes)
+  {
+    std::map<TComPic*, State>::iterator it = m_state.find(pic);
+    if (it == m_state.end()) return false;
+    return hmr_read_packed(m_eng, it->second.slot, outBitDepth, crop, dst, capacity, bytes) == HMR_OK;
+  }
+
   virtual bool asyncMd5(TComPic* pic, const unsigned char* expected, int ncomp, const std::string& line, bool quiet)
   {
     std::map<TComPic*, State>::iterator it = m_state.find(pic);

@@ -43,6 +43,10 @@ struct HmFrameSink
   // Deliver digests that have arrived (wait = true: all of them).
   virtual void drainHashes(bool wait) { (void)wait; }
   virtual bool hashMismatchSeen() const { return false; }
+  // The picture in TAppDecoder's `-o` wire format, packed where it lives (crop = left, right, top, bottom luma samples;
+  // outBitDepth = luma, chroma; 0 = internal).  *bytes = packed size; dst == NULL only queries it.  false = not available.
+  virtual bool readPacked(TComPic* pic, const int outBitDepth[2], const int crop[4], void* dst, size_t capacity, size_t* bytes)
+  { (void)pic; (void)outBitDepth; (void)crop; (void)dst; (void)capacity; (void)bytes; return false; }
   // Called before HM's picture buffers are freed (the sink may hold page-locks on them).
   virtual void releaseHostBuffers() {}
 };

@@ -197,6 +197,20 @@ bool libHMDecB200_hash_mismatch(libHMDec_context* decCtx)
   if (d->sink->hashMismatchSeen()) d->hashMismatch = true;
   return d->hashMismatch;
 }
+long libHMDecB200_pack_picture(libHMDec_context* decCtx, libHMDec_picture* pic, int outBitDepthLuma, int outBitDepthChroma, void* dst, size_t capacity)
+{
+  Decoder* d = D(decCtx);
+  if (!d || !pic) return -1;
+  TComPic* p = (TComPic*)pic;
+  // the window TAppDecoder crops to when writing `-o` (TAppDecTop.cpp:476-487): conformance window (+ default display window: not respected by default)
+  const Window& conf = p->getConformanceWindow();
+  const int crop[4] = { conf.getWindowLeftOffset(), conf.getWindowRightOffset(), conf.getWindowTopOffset(), conf.getWindowBottomOffset() };
+  const int bd[2] = { outBitDepthLuma, outBitDepthChroma };
+  size_t bytes = 0;
+  if (!d->sink->readPacked(p, bd, crop, dst, capacity, &bytes)) return -1;
+  return (long)bytes;
+}
+
 const char* libHMDecB200_unsupported(libHMDec_context* decCtx) { return decCtx ? D(decCtx)->emitter->unsupported() : NULL; }
 
 libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data8, int length, bool eof, bool& bNewPicture, bool& checkOutputPictures)

@@ -1,7 +1,7 @@
 // hmdec_cli.cpp — Annex-B harness around the libHMDec_* entry points (the loop documented in the
 // reference header, libHMDecoder.h:38-77): split the byte stream into NAL units, push them one at a
 // time, re-push when bNewPicture comes back, drain pictures when checkOutputPictures is set.
-//   hmdec_cli -b in.bin [-o out.yuv] [--dump records.hmr] [--no-hash] [--touch-planes]
+//   hmdec_cli -b in.bin [-o out.yuv [--packed [-d bits]]] [--dump records.hmr] [--no-hash] [--touch-planes]
 // -o writes the FULL coded picture (the wrapper API exposes no conformance window), 1 byte/sample for
 // 8-bit streams and 2 bytes little-endian otherwise.
 #include <cstdio>
@@ -35,13 +35,16 @@ static void writePicture(FILE* f, libHMDec_picture* pic, int bitDepth[2])
 int main(int argc, char** argv)
 {
   const char* in = NULL; const char* out = NULL; const char* dump = NULL;
-  bool hash = true, touch = false; int repeat = 1;
+  bool hash = true, touch = false, packed = false; int repeat = 1, outDepth = 0;
+  std::vector<uint8_t> packBuf;
   for (int i = 1; i < argc; i++)
   {
     if (!strcmp(argv[i], "-b") && i + 1 < argc) in = argv[++i];
     else if (!strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
     else if (!strcmp(argv[i], "--dump") && i + 1 < argc) dump = argv[++i];
     else if (!strcmp(argv[i], "--no-hash")) hash = false;
+    else if (!strcmp(argv[i], "--packed")) packed = true;                       // -o in TAppDecoder's format (cropped / converted on the GPU)
+    else if (!strcmp(argv[i], "-d") && i + 1 < argc) outDepth = atoi(argv[++i]);   // output bit depth for --packed (0 = internal)
     else if (!strcmp(argv[i], "--touch-planes")) touch = true;
     else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = atoi(argv[++i]);
     else { fprintf(stderr, "usage: %s -b in.bin [-o out.yuv] [--dump file] [--no-hash] [--touch-planes] [--repeat N]\n", argv[0]); return 2; }
@@ -74,7 +77,16 @@ int main(int argc, char** argv)
         {
           pictures++;
           int bd[2] = { libHMDEC_get_internal_bit_depth(LIBHMDEC_LUMA), libHMDEC_get_internal_bit_depth(LIBHMDEC_CHROMA_U) };
-          if (fo) writePicture(fo, pic, bd);
+          if (fo && packed)
+          {
+            // TAppDecoder -o equivalent: cropped, bit-depth converted and packed on the GPU
+            long n = libHMDecB200_pack_picture(dec, pic, outDepth, outDepth, NULL, 0);
+            if (n < 0) { fprintf(stderr, "pack_picture failed\n"); return 5; }
+            if ((size_t)n > packBuf.size()) packBuf.resize((size_t)n);
+            if (libHMDecB200_pack_picture(dec, pic, outDepth, outDepth, packBuf.data(), packBuf.size()) != n) { fprintf(stderr, "pack_picture failed\n"); return 5; }
+            fwrite(packBuf.data(), 1, (size_t)n, fo);
+          }
+          else if (fo) writePicture(fo, pic, bd);
           else if (touch) for (int c = 0; c < 3; c++) (void)libHMDEC_get_image_plane(pic, (libHMDec_ColorComponent)c);
         }
       }

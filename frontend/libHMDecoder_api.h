@@ -54,6 +54,10 @@ libHMDec_error     libHMDEC_clear_internal_info(libHMDec_context* decCtx);
 libHMDec_context*  libHMDecB200_new_decoder_ex(int backend, const char* arg);
 // true when any SEI decoded-picture-hash check failed so far (the reference only prints it, libHMDecoder.cpp:59,165)
 bool               libHMDecB200_hash_mismatch(libHMDec_context* decCtx);
+// The picture as TAppDecoder's `-o` would write it (conformance-window crop, output bit depth 0 = internal, planar Y/Cb/Cr,
+// 1 byte per sample when both depths <= 8 else 2 bytes LE), packed on the device: only these bytes cross PCIe.
+// Returns the number of bytes (dst == NULL: query only) or -1.
+long               libHMDecB200_pack_picture(libHMDec_context* decCtx, libHMDec_picture* pic, int outBitDepthLuma, int outBitDepthChroma, void* dst, size_t capacity);
 // name of the first bitstream feature the GPU path does not implement, or NULL
 const char*        libHMDecB200_unsupported(libHMDec_context* decCtx);
 

@@ -9,6 +9,8 @@
  *                        (TDecGop::filterPicture, Lib/TLibDecoder/TDecGop.cpp:157-174)
  *   hmr_read_plane       replaces the host-memory plane access of TComPicYuv::getAddr as used by
  *                        libHMDEC_get_image_plane (App/libHMDecoder/libHMDecoder.cpp:402-417)
+ *   hmr_read_packed      replaces TVideoIOYuv::write (Lib/TLibVideoIO/TVideoIOYuv.cpp:706-790): crop, bit-depth conversion,
+ *                        8/16-bit packing of an output picture, on the device
  *   hmr_picture_hash     replaces calcChecksum / calcCRC (Lib/TLibCommon/TComPicYuvMD5.cpp:127-175)
  *   hmr_md5_submit/result replace calcMD5 (TComPicYuvMD5.cpp:183-205): one serial chain per plane, run asynchronously on
  *                        the device (many pictures in flight), so the SEI MD5 check costs the host nothing
@@ -71,6 +73,13 @@ int  hmr_picture_hash(hmr_engine* e, int slot, int type, uint32_t out[3]);
  * hmr_md5_result: out = 3 x 16 digest bytes (Y, Cb, Cr); wait = 0 polls (HMR_PENDING while running). */
 int  hmr_md5_submit(hmr_engine* e, int slot, uint64_t* job);
 int  hmr_md5_result(hmr_engine* e, uint64_t job, uint8_t out[48], int wait);
+
+/* The picture in `slot` in TAppDecoder's `-o` wire format (replaces TVideoIOYuv::write, Lib/TLibVideoIO/TVideoIOYuv.cpp:706-790):
+ * cropped by crop[4] = {left, right, top, bottom} luma samples (conformance + default display window), converted to
+ * out_bit_depth[2] = {luma, chroma} (0 = internal; rounding shift + clip when smaller), planar Y, Cb, Cr, one byte per sample
+ * when both output depths are <= 8, else two bytes little endian.  Packing runs on the device, only the packed bytes cross
+ * PCIe.  *bytes = size of the packed picture; dst == NULL only queries it.  Synchronous. */
+int  hmr_read_packed(hmr_engine* e, int slot, const int out_bit_depth[2], const int crop[4], void* dst, size_t capacity, size_t* bytes);
 
 /* Page-lock / unlock caller memory so that hmr_read_plane_async can DMA straight into it (e.g. HM's TComPicYuv planes). */
 int  hmr_host_register(void* p, size_t bytes);

@@ -55,3 +55,5 @@ void launch_sao(const FrameParams& P, cudaStream_t s);
 void launch_hash(const PlaneSet& pic, const int w[3], const int h[3], const int bd[3], int type, uint32_t* d_out, uint32_t* d_scratch, cudaStream_t s);
 int  intra_max_coresident_blocks(int device);
 size_t intra_table_bytes(int nctu);
+size_t launch_pack(const PlaneSet& pic, const int w[3], const int h[3], int csx, int csy, int ncomp, const int bdInternal[3], const int bdOut[3],
+                   const int crop[4], uint8_t* d_dst, cudaStream_t s);

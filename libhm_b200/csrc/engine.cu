@@ -52,6 +52,7 @@ struct hmr_engine
   int ringPos;
   int16_t* resid; size_t residCap;
   hmr_pu* mcTiles; size_t mcTilesCap; uint8_t* mcTileRef;
+  uint8_t* packBuf; size_t packCap;
   unsigned long long* progress; size_t progressCap;
   uint4* intraOps; size_t intraOpsCap; uint16_t* intraTab; size_t intraTabBytes; uint4* intraPrep; size_t intraPrepBytes;
   unsigned long long epoch;
@@ -390,7 +391,7 @@ int hmr_engine_create(hmr_engine** out, int device)
   e->haveGeom = false; e->workAlloc = false;
   memset(e->slotAlloc, 0, sizeof(e->slotAlloc));
   memset(e->ring, 0, sizeof(e->ring));
-  e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->mcTiles = nullptr; e->mcTilesCap = 0; e->mcTileRef = nullptr; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
+  e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->mcTiles = nullptr; e->mcTilesCap = 0; e->mcTileRef = nullptr; e->packBuf = nullptr; e->packCap = 0; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
   e->intraOps = nullptr; e->intraOpsCap = 0; e->intraTab = nullptr; e->intraTabBytes = 0; e->intraPrep = nullptr; e->intraPrepBytes = 0;
   e->stageMask = HMR_STAGE_ALL; e->timing = false;
   memset(e->accMs, 0, sizeof(e->accMs)); e->accFrames = e->accLaunches = 0;
@@ -427,6 +428,7 @@ void hmr_engine_destroy(hmr_engine* e)
   pool_free(e->device, e->resid, e->residCap * sizeof(int16_t));
   pool_free(e->device, e->mcTiles, e->mcTilesCap * sizeof(hmr_pu));
   pool_free(e->device, e->mcTileRef, e->mcTilesCap);
+  pool_free(e->device, e->packBuf, e->packCap);
   pool_free(e->device, e->progress, e->progressCap * sizeof(unsigned long long));
   pool_free(e->device, e->intraOps, e->intraOpsCap * sizeof(uint4));
   pool_free(e->device, e->intraTab, e->intraTabBytes);
@@ -772,6 +774,31 @@ int hmr_md5_result(hmr_engine* e, uint64_t job, uint8_t out[48], int wait)
   m.busy = false;
   if (st < 0) return fail(e, HMR_ERR_CUDA, "md5_result: the hash service failed");
   memcpy(out, m.hOut, 48);
+  return HMR_OK;
+}
+
+int hmr_read_packed(hmr_engine* e, int slot, const int out_bit_depth[2], const int crop[4], void* dst, size_t capacity, size_t* bytes)
+{
+  if (!e || slot < 0 || slot >= HMR_MAX_SLOTS || !e->slotAlloc[slot] || !out_bit_depth || !crop || !bytes) return fail(e, HMR_ERR_ARG, "read_packed: bad argument");
+  CK(cudaSetDevice(e->device));
+  const int ncomp = e->fmt == HMR_CHROMA_400 ? 1 : 3;
+  const int bdIn[3] = { e->bdLuma, e->bdChroma, e->bdChroma };
+  const int bdOut[3] = { out_bit_depth[0] > 0 ? out_bit_depth[0] : e->bdLuma, out_bit_depth[1] > 0 ? out_bit_depth[1] : e->bdChroma, out_bit_depth[1] > 0 ? out_bit_depth[1] : e->bdChroma };
+  for (int c = 0; c < 3; c++) if (bdOut[c] < 1 || bdOut[c] > 16) return fail(e, HMR_ERR_ARG, "read_packed: output bit depth outside 1..16");
+  const size_t need = launch_pack(e->slots[slot], e->w, e->h, e->csx, e->csy, ncomp, bdIn, bdOut, crop, nullptr, e->stream);   // size only
+  *bytes = need;
+  if (!dst) return HMR_OK;
+  if (need > capacity) return fail(e, HMR_ERR_ARG, "read_packed: destination too small");
+  if (need > e->packCap)
+  {
+    pool_free(e->device, e->packBuf, e->packCap);
+    e->packCap = ALIGN_UP(need, 1 << 20);
+    CK(pool_malloc(e->device, (void**)&e->packBuf, e->packCap));
+  }
+  launch_pack(e->slots[slot], e->w, e->h, e->csx, e->csy, ncomp, bdIn, bdOut, crop, e->packBuf, e->stream);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst, e->packBuf, need, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
   return HMR_OK;
 }
 

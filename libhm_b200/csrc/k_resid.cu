@@ -175,20 +175,32 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
   const int maxv = (1 << bd) - 1;
   int16_t* plane = P.work.p[t.comp];
   const int pitch = P.work.pitch[t.comp];
-  for (int y = 0; y < N; y++)
+  int16_t* d0 = plane + (size_t)t.y * pitch + t.x + j;
+  // loads of a batch of rows first (prediction samples, luma residuals for CCP): independent loads in flight instead of
+  // one load -> store round trip per row
+  constexpr int BATCH = N < 8 ? N : 8;
+#pragma unroll 1
+  for (int y0 = 0; y0 < N; y0 += BATCH)
   {
-    int r = sb[y * LD + j];
-    if (ccp)
+    int cur[BATCH], lum[BATCH];
+#pragma unroll
+    for (int i = 0; i < BATCH; i++)
     {
-      const int l = P.resid[t.luma_off + y * N + j];
-      const int ls = diffBd >= 0 ? (l >> diffBd) : (l << (-diffBd));
-      r = (int16_t)(r + ((t.ccp_alpha * ls) >> 3));
+      cur[i] = add ? (int)d0[(size_t)(y0 + i) * pitch] : 0;
+      lum[i] = ccp ? (int)P.resid[t.luma_off + (y0 + i) * N + j] : 0;
     }
-    if (keep) P.resid[t.coef_off + y * N + j] = (int16_t)r;
-    if (add)
+#pragma unroll
+    for (int i = 0; i < BATCH; i++)
     {
-      int16_t* d = plane + (size_t)(t.y + y) * pitch + t.x + j;
-      *d = (int16_t)clip3i(0, maxv, *d + r);
+      const int y = y0 + i;
+      int r = sb[y * LD + j];
+      if (ccp)
+      {
+        const int ls = diffBd >= 0 ? (lum[i] >> diffBd) : (lum[i] << (-diffBd));
+        r = (int16_t)(r + ((t.ccp_alpha * ls) >> 3));
+      }
+      if (keep) P.resid[t.coef_off + y * N + j] = (int16_t)r;
+      if (add) d0[(size_t)y * pitch] = (int16_t)clip3i(0, maxv, cur[i] + r);
     }
   }
 }

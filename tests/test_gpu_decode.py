@@ -57,3 +57,20 @@ def test_full_size_streams_pass_the_sei_md5_check(name):
     ref_file = os.path.join(BENCH, name + ".md5")
     if os.path.exists(ref_file):
         assert got == _md5s(open(ref_file).read())
+
+
+def test_packed_output_equals_tappdecoder_o(tmp_path):
+    """Output wire format: `hmdec_cli -o --packed [-d N]` = conformance-window crop + bit-depth conversion +
+    8/16-bit packing on the GPU (hmr_read_packed) must give the very file `TAppDecoder -o [-d N]` writes.  The stream is
+    202x134 10-bit (coded 208x136, non-zero conformance window); tests/golden/s_crop10.yuvmd5 holds the reference MD5s."""
+    import hashlib
+    if not os.path.exists(CLI):
+        pytest.skip("frontend not built")
+    want = dict(l.split() for l in open(os.path.join(GOLDEN, "s_crop10.yuvmd5")))
+    for depth, key, size in ((0, "d0", 202 * 134 * 3 * 5), (8, "d8", 202 * 134 * 3 // 2 * 5)):
+        out = str(tmp_path / f"o{depth}.yuv")
+        r = subprocess.run([CLI, "-b", os.path.join(GOLDEN, "s_crop10.bin"), "-o", out, "--packed", "-d", str(depth)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        data = open(out, "rb").read()
+        assert len(data) == size
+        assert hashlib.md5(data).hexdigest() == want[key], f"-d {depth}"
