@@ -630,8 +630,18 @@ void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, T
   const int cuSize = g_uiMaxCUWidth >> depth;
   for (int dir = 0; dir < 2; dir++)
   {
+    const Bool* edgeFlag = lf->m_aapbEdgeFilter[dir];
     for (unsigned part = absZorderIdx; part < absZorderIdx + curNumParts; part++)
     {
+      // most partitions carry no edge at all (large CUs): skip runs of 8 clear flags at once (CUs start at multiples of 4
+      // partitions and the flag arrays are 8-byte aligned allocations)
+      if ((part & 7) == 0 && part + 8 <= absZorderIdx + curNumParts)
+      {
+        uint64_t w;
+        memcpy(&w, edgeFlag + part, 8);
+        if (w == 0) { part += 7; continue; }
+      }
+      if (!edgeFlag[part]) continue;
       // only partitions on the 8x8 luma grid carry an edge (uiBSCheck, TComLoopFilter.cpp:199-206)
       const unsigned raster = g_auiZscanToRaster[part];
       const int ux = g_auiRasterToPelX[raster] >> 2, uy = g_auiRasterToPelY[raster] >> 2;

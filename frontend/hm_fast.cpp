@@ -140,6 +140,70 @@ static void forgetMotion(TComPic* pic)
   g_motionPending.erase(pic);
 }
 
+// ---- process-wide pool of complete picture buffers ------------------------------------------------------------
+// A TComPic of a 2160p stream is ~70 000 allocations (2040 CTUs x ~35 arrays).  A decoder that ends parks its pictures here
+// (planes attached) and the next decoder of the same geometry adopts them: opening a new bitstream costs no allocation.
+// HMDEC_B200_NO_PIC_POOL=1 disables the pool (pictures are then freed with their decoder, as in stock HM).
+struct PicKey
+{
+  int w, h, fmt; unsigned cuW, cuH, depth;
+  bool operator<(const PicKey& o) const
+  {
+    if (w != o.w) return w < o.w; if (h != o.h) return h < o.h; if (fmt != o.fmt) return fmt < o.fmt;
+    if (cuW != o.cuW) return cuW < o.cuW; if (cuH != o.cuH) return cuH < o.cuH; return depth < o.depth;
+  }
+};
+static std::mutex g_picPoolLock;
+static std::multimap<PicKey, TComPic*> g_picPool;
+
+static PicKey keyOfSps(TComSPS* sps)
+{
+  PicKey k = { (int)sps->getPicWidthInLumaSamples(), (int)sps->getPicHeightInLumaSamples(), (int)sps->getChromaFormatIdc(), g_uiMaxCUWidth, g_uiMaxCUHeight, g_uiMaxCUDepth };
+  return k;
+}
+static PicKey keyOfPic(TComPic* pic)
+{
+  TComPicYuv* rec = pic->getPicYuvRec();
+  TComPicSym* sym = pic->m_apcPicSym;
+  PicKey k = { rec->getWidth(COMPONENT_Y), rec->getHeight(COMPONENT_Y), (int)rec->getChromaFormat(), sym->m_uiMaxCUWidth, sym->m_uiMaxCUHeight, (unsigned)sym->m_uhTotalDepth };
+  return k;
+}
+
+static bool poolEnabled() { static const bool on = getenv("HMDEC_B200_NO_PIC_POOL") == NULL; return on; }
+
+// A parked picture of this geometry, made safe for the calling thread, or NULL.
+static TComPic* takeFromPool(TComSPS* sps)
+{
+  if (!poolEnabled()) return NULL;
+  TComPic* pic = NULL;
+  {
+    std::lock_guard<std::mutex> g(g_picPoolLock);
+    std::multimap<PicKey, TComPic*>::iterator it = g_picPool.find(keyOfSps(sps));
+    if (it == g_picPool.end()) return NULL;
+    pic = it->second;
+    g_picPool.erase(it);
+  }
+  // The CTUs' ARL coefficient pointers alias a per-THREAD global buffer of the thread that created them
+  // (TComDataCU.cpp:178-181, made thread_local by frontend/Makefile): re-point them at this thread's buffer.
+  TComPicSym* sym = pic->m_apcPicSym;
+  for (UInt a = 0; a < sym->m_uiNumCUsInFrame; a++)
+  {
+    TComDataCU* cu = sym->m_apcTComDataCU[a];
+    if (!cu->m_ArlCoeffIsAliasedAllocation) continue;
+    for (UInt c = 0; c < MAX_NUM_COMPONENT; c++)
+    {
+      if (!cu->m_pcArlCoeff[c]) continue;
+      if (!TComDataCU::m_pcGlbArlCoeff[c])
+      {
+        const UInt shift = getComponentScaleX(ComponentID(c), sps->getChromaFormatIdc()) + getComponentScaleY(ComponentID(c), sps->getChromaFormatIdc());
+        TComDataCU::m_pcGlbArlCoeff[c] = (TCoeff*)xMalloc(TCoeff, (g_uiMaxCUWidth * g_uiMaxCUHeight) >> shift);
+      }
+      cu->m_pcArlCoeff[c] = TComDataCU::m_pcGlbArlCoeff[c];
+    }
+  }
+  return pic;
+}
+
 // Every picture buffer a decoder ever created.  The wrapper's flush (like the reference's, libHMDecoder.cpp:329-336) only
 // drops the pointers from the DPB list; without this registry those pictures would be lost and never reused.
 static std::mutex g_createdLock;
@@ -179,6 +243,17 @@ void hm_fast_release_decoder(TDecTop* dec)
   {
     TComPic* pic = mine[i];
     forgetMotion(pic);
+    if (poolEnabled() && pic->m_apcPicSym && pic->getPicYuvRec())
+    {
+      // park the complete buffer (planes stay attached); HM's teardown must not see it any more
+      for (TComList<TComPic*>::iterator it = dec->m_cListPic.begin(); it != dec->m_cListPic.end();)
+        if (*it == pic) it = dec->m_cListPic.erase(it); else ++it;
+      if (pic->m_SEIs.size() > 0) deleteSEIs(pic->m_SEIs);
+      pic->m_apcPicSym->clearSliceBuffer();                  // slices point into the dying decoder's parameter sets
+      std::lock_guard<std::mutex> g(g_picPoolLock);
+      g_picPool.insert(std::make_pair(keyOfPic(pic), pic));
+      continue;
+    }
     releasePlanes(pic->getPicYuvRec());
     bool listed = false;
     for (TComList<TComPic*>::iterator it = dec->m_cListPic.begin(); it != dec->m_cListPic.end() && !listed; ++it) listed = (*it == pic);
@@ -237,6 +312,12 @@ Void TDecTop::xGetNewPicBuffer(TComSlice* pcSlice, TComPic*& rpcPic)
       rpcPic->setOutputMark(false); rpcPic->setReconMark(false);
       resetPicture(rpcPic, conf, disp, reorder);
     }
+    else if ((rpcPic = takeFromPool(sps)) != NULL)
+    {
+      rpcPic->setOutputMark(false); rpcPic->setReconMark(false);
+      resetPicture(rpcPic, conf, disp, reorder);
+      remember(this, rpcPic);
+    }
     else
     {
       rpcPic = new TComPic();
@@ -259,9 +340,17 @@ Void TDecTop::xGetNewPicBuffer(TComSlice* pcSlice, TComPic*& rpcPic)
   {
     // no room (faulty encoder or dropped NAL): extend the buffer
     m_iMaxRefPicNum++;
-    rpcPic = new TComPic();
+    if ((rpcPic = takeFromPool(sps)) != NULL)
+    {
+      rpcPic->setOutputMark(false); rpcPic->setReconMark(false);
+      resetPicture(rpcPic, conf, disp, reorder);
+    }
+    else
+    {
+      rpcPic = new TComPic();
+      createPicture(rpcPic, sps, conf, disp, reorder);
+    }
     m_cListPic.pushBack(rpcPic);
-    createPicture(rpcPic, sps, conf, disp, reorder);
     remember(this, rpcPic);
     return;
   }

@@ -1,0 +1,36 @@
+import sys,subprocess,bisect,collections
+maps=[];samples=[]
+for l in open(sys.argv[1]):
+    if l[0]=='M':
+        p=l[2:].split()
+        a,b=[int(x,16) for x in p[0].split('-')]; off=int(p[2],16); path=p[5] if len(p)>5 else ''
+        maps.append((a,b,off,path))
+    else: samples.append(int(l[2:],16))
+syms={}
+def load(path):
+    if path in syms: return syms[path]
+    try:
+        out=subprocess.run(['nm','-C','--defined-only','-n',path],capture_output=True,text=True).stdout
+        if not out.strip(): out=subprocess.run(['nm','-C','-D','--defined-only','-n',path],capture_output=True,text=True).stdout
+    except Exception: out=''
+    arr=[]
+    for l in out.splitlines():
+        p=l.split(' ',2)
+        if len(p)==3 and p[1] in 'TtWw':
+            arr.append((int(p[0],16),p[2]))
+    arr.sort(); syms[path]=(arr,[a for a,_ in arr]); return syms[path]
+cnt=collections.Counter(); mod=collections.Counter()
+for pc in samples:
+    for a,b,off,path in maps:
+        if a<=pc<b:
+            arr,keys=load(path) if path.startswith('/') else ([],[])
+            va=pc-a+off
+            # for PIE/shared: symbol addresses are file vaddrs; assume vaddr==file offset mapping for text
+            i=bisect.bisect_right(keys,va)-1
+            name=arr[i][1] if i>=0 else '?'
+            cnt[(path.split('/')[-1],name)]+=1; mod[path.split('/')[-1]]+=1
+            break
+    else: cnt[('?','?')]+=1
+tot=len(samples); print('samples',tot)
+for m,c in mod.most_common(8): print(f'  module {m}: {100*c/tot:.1f}%')
+for (m,nm),c in cnt.most_common(int(sys.argv[2]) if len(sys.argv)>2 else 45): print(f'{100*c/tot:5.1f}% {c:6d} {m[:22]:22s} {nm[:100]}')
