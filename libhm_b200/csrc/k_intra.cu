@@ -348,46 +348,60 @@ __device__ __forceinline__ void intra_tu(const IntraOp op, const int a[IN_NJMAX]
 }
 
 // ---- pre-pass: everything about the intra TUs that does not depend on sample data, for the whole picture at once ----
-// One CTA per (component, CTU): reference-address tables (compact, TU after TU), decoded micro-ops, and the CTU's
-// residual span.  The wavefront kernel below only copies these into shared memory.
-__global__ void __launch_bounds__(128) intra_prep_kernel(const __grid_constant__ FrameParams P)
+// One WARP per (component, CTU), four per CTA: reference-address tables (compact, TU after TU), decoded micro-ops, and the
+// CTU's residual span.  The wavefront kernel below only copies these into shared memory.  (A warp, not a CTA, per CTU:
+// most CTUs of an inter picture have no intra TU at all and a warp that finds nothing costs next to nothing.)
+#define PREP_WARPS 4
+__global__ void __launch_bounds__(PREP_WARPS * 32) intra_prep_kernel(const __grid_constant__ FrameParams P)
 {
-  __shared__ int s_off[IN_MAXREC + 1];
-  __shared__ unsigned s_mn, s_mx;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_offAll[PREP_WARPS][IN_MAXREC + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nctu = P.ctus_w * P.ctus_h;
-  const int comp = blockIdx.x / nctu, ctu = blockIdx.x - comp * nctu;
+  const int job = blockIdx.x * PREP_WARPS + warp;
+  if (job >= 3 * nctu) return;
+  const int comp = job / nctu, ctu = job - comp * nctu;
   if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) return;
-  const hmr_ctu_intra_range rg = P.irange[ctu];
-  const uint32_t first = rg.first[comp];
-  const int count = (int)min(rg.count[comp], (uint32_t)IN_MAXREC);
-  if (count == 0) { if (tid == 0) P.intra_prep[blockIdx.x] = make_uint4(0, 0, 0, 0); return; }
+  const uint32_t first = __ldg(&P.irange[ctu].first[comp]);
+  const int count = (int)min(__ldg(&P.irange[ctu].count[comp]), (uint32_t)IN_MAXREC);
+  if (count == 0) { if (lane == 0) P.intra_prep[job] = make_uint4(0, 0, 0, 0); return; }
+  int* s_off = s_offAll[warp];
   const int csx = comp ? P.csx : 0, csy = comp ? P.csy : 0;
   IntraGeom g;
   g.CTW = (1 << P.hdr.log2_ctu) >> csx; g.CTH = (1 << P.hdr.log2_ctu) >> csy;
   g.uws = 2 - csx; g.uhs = 2 - csy; g.gw = g.CTW >> 2;
   g.ox = (ctu % P.ctus_w) * g.CTW; g.oy = (ctu / P.ctus_w) * g.CTH;
-  if (tid == 0) { s_mn = 0xffffffffu; s_mx = 0; s_off[0] = 0; }
-  __syncthreads();
-  for (int k = tid; k < count; k += 128)
+  // table lengths -> exclusive prefix (warp scan over chunks of 32), residual span (warp min / max)
+  unsigned mn = 0xffffffffu, mx = 0;
+  int running = 0;
+  for (int k0 = 0; k0 < count; k0 += 32)
   {
-    const hmr_intra r = P.intra[first + k];
-    s_off[k + 1] = (4 << r.log2_size) + 1;
-    if (r.resid_off != HMR_NO_OFFSET) { atomicMin(&s_mn, r.resid_off); atomicMax(&s_mx, r.resid_off + (1u << (2 * r.log2_size))); }
+    const int k = k0 + lane;
+    int len = 0;
+    if (k < count)
+    {
+      const hmr_intra r = P.intra[first + k];
+      len = (4 << r.log2_size) + 1;
+      if (r.resid_off != HMR_NO_OFFSET) { mn = min(mn, r.resid_off); mx = max(mx, r.resid_off + (1u << (2 * r.log2_size))); }
+    }
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (k < count) s_off[k] = running + incl - len;
+    running += __shfl_sync(0xffffffffu, incl, 31);
   }
-  __syncthreads();
-  if (tid == 0) for (int k = 0; k < count; k++) s_off[k + 1] += s_off[k];     // <= 256 short steps; everything else is parallel
-  __syncthreads();
-  const unsigned mn = s_mn;
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  __syncwarp();
   const bool strongAllowed = P.hdr.flags & HMR_FRM_STRONG_INTRA_SMOOTHING;
-  uint16_t* tab = P.intra_tab + (size_t)blockIdx.x * IN_ADDR;
-  for (int k = warp; k < count; k += 4)
+  uint16_t* tab = P.intra_tab + (size_t)job * IN_ADDR;
+  for (int k = 0; k < count; k++)
   {
     const hmr_intra r = P.intra[first + k];
-    intra_addr_table(r, tab + s_off[k], g, lane);
-    if (lane == 0) P.intra_ops[first + k] = intra_make_op(r, g, mn, strongAllowed, s_off[k]);
+    const int off = s_off[k];
+    intra_addr_table(r, tab + off, g, lane);
+    if (lane == 0) P.intra_ops[first + k] = intra_make_op(r, g, mn, strongAllowed, off);
   }
-  if (tid == 0) P.intra_prep[blockIdx.x] = make_uint4(mn, s_mx > mn ? s_mx - mn : 0u, (unsigned)s_off[count], 0u);
+  if (lane == 0) P.intra_prep[job] = make_uint4(mn, mx > mn ? mx - mn : 0u, (unsigned)running, 0u);
 }
 
 // named barriers (id 0 is __syncthreads)
@@ -642,7 +656,7 @@ cudaError_t launch_intra(const FrameParams& P, cudaStream_t s)
   if (P.hdr.n_intra == 0) return cudaSuccess;
   if (P.ctus_w > IN_MAXCOLS) return cudaErrorInvalidValue;
   int resSamples = intra_res_samples(P);
-  intra_prep_kernel<<<3 * P.ctus_w * P.ctus_h, 128, 0, s>>>(P);
+  intra_prep_kernel<<<(3 * P.ctus_w * P.ctus_h + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, s>>>(P);
   void* args[] = { (void*)&P, (void*)&resSamples };
   return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(3 * P.ctus_h), dim3(IN_THREADS), args, intra_dyn_smem(resSamples), s);
 }
