@@ -27,6 +27,8 @@ JOBS=(
  "s_sl8_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 20 --ScalingList=1 -q 27"
  "s_pcm_240p         encoder_randomaccess_main10.cfg       416  240  5  8  420 21 --InternalBitDepth=10 --PCMEnabledFlag=1 --PCMFilterDisableFlag=1 -q 1"
  "s_lossless_240p    encoder_randomaccess_main.cfg         208  120  5  8  420 22 --TransquantBypassEnableFlag=1 --CUTransquantBypassFlagForce=1 -q 30"
+ "s_tiles_240p       encoder_randomaccess_main.cfg         640  256  9  8  420 27 --TileUniformSpacing=1 --NumTileColumnsMinus1=1 --NumTileRowsMinus1=1 --LFCrossTileBoundaryFlag=0 -q 27"
+ "s_wavefront_240p   encoder_randomaccess_main.cfg         416  240  9  8  420 28 --WaveFrontSynchro=1 -q 27"
  "s_wpp_240p         encoder_lowdelay_P_main.cfg           416  240  9  8  420 23 --WeightedPredP=1 -q 30"
  "s_wpb_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 24 --WeightedPredB=1 --WeightedPredP=1 -q 30"
  "c2_ra8_1080p       encoder_randomaccess_main.cfg         1920 1080 64 8  420 2"
