@@ -18,7 +18,8 @@
 //   * the CTA is warp-specialised and double-buffered: warps 1-3 ("stagers") do everything that touches global
 //     memory for CTU n+1 while warp 0 ("chain") predicts CTU n — the CTU's current samples plus the row above
 //     (x = -1 .. CTU+31, after waiting for the row above) and the column to the left, the residuals of its TUs
-//     (16-byte cp.async copies all in flight together), the records — then write CTU n back and publish the progress;
+//     and its decoded TUs / address tables (TMA bulk copies for the contiguous spans, 16-byte cp.async for the tile
+//     rows, all in flight together) — then write CTU n back and publish the progress;
 //     hand-over through named barriers (bar.arrive / bar.sync), never a full __syncthreads;
 //   * a pre-pass kernel (intra_prep_kernel, fully parallel over the picture) turns the records into reference-address
 //     tables — for every TU, entry i = shared-memory position of reference sample i AFTER HM's substitution of
@@ -52,6 +53,29 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// ---- TMA bulk copies (cp.async.bulk, the 1-D mode of the tensor memory accelerator) for the contiguous spans a CTU needs:
+// decoded micro-ops, reference-address tables, residuals.  One thread arms an mbarrier with the byte count and issues the
+// copies; everybody who reads the data waits on the barrier's phase.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}\n"
+               :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // first column >= from whose CTU has intra records of this component (warp-convergent), n if none
 __device__ __forceinline__ int next_intra_ctu(const uint16_t* cnt, int from, int n, int lane)
@@ -426,6 +450,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   __shared__ uint16_t s_count[IN_MAXCOLS];
   __shared__ uint4 s_prep[IN_MAXCOLS];    // per CTU of this row: x = first residual, y = residual span, z = table entries
   __shared__ int16_t s_col[IN_MAXCT];     // right-most column of the CTU the chain just finished (left neighbours of the next one)
+  __shared__ __align__(8) unsigned long long s_mbar[2];   // one per buffer: completion of the TMA bulk copies
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int comp = blockIdx.x / P.ctus_h, row = blockIdx.x % P.ctus_h;
   if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) return;
@@ -454,7 +479,12 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
     s_count[c] = (uint16_t)min(rg.count[comp], (uint32_t)IN_MAXREC);
     s_prep[c] = P.intra_prep[(size_t)comp * ctusW * P.ctus_h + (size_t)row * ctusW + c];
   }
-  if (tid == 0) { s_tileB[0] = s_tileB[TILE_PAD] = (int16_t)(1 << (bd - 1)); }
+  if (tid == 0)
+  {
+    s_tileB[0] = s_tileB[TILE_PAD] = (int16_t)(1 << (bd - 1));
+    mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1);
+    fence_proxy_async();                                       // the barriers exist before the async proxy touches them
+  }
   __syncthreads();
 
   const int c0 = next_intra_ctu(s_count, 0, ctusW, lane);
@@ -475,6 +505,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
       const int count = s_count[c];
       const int ox = c * CTW;
       bar_sync(BAR_FULL + b, IN_THREADS);                    // staged: tile, decoded TUs, tables, residuals
+      mbar_wait(&s_mbar[b], (n >> 1) & 1);                   // (already complete: makes the bulk-copied bytes visible to this warp)
       if (prev == c - 1)                                     // left neighbours = what this warp produced a moment ago
         for (int y = lane; y < ch; y += 32) tile[TIDX(y, -1)] = s_col[y];
       IntraOp op = ops[0];
@@ -541,16 +572,18 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
         cp_async8(&tile[TIDX(y, 4 * v)], plane + (size_t)(oy + y) * pitch + ox + 4 * v);
       }
     }
+    if (st == 0)
     {
+      // contiguous spans by TMA bulk copy: decoded TUs, reference-address tables, the CTU's residual span
       const uint4 prep = s_prep[c];
-      const uint4* gops = P.intra_ops + first;                                   // decoded TUs
-      for (int i = st; i < count; i += IN_STAGERS) cp_async16(ops + i, gops + i);
-      const uint16_t* gtab = P.intra_tab + ((size_t)comp * ctusW * P.ctus_h + (size_t)row * ctusW + c) * IN_ADDR;
-      const int tabVec = ((int)prep.z + 7) >> 3;                                 // reference-address tables, 8 entries per copy
-      for (int i = st; i < tabVec; i += IN_STAGERS) cp_async16(addrTab + 8 * i, gtab + 8 * i);
-      const int resVec = (int)(min(prep.y, (unsigned)resSamples) >> 3);          // the CTU's residual span (a multiple of 16 samples)
-      const int16_t* gres = P.resid + prep.x;
-      for (int i = st; i < resVec; i += IN_STAGERS) cp_async16(resB + 8 * i, gres + 8 * i);
+      const unsigned opsBytes = 16u * count;
+      const unsigned tabBytes = 16u * (((unsigned)prep.z + 7) >> 3);
+      const unsigned resBytes = 16u * (min(prep.y, (unsigned)resSamples) >> 3);
+      fence_proxy_async();                                   // earlier generic-proxy reads of this buffer are ordered before the async writes
+      mbar_expect_tx(&s_mbar[b], opsBytes + tabBytes + resBytes);
+      bulk_copy_g2s(ops, P.intra_ops + first, opsBytes, &s_mbar[b]);
+      if (tabBytes) bulk_copy_g2s(addrTab, P.intra_tab + ((size_t)comp * ctusW * P.ctus_h + (size_t)row * ctusW + c) * IN_ADDR, tabBytes, &s_mbar[b]);
+      if (resBytes) bulk_copy_g2s(resB, P.resid + prep.x, resBytes, &s_mbar[b]);
     }
     if (ox > 0 && prev != c - 1)                             // left CTU has no intra blocks: its samples have been final since the kernel started
       for (int y = st; y < ch; y += IN_STAGERS) tile[TIDX(y, -1)] = __ldcg(plane + (size_t)(oy + y) * pitch + ox - 1);
@@ -571,6 +604,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
       }
     }
     cp_async_wait_all();
+    mbar_wait(&s_mbar[b], (n >> 1) & 1);
     __threadfence_block();
     bar_arrive(BAR_FULL + b, IN_THREADS);
 
