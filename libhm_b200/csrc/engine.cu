@@ -47,6 +47,7 @@ struct hmr_engine
   bool slotAlloc[HMR_MAX_SLOTS];
   PlaneSet work;
   bool workAlloc;
+  PlaneSet lastWork;           // where the last picture's pre-SAO state lives (the work picture, or its DPB slot when it had no SAO)
   // staging ring
   struct Stage { uint8_t* host; uint8_t* dev; size_t cap; cudaEvent_t done; bool inflight; } ring[RING];
   int ringPos;
@@ -240,6 +241,7 @@ static int ensure_geometry(hmr_engine* e, const hmr_frame_hdr& h)
     int r = alloc_planes(e, e->work);
     if (r) return r;
     e->workAlloc = true;
+    e->lastWork = e->work;
     e->haveGeom = true;
   }
   return HMR_OK;
@@ -261,8 +263,10 @@ static void fill_params(hmr_engine* e, FrameParams& P, const hmr_frame_hdr& h, c
   for (int c = 0; c < 3; c++) { P.w[c] = e->w[c]; P.h[c] = e->h[c]; }
   P.csx = e->csx; P.csy = e->csy; P.ctus_w = e->ctusW; P.ctus_h = e->ctusH;
   P.w4 = (h.width + 3) >> 2; P.h4 = (h.height + 3) >> 2; P.w8 = (h.width + 7) >> 3;
-  P.work = e->work;
   P.out = e->slots[h.out_slot];
+  // No SAO anywhere in the picture: nothing ever needs the un-offset neighbours, so the picture is reconstructed and
+  // deblocked IN PLACE in its DPB slot and the SAO pass (which would be a 2 x S_b copy) disappears.
+  P.work = (h.flags & HMR_FRM_SAO) ? e->work : P.out;
   for (int s = 0; s < HMR_MAX_SLOTS; s++) P.dpb[s] = e->slotAlloc[s] ? e->slots[s] : e->slots[h.out_slot];
   P.tu = (const hmr_tu*)(dev + L.tu.off);
   P.coef = (const int16_t*)(dev + L.coef.off);
@@ -350,7 +354,8 @@ static int run_frame(hmr_engine* e, FrameParams& P, FrameEvents* fe)
   mark(HMR_T_DEBLOCK_H);
   if ((m & HMR_STAGE_DEBLOCK_H) && (h.flags & HMR_FRM_DEBLOCK)) { launch_deblock(P, 1, e->stream); launches++; }
   mark(HMR_T_SAO);
-  if (m & HMR_STAGE_SAO) { launch_sao(P, e->stream); launches++; }
+  if ((m & HMR_STAGE_SAO) && (h.flags & HMR_FRM_SAO)) { launch_sao(P, e->stream); launches++; }
+  e->lastWork = P.work;
   mark(HMR_T_COUNT);
   CK(cudaGetLastError());
   e->epoch++;
@@ -519,7 +524,7 @@ int hmr_read_plane_async(hmr_engine* e, int slot, int comp, int16_t* dst, size_t
 int hmr_read_work_plane(hmr_engine* e, int comp, int16_t* dst, size_t dst_stride)
 {
   if (!e || !e->workAlloc) return fail(e, HMR_ERR_ARG, "read_work_plane: no picture yet");
-  return read_planeset(e, e->work, comp, dst, dst_stride, false);
+  return read_planeset(e, e->lastWork, comp, dst, dst_stride, false);
 }
 
 int hmr_write_plane(hmr_engine* e, int slot, int comp, const int16_t* src, size_t src_stride, int width, int height)
