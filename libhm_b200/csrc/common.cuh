@@ -47,7 +47,7 @@ struct FrameParams
 __device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(hi, max(lo, v)); }
 
 // launchers (one per kernel file)
-void launch_mc(const FrameParams& P, cudaStream_t s);
+int  launch_mc(const FrameParams& P, cudaStream_t s);                 // returns number of launches
 int  launch_resid(const FrameParams& P, cudaStream_t s);             // returns number of launches
 cudaError_t launch_intra(const FrameParams& P, cudaStream_t s);
 void launch_deblock(const FrameParams& P, int dir, cudaStream_t s);

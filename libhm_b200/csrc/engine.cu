@@ -344,7 +344,7 @@ static int run_frame(hmr_engine* e, FrameParams& P, FrameEvents* fe)
   const int m = e->stageMask;
   uint32_t launches = 0;
   mark(HMR_T_MC);
-  if ((m & HMR_STAGE_MC) && h.n_mc_tiles) { launch_mc(P, e->stream); launches += 2; }
+  if ((m & HMR_STAGE_MC) && h.n_mc_tiles) launches += launch_mc(P, e->stream);
   mark(HMR_T_RESID);
   if ((m & HMR_STAGE_RESID) && h.n_tu) launches += launch_resid(P, e->stream);
   mark(HMR_T_INTRA);

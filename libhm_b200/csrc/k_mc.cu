@@ -293,6 +293,10 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
   }
 }
 
+// LUMA = true: the luma tile; false: the two co-located chroma tiles.  Two launches instead of one kernel doing all three
+// components: each then needs half the shared memory per warp, which doubles the warps in flight per SM — and what this
+// kernel waits for is memory latency (ncu: issue slots idle on cp.async completion), not arithmetic.
+template <bool LUMA>
 __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant__ FrameParams P, const int warpBytes, const int chromaRows)
 {
   extern __shared__ __align__(16) uint8_t s_mc[];
@@ -301,20 +305,17 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
   if (tile >= P.hdr.n_mc_tiles) return;
   uint8_t* base = s_mc + (size_t)warp * warpBytes;
   uint32_t* tmp = (uint32_t*)base;                                        // 12 row pairs x 16 words
-  int16_t* lumaWin = (int16_t*)(base + 12 * MC_TMPW * 4);                 // 2 lists x 24 rows
-  int16_t* chromaWin = lumaWin + 2 * 24 * MC_PITCH;                       // 2 planes x 2 lists x chromaRows
+  int16_t* win = (int16_t*)(base + 12 * MC_TMPW * 4);                     // luma: 2 lists x 24 rows; chroma: 2 planes x 2 lists x chromaRows
 
   const uint4 raw = __ldg((const uint4*)(P.mc_tiles + tile));
   const hmr_pu t = *(const hmr_pu*)&raw;
-  const bool chroma = P.hdr.chroma_format != HMR_CHROMA_400;
   int16_t* sref[3][2];
   int offs[3][2];
 
-  // ---- stage all windows: luma first (own commit group), then chroma ----
+  // ---- stage all windows of this launch's component(s), all copies in flight together ----
 #pragma unroll
-  for (int comp = 0; comp < 3; comp++)
+  for (int comp = LUMA ? 0 : 1; comp < (LUMA ? 1 : 3); comp++)
   {
-    if (comp > 0 && !chroma) continue;
     const int cx = comp ? P.csx : 0, cy = comp ? P.csy : 0;
     const int nt = comp ? 4 : 8, half = nt / 2 - 1;
     const int tw = 16 >> cx, th = 16 >> cy;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
 #pragma unroll
     for (int list = 0; list < 2; list++)
     {
-      int16_t* s = comp == 0 ? lumaWin + list * 24 * MC_PITCH : chromaWin + ((comp - 1) * 2 + list) * chromaRows * MC_PITCH;
+      int16_t* s = comp == 0 ? win + list * 24 * MC_PITCH : win + ((comp - 1) * 2 + list) * chromaRows * MC_PITCH;
       sref[comp][list] = s;
       offs[comp][list] = 0;
       if (!(t.lists & (1 << list))) continue;
@@ -335,25 +336,30 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
       const int wrows = whole ? th : rows, wcols = whole ? tw : cols;
       mc_stage(s, P.dpb[slot].p[comp], P.dpb[slot].pitch[comp], P.w[comp], P.h[comp], ix, iy, xa, wrows, wcols, (off + wcols + 7) >> 3, lane);
     }
-    if (comp == 0 || comp == 2) mc_cp_async_commit();
   }
-  if (chroma) mc_cp_async_wait<1>(); else mc_cp_async_wait<0>();
-  __syncwarp();
-  const int refIdx = P.wp ? (int)P.mc_tile_refidx[tile] : 0;
-  mc_component<8>(P, t, 0, 0, 0, sref[0], offs[0], tmp, lane, refIdx);
-  if (!chroma) return;
+  mc_cp_async_commit();
   mc_cp_async_wait<0>();
   __syncwarp();
-  mc_component<4>(P, t, 1, P.csx, P.csy, sref[1], offs[1], tmp, lane, refIdx);
-  mc_component<4>(P, t, 2, P.csx, P.csy, sref[2], offs[2], tmp, lane, refIdx);
+  const int refIdx = P.wp ? (int)P.mc_tile_refidx[tile] : 0;
+  if (LUMA) mc_component<8>(P, t, 0, 0, 0, sref[0], offs[0], tmp, lane, refIdx);
+  else
+  {
+    mc_component<4>(P, t, 1, P.csx, P.csy, sref[1], offs[1], tmp, lane, refIdx);
+    mc_component<4>(P, t, 2, P.csx, P.csy, sref[2], offs[2], tmp, lane, refIdx);
+  }
 }
 
-void launch_mc(const FrameParams& P, cudaStream_t s)
+int launch_mc(const FrameParams& P, cudaStream_t s)
 {
-  if (P.hdr.n_mc_tiles == 0) return;
+  if (P.hdr.n_mc_tiles == 0) return 0;
   upload_taps();
   mc_expand_kernel<<<(P.hdr.n_pu * 16 + 255) / 256, 256, 0, s>>>(P);
   const int chromaRows = ((16 >> P.csy) + 4) & ~1;
-  const int warpBytes = 12 * MC_TMPW * 4 + 2 * 24 * MC_PITCH * 2 + 4 * chromaRows * MC_PITCH * 2;
-  mc_kernel<<<(P.hdr.n_mc_tiles + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, MC_WARPS * warpBytes, s>>>(P, warpBytes, chromaRows);
+  const int grid = (P.hdr.n_mc_tiles + MC_WARPS - 1) / MC_WARPS;
+  const int lumaBytes = 12 * MC_TMPW * 4 + 2 * 24 * MC_PITCH * 2;
+  mc_kernel<true><<<grid, MC_WARPS * 32, MC_WARPS * lumaBytes, s>>>(P, lumaBytes, chromaRows);
+  if (P.hdr.chroma_format == HMR_CHROMA_400) return 2;
+  const int chromaBytes = 12 * MC_TMPW * 4 + 4 * chromaRows * MC_PITCH * 2;
+  mc_kernel<false><<<grid, MC_WARPS * 32, MC_WARPS * chromaBytes, s>>>(P, chromaBytes, chromaRows);
+  return 3;
 }
