@@ -34,6 +34,7 @@
 #include "TLibCommon/TComRom.h"
 
 #include "hm_emit.h"
+#include "hm_fast.h"
 #include <chrono>
 static inline double nowSec() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -164,7 +165,10 @@ void HmEmitter::onCtuParsed(TComDataCU* ctu)
   TComPic* pic = ctu->getPic();
   if (!m_open || pic != m_curPic) beginFrame(pic, ctu);
   for (int c = 0; c < 3; c++) m_intraTmp[c].clear();
+  static const bool prefetch = getenv("HMDEC_B200_NO_PREFETCH") == NULL;
+  if (prefetch) hm_fast_prefetch_begin(pic, ctu->getAddr() + 2);   // the parser is about to init + parse CTU addr+1
   walkCU(ctu, 0, 0);
+  hm_fast_prefetch_step(1 << 20);                                  // whatever the walk did not get to
   hmr_ctu_intra_range& r = m_range[ctu->getAddr()];
   for (int c = 0; c < 3; c++)
   {
@@ -204,6 +208,7 @@ void HmEmitter::walkCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth)
     return;
   }
 
+  hm_fast_prefetch_step(8);
   const int cuSize = g_uiMaxCUWidth >> depth;
   switch (ctu->getPredictionMode(absPartIdx))
   {

@@ -16,4 +16,6 @@ void hm_fast_release_decoder(TDecTop* dec);
 // Motion-field compression of a picture nobody will reference, postponed until somebody asks for its motion data.
 void hm_fast_defer_motion_compression(TComPic* pic);
 void hm_fast_ensure_motion_compressed(TComPic* pic);
+void hm_fast_prefetch_begin(TComPic* pic, unsigned ctuAddr);   // warm the per-partition arrays of a CTU ahead of initCU:
+void hm_fast_prefetch_step(int nLines);                        // ... a few cache lines at a time
 #endif

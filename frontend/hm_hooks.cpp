@@ -140,9 +140,9 @@ Void TDecGop::filterPicture(TComPic*& rpcPic)
     e->sink()->hmStage(2, rpcPic);
   }
 
-  // TMVP storage (TDecGop.cpp:176): only a picture that can be referenced needs it now (hm_fast.cpp)
-  if (slice->isReferenced() || e->sink()->wantHmRecon()) rpcPic->compressMotion();
-  else hm_fast_defer_motion_compression(rpcPic);
+  // TMVP storage (TDecGop.cpp:176): never rewritten — xGetColMVP reads the uncompressed field at the 16x16 run start
+  // (hm_fast_memset.h: hm_fast_col_part); only libHMDEC_get_internal_info compresses, on demand
+  hm_fast_defer_motion_compression(rpcPic);
   static const bool quiet = getenv("HMDEC_B200_QUIET") != NULL;   // the hash is still verified
   printStatusAndHash(rpcPic, slice, m_decodedPictureHashSEIEnabled, e, quiet);
   e->sink()->drainHashes(false);

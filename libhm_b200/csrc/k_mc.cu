@@ -87,10 +87,11 @@ __device__ __forceinline__ void mc_stage(int16_t* s, const int16_t* __restrict__
   const bool inside = iy >= 0 && iy + rows <= Hc && ix >= 0 && ix + cols <= Wc && xa + 32 <= rpitch;
   if (inside)
   {
-    // always 4 x 16 bytes per row (the row pitch of the window holds them): 8 rows per round, pointers only advance
+    // up to 4 x 16 bytes per row (only the vectors the window touches): 8 rows per round, pointers only advance
     const int16_t* g = ref + (size_t)(iy + (lane >> 2)) * rpitch + xa + 8 * (lane & 3);
     int16_t* d = s + (lane >> 2) * MC_PITCH + 8 * (lane & 3);
-    for (int r = lane >> 2; r < rows; r += 8, g += 8 * (size_t)rpitch, d += 8 * MC_PITCH) mc_cp_async16(d, g);
+    if ((lane & 3) < nvec)
+      for (int r = lane >> 2; r < rows; r += 8, g += 8 * (size_t)rpitch, d += 8 * MC_PITCH) mc_cp_async16(d, g);
   }
   else
   {

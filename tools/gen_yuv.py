@@ -2,7 +2,7 @@
 """Seeded synthetic planar YUV generator (SURVEY.md §8d recipe).
 
 Content = 4 octaves of value noise (cells 64/16/4/1 px, weights .45/.30/.15/.10) scaled to the
-legal video range, panned (+3,+2) px/frame, plus fresh N(0,3) noise per frame and six inverted
+legal video range, panned (+3,+2) px/frame (--pan: other, also fractional, velocities), plus fresh N(0,3) noise per frame and six inverted
 160x160 squares moving at distinct velocities.  That forces intra blocks, bi-prediction, all TU
 sizes and non-zero motion vectors; smooth gradients compress to nothing and exercise nothing.
 
@@ -38,10 +38,10 @@ def make_field(rng, h, w):
     return f
 
 
-def generate(path, width, height, frames, bitdepth, seed, chroma="420"):
+def generate(path, width, height, frames, bitdepth, seed, chroma="420", pan=(3.0, 2.0)):
     rng = np.random.default_rng(seed)
     # canvas big enough for the pan
-    ch, cw = height + 2 * frames + 8, width + 3 * frames + 8
+    ch, cw = height + int(np.ceil(pan[1] * frames)) + 8, width + int(np.ceil(pan[0] * frames)) + 8
     luma = make_field(rng, ch, cw)
     cb = make_field(rng, ch, cw)
     cr = make_field(rng, ch, cw)
@@ -55,10 +55,15 @@ def generate(path, width, height, frames, bitdepth, seed, chroma="420"):
     dt = np.uint8 if bitdepth <= 8 else np.dtype("<u2")
     with open(path, "wb") as fh:
         for t in range(frames):
-            oy, ox = 2 * t, 3 * t
+            oy, ox = int(pan[1] * t), int(pan[0] * t)
+            fy, fx = np.float32(pan[1] * t - oy), np.float32(pan[0] * t - ox)
             planes = []
             for k, fld in enumerate((luma, cb, cr)):
-                p = fld[oy:oy + height, ox:ox + width] * (hi - lo) + lo
+                p = fld[oy:oy + height, ox:ox + width]
+                if fx or fy:   # sub-sample pan: bilinear resample of the canvas (forces fractional motion vectors)
+                    q = fld[oy:oy + height + 1, ox:ox + width + 1]
+                    p = (q[:-1, :-1] * (1 - fx) + q[:-1, 1:] * fx) * (1 - fy) + (q[1:, :-1] * (1 - fx) + q[1:, 1:] * fx) * fy
+                p = p * (hi - lo) + lo
                 p = p + rng.normal(0.0, 3.0 * scale / 4 if k else 3.0 * scale / 2, p.shape).astype(np.float32)
                 for (qx, qy, vx, vy) in sq:
                     x = int((qx + vx * t) % max(1, width - 160))
@@ -81,5 +86,6 @@ if __name__ == "__main__":
     ap.add_argument("--bitdepth", type=int, default=8)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--chroma", default="420")
+    ap.add_argument("--pan", default="3,2", help="pan in samples per frame (x,y); fractional values resample the canvas")
     a = ap.parse_args()
-    generate(a.out, a.width, a.height, a.frames, a.bitdepth, a.seed, a.chroma)
+    generate(a.out, a.width, a.height, a.frames, a.bitdepth, a.seed, a.chroma, tuple(float(v) for v in a.pan.split(",")))

@@ -29,6 +29,7 @@ JOBS=(
  "s_lossless_240p    encoder_randomaccess_main.cfg         208  120  5  8  420 22 --TransquantBypassEnableFlag=1 --CUTransquantBypassFlagForce=1 -q 30"
  "s_tiles_240p       encoder_randomaccess_main.cfg         640  256  9  8  420 27 --TileUniformSpacing=1 --NumTileColumnsMinus1=1 --NumTileRowsMinus1=1 --LFCrossTileBoundaryFlag=0 -q 27"
  "s_wavefront_240p   encoder_randomaccess_main.cfg         416  240  9  8  420 28 --WaveFrontSynchro=1 -q 27"
+ "s_cip_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 29 --ConstrainedIntraPred=1 -q 30"
  "s_wpp_240p         encoder_lowdelay_P_main.cfg           416  240  9  8  420 23 --WeightedPredP=1 -q 30"
  "s_wpb_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 24 --WeightedPredB=1 --WeightedPredP=1 -q 30"
  "c2_ra8_1080p       encoder_randomaccess_main.cfg         1920 1080 64 8  420 2"
@@ -43,6 +44,8 @@ JOBS=(
  "c5_ld10_2160p_s56  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 56"
  "c5_ld10_2160p_s57  encoder_lowdelay_main10.cfg           3840 2160 17 10 420 57"
  "m_ra10_1080p       encoder_randomaccess_main10.cfg       1920 1080 17 10 420 5"
+ "f_ra10_1080p       encoder_randomaccess_main10.cfg       1920 1080 17 10 420 6"
+ "f_ra10_2160p       encoder_randomaccess_main10.cfg       3840 2160 33 10 420 7"
 )
 WANT=$1
 if [ "$1" == "--list" ]; then for j in "${JOBS[@]}"; do echo "$j" | awk '{print $1}'; done; exit 0; fi
@@ -55,6 +58,7 @@ for j in "${JOBS[@]}"; do
   yuv=$TMP_YUV/$name.yuv
   if [ "$name" == "s_wpp_240p" ] || [ "$name" == "s_wpb_240p" ]; then python "$ROOT/tools/gen_fade_yuv.py" "$yuv" --width $W --height $H --frames $F --seed $SEED   # fade: non-trivial WP weights
   elif [ "$name" == "s_pcm_240p" ]; then python "$ROOT/tools/gen_pcm_yuv.py" "$yuv" --width $W --height $H --frames $F --seed $SEED   # noise: makes the encoder choose I_PCM
+  elif [ "${name:0:2}" == "f_" ]; then python "$ROOT/tools/gen_yuv.py" "$yuv" --width $W --height $H --frames $F --bitdepth $BD --seed $SEED --chroma $CH --pan 2.75,1.25   # quarter-sample pan: fractional motion vectors
   else python "$ROOT/tools/gen_yuv.py" "$yuv" --width $W --height $H --frames $F --bitdepth $BD --seed $SEED --chroma $CH; fi
   CF=""; [ "$CH" != "420" ] && CF="--InputChromaFormat=$CH"
   "$ENC" -c "$REF/cfg/$cfg" -i "$yuv" -wdt $W -hgt $H -f $F -fr 30 --InputBitDepth=$BD $CF \

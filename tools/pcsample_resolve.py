@@ -19,7 +19,7 @@ def load(path):
         if len(p)==3 and p[1] in 'TtWw':
             arr.append((int(p[0],16),p[2]))
     arr.sort(); syms[path]=(arr,[a for a,_ in arr]); return syms[path]
-cnt=collections.Counter(); mod=collections.Counter()
+cnt=collections.Counter(); mod=collections.Counter(); raw=collections.Counter()
 for pc in samples:
     for a,b,off,path in maps:
         if a<=pc<b:
@@ -29,8 +29,11 @@ for pc in samples:
             i=bisect.bisect_right(keys,va)-1
             name=arr[i][1] if i>=0 else '?'
             cnt[(path.split('/')[-1],name)]+=1; mod[path.split('/')[-1]]+=1
+            if 'libc.so' in path: raw[va & ~0x3f]+=1
             break
     else: cnt[('?','?')]+=1
 tot=len(samples); print('samples',tot)
 for m,c in mod.most_common(8): print(f'  module {m}: {100*c/tot:.1f}%')
 for (m,nm),c in cnt.most_common(int(sys.argv[2]) if len(sys.argv)>2 else 45): print(f'{100*c/tot:5.1f}% {c:6d} {m[:22]:22s} {nm[:100]}')
+
+print('libc hot 64-byte blocks (file vaddr):', ' '.join(f'{a:#x}:{c}' for a,c in raw.most_common(12)))
