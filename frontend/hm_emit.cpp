@@ -166,9 +166,9 @@ void HmEmitter::onCtuParsed(TComDataCU* ctu)
   if (!m_open || pic != m_curPic) beginFrame(pic, ctu);
   for (int c = 0; c < 3; c++) m_intraTmp[c].clear();
   static const bool prefetch = getenv("HMDEC_B200_NO_PREFETCH") == NULL;
-  if (prefetch) hm_fast_prefetch_begin(pic, ctu->getAddr() + 2);   // the parser is about to init + parse CTU addr+1
+  if (prefetch) hm_fast_prefetch_begin(m_prefetch, pic, ctu->getAddr() + 2);   // the parser is about to init + parse CTU addr+1
   walkCU(ctu, 0, 0);
-  hm_fast_prefetch_step(1 << 20);                                  // whatever the walk did not get to
+  m_prefetch.step(1 << 20);                                        // whatever the walk did not get to
   hmr_ctu_intra_range& r = m_range[ctu->getAddr()];
   for (int c = 0; c < 3; c++)
   {
@@ -208,7 +208,7 @@ void HmEmitter::walkCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth)
     return;
   }
 
-  hm_fast_prefetch_step(8);
+  m_prefetch.step(8);
   const int cuSize = g_uiMaxCUWidth >> depth;
   switch (ctu->getPredictionMode(absPartIdx))
   {

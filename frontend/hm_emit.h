@@ -51,6 +51,8 @@ struct HmFrameSink
   virtual void releaseHostBuffers() {}
 };
 
+#include "hm_fast.h"
+
 class HmEmitter
 {
 public:
@@ -63,6 +65,7 @@ public:
   int  slotOf(TComPic* pic);
   const char* unsupported() const { return m_unsupported; }
   bool cleanCoeffs() const { return m_cleanCoeffs; }
+  HmPrefetchCursor m_prefetch;                                            // CTU metadata prefetch (hm_fast.h)
 
 private:
   struct CuCtx;

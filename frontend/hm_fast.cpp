@@ -370,47 +370,32 @@ Void TDecTop::xGetNewPicBuffer(TComSlice* pcSlice, TComPic*& rpcPic)
 // The sampling profile shows the parser thread stalled on exactly those stores (memset + initCU + clearMvField ≈ 17 %).
 // While the emitter walks CTU n it therefore asks for the lines of CTU n+2, a few per coding unit so that the
 // requests trickle out between real work instead of queueing behind the core's dozen line-fill buffers.
-namespace {
-struct PrefetchCursor { const char* base[48]; unsigned lines[48]; int count, cur; unsigned line; };
-thread_local PrefetchCursor t_pf = { {0}, {0}, 0, 0, 0 };
-inline void pfAdd(const void* p, size_t bytes)
+static inline void pfAdd(HmPrefetchCursor& c, const void* p, size_t bytes)
 {
-  if (!p || t_pf.count >= 48) return;
-  t_pf.base[t_pf.count] = (const char*)p; t_pf.lines[t_pf.count] = (unsigned)((bytes + 63) >> 6); t_pf.count++;
-}
+  if (!p || c.count >= 48) return;
+  c.base[c.count] = (const char*)p; c.lines[c.count] = (unsigned)((bytes + 63) >> 6); c.count++;
 }
 
-void hm_fast_prefetch_begin(TComPic* pic, unsigned ctuAddr)
+void hm_fast_prefetch_begin(HmPrefetchCursor& pf, TComPic* pic, unsigned ctuAddr)
 {
-  t_pf.count = t_pf.cur = 0; t_pf.line = 0;
+  pf.count = pf.cur = 0; pf.line = 0;
   if (ctuAddr >= pic->getNumCUsInFrame()) return;
   TComDataCU* cu = pic->getCU(ctuAddr);
   const size_t n = cu->m_uiNumPartition;
-  pfAdd(cu->m_puhDepth, n);            pfAdd(cu->m_pePartSize, n);     pfAdd(cu->m_skipFlag, n);      pfAdd(cu->m_pePredMode, n);
-  pfAdd(cu->m_CUTransquantBypass, n);  pfAdd(cu->m_puhWidth, n);       pfAdd(cu->m_puhHeight, n);     pfAdd(cu->m_phQP, n);
-  pfAdd(cu->m_ChromaQpAdj, n);         pfAdd(cu->m_puhTrIdx, n);       pfAdd(cu->m_pbMergeFlag, n);   pfAdd(cu->m_puhMergeIndex, n);
-  pfAdd(cu->m_puhInterDir, n);         pfAdd(cu->m_pbIPCMFlag, n);
+  pfAdd(pf, cu->m_puhDepth, n);            pfAdd(pf, cu->m_pePartSize, n);     pfAdd(pf, cu->m_skipFlag, n);      pfAdd(pf, cu->m_pePredMode, n);
+  pfAdd(pf, cu->m_CUTransquantBypass, n);  pfAdd(pf, cu->m_puhWidth, n);       pfAdd(pf, cu->m_puhHeight, n);     pfAdd(pf, cu->m_phQP, n);
+  pfAdd(pf, cu->m_ChromaQpAdj, n);         pfAdd(pf, cu->m_puhTrIdx, n);       pfAdd(pf, cu->m_pbMergeFlag, n);   pfAdd(pf, cu->m_puhMergeIndex, n);
+  pfAdd(pf, cu->m_puhInterDir, n);         pfAdd(pf, cu->m_pbIPCMFlag, n);
   for (int c = 0; c < MAX_NUM_COMPONENT; c++)
   {
-    pfAdd(cu->m_crossComponentPredictionAlpha[c], n); pfAdd(cu->m_puhTransformSkip[c], n);
-    pfAdd(cu->m_explicitRdpcmMode[c], n);             pfAdd(cu->m_puhCbf[c], n);
+    pfAdd(pf, cu->m_crossComponentPredictionAlpha[c], n); pfAdd(pf, cu->m_puhTransformSkip[c], n);
+    pfAdd(pf, cu->m_explicitRdpcmMode[c], n);             pfAdd(pf, cu->m_puhCbf[c], n);
   }
-  for (int c = 0; c < MAX_NUM_CHANNEL_TYPE; c++) pfAdd(cu->m_puhIntraDir[c], n);
+  for (int c = 0; c < MAX_NUM_CHANNEL_TYPE; c++) pfAdd(pf, cu->m_puhIntraDir[c], n);
   for (int l = 0; l < NUM_REF_PIC_LIST_01; l++)
   {
-    pfAdd(cu->m_apiMVPIdx[l], n); pfAdd(cu->m_apiMVPNum[l], n);
+    pfAdd(pf, cu->m_apiMVPIdx[l], n); pfAdd(pf, cu->m_apiMVPNum[l], n);
     TComCUMvField& f = cu->m_acCUMvField[l];
-    pfAdd(f.m_pcMv, n * sizeof(TComMv)); pfAdd(f.m_pcMvd, n * sizeof(TComMv)); pfAdd(f.m_piRefIdx, n);
-  }
-}
-
-void hm_fast_prefetch_step(int nLines)
-{
-  PrefetchCursor& c = t_pf;
-  while (nLines > 0 && c.cur < c.count)
-  {
-    __builtin_prefetch(c.base[c.cur] + ((size_t)c.line << 6), 1, 2);
-    nLines--;
-    if (++c.line >= c.lines[c.cur]) { c.cur++; c.line = 0; }
+    pfAdd(pf, f.m_pcMv, n * sizeof(TComMv)); pfAdd(pf, f.m_pcMvd, n * sizeof(TComMv)); pfAdd(pf, f.m_piRefIdx, n);
   }
 }

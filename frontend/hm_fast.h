@@ -16,6 +16,20 @@ void hm_fast_release_decoder(TDecTop* dec);
 // Motion-field compression of a picture nobody will reference, postponed until somebody asks for its motion data.
 void hm_fast_defer_motion_compression(TComPic* pic);
 void hm_fast_ensure_motion_compressed(TComPic* pic);
-void hm_fast_prefetch_begin(TComPic* pic, unsigned ctuAddr);   // warm the per-partition arrays of a CTU ahead of initCU:
-void hm_fast_prefetch_step(int nLines);                        // ... a few cache lines at a time
+// warm the per-partition arrays of a CTU ahead of TComDataCU::initCU, a few cache lines at a time (hm_fast.cpp)
+struct HmPrefetchCursor
+{
+  const char* base[48]; unsigned lines[48]; int count, cur; unsigned line;
+  HmPrefetchCursor() : count(0), cur(0), line(0) {}
+  inline void step(int nLines)
+  {
+    while (nLines > 0 && cur < count)
+    {
+      __builtin_prefetch(base[cur] + ((unsigned long)line << 6), 1, 2);
+      nLines--;
+      if (++line >= lines[cur]) { cur++; line = 0; }
+    }
+  }
+};
+void hm_fast_prefetch_begin(HmPrefetchCursor& c, TComPic* pic, unsigned ctuAddr);
 #endif

@@ -38,7 +38,7 @@ def test_dropin_decoder_selfcheck_against_hm_cpu_recon():
 
 
 BENCH = os.path.join(ROOT, "bench_data")
-BENCH_STREAMS = ["c3_ra10_2160p", "c4_rext444_1080p", "c5_ld10_2160p_s50", "m_ra10_1080p"]
+BENCH_STREAMS = ["c3_ra10_2160p", "c4_rext444_1080p", "c5_ld10_2160p_s50", "m_ra10_1080p", "f_ra10_1080p"]
 
 
 @pytest.mark.parametrize("name", BENCH_STREAMS)

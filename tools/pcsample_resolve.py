@@ -1,11 +1,12 @@
 import sys,subprocess,bisect,collections
-maps=[];samples=[]
+maps=[];samples=[];tids=[]
 for l in open(sys.argv[1]):
     if l[0]=='M':
         p=l[2:].split()
         a,b=[int(x,16) for x in p[0].split('-')]; off=int(p[2],16); path=p[5] if len(p)>5 else ''
         maps.append((a,b,off,path))
-    else: samples.append(int(l[2:],16))
+    else:
+        q=l[2:].split(); samples.append(int(q[0],16)); tids.append(int(q[1]) if len(q)>1 else 0)
 syms={}
 def load(path):
     if path in syms: return syms[path]
@@ -20,7 +21,8 @@ def load(path):
             arr.append((int(p[0],16),p[2]))
     arr.sort(); syms[path]=(arr,[a for a,_ in arr]); return syms[path]
 cnt=collections.Counter(); mod=collections.Counter(); raw=collections.Counter()
-for pc in samples:
+bytid=collections.Counter(tids); polltid=collections.Counter()
+for pc,tid in zip(samples,tids):
     for a,b,off,path in maps:
         if a<=pc<b:
             arr,keys=load(path) if path.startswith('/') else ([],[])
@@ -30,6 +32,7 @@ for pc in samples:
             name=arr[i][1] if i>=0 else '?'
             cnt[(path.split('/')[-1],name)]+=1; mod[path.split('/')[-1]]+=1
             if 'libc.so' in path: raw[va & ~0x3f]+=1
+            if name.startswith('poll') or name.startswith('ioctl'): polltid[tid]+=1
             break
     else: cnt[('?','?')]+=1
 tot=len(samples); print('samples',tot)
@@ -37,3 +40,4 @@ for m,c in mod.most_common(8): print(f'  module {m}: {100*c/tot:.1f}%')
 for (m,nm),c in cnt.most_common(int(sys.argv[2]) if len(sys.argv)>2 else 45): print(f'{100*c/tot:5.1f}% {c:6d} {m[:22]:22s} {nm[:100]}')
 
 print('libc hot 64-byte blocks (file vaddr):', ' '.join(f'{a:#x}:{c}' for a,c in raw.most_common(12)))
+print('samples per thread:', dict(bytid.most_common(8)), ' poll/ioctl samples per thread:', dict(polltid.most_common(8)))
