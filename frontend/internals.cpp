@@ -110,7 +110,14 @@ void tuEntries(Out& out, TComDataCU* ctu, UInt part, UInt depth, UInt trDepth, l
       const TCoeff* co = ctu->getCoeff(c);
       const int perPart = 16 >> (ctu->getPic()->getComponentScaleX(c) + ctu->getPic()->getComponentScaleY(c));   // levels per 4x4 partition
       int64_t e = 0;
-      for (int i = 0; i < n; i++) if (ctu->getCbf((UInt)(i / perPart), c) != 0) e += (int64_t)(co[i] * co[i]);
+      // a partition's levels are defined iff its own leaf TU is coded: cbf bit at the leaf's transform depth (4:2:2 chroma:
+      // one level deeper, the two square halves of a TU carry separate flags)
+      const UInt deeper = (c != COMPONENT_Y && ctu->getPic()->getChromaFormat() == CHROMA_422) ? 1 : 0;
+      for (int i = 0; i < n; i++)
+      {
+        const UInt p = (UInt)(i / perPart);
+        if (ctu->getCbf(p, c, ctu->getTransformIdx(p) + deeper) != 0) e += (int64_t)(co[i] * co[i]);
+      }
       b.value = e > MAX_INT ? MAX_INT : (int)e;
       break;
     }

@@ -1,0 +1,88 @@
+"""libHMDEC_get_internal_info and the picture accessors of the drop-in against the REFERENCE wrapper itself
+(oracle/_ref/liblibHMDecoderStatic.so, built from /root/reference by oracle/Makefile.ref): the same dlopen-based caller
+(frontend/hmdec_internals.cpp) drives both libraries over the golden bitstreams and the two dumps must agree — POC order,
+geometry, strides, every visible sample (position-dependent checksum) and the complete block list of all 24 info types.
+
+Values the reference leaves uninitialised are not compared (they are stack garbage there, zero here):
+  * LIBHMDEC_TU_COEFF_ENERGY_CR: never computed (libHMDecoder.cpp:581 tests ENERGY_CB twice) — geometry only;
+  * LIBHMDEC_PU_REFERENCE_POC_1 / PU_MV_1: only set when interDir == 2 (libHMDecoder.cpp:534-540);
+  * LIBHMDEC_PU_MERGE_INDEX: only set when the merge flag is set (libHMDecoder.cpp:522-523)."""
+import os
+import subprocess
+import pytest
+from conftest import GOLDEN, STREAMS, ROOT
+
+TOOL = os.path.join(ROOT, "frontend", "_build", "hmdec_internals")
+OURS = os.path.join(ROOT, "frontend", "_build", "libHMDecoder_b200.so")
+REF = os.path.join(ROOT, "oracle", "_ref", "liblibHMDecoderStatic.so")
+T_MERGE_FLAG, T_MERGE_INDEX, T_INTER_DIR, T_REF1, T_MV1, T_ENERGY_CR = 8, 9, 10, 13, 14, 23
+
+
+def _dump(lib, stream, out, extra=(), env=None):
+    r = subprocess.run([TOOL, lib, stream, out, *extra], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-2000:])
+    pics, cur = [], None
+    for line in open(out):
+        f = line.split()
+        if f[0] == "PIC":
+            cur = {"head": line, "planes": [], "types": {}}
+            pics.append(cur)
+        elif f[0] == "plane":
+            cur["planes"].append(line)
+        elif f[0] == "type":
+            blocks = []
+            cur["types"][int(f[1])] = blocks
+        else:
+            blocks.append(tuple(int(v) for v in f))
+    return pics
+
+
+def _compare(ref, got, name):
+    assert len(ref) == len(got) and len(ref) > 0
+    for r, g in zip(ref, got):
+        assert r["head"] == g["head"], name
+        assert r["planes"] == g["planes"], (name, r["head"])
+        assert sorted(r["types"]) == sorted(g["types"]) == list(range(24))
+        for t in range(24):
+            a, b = r["types"][t], g["types"][t]
+            assert len(a) == len(b), (name, r["head"], t)
+            if t == T_ENERGY_CR:
+                a, b = [x[:4] for x in a], [x[:4] for x in b]
+            elif t in (T_REF1, T_MV1):
+                d = r["types"][T_INTER_DIR]
+                a = [x if d[i][4] == 2 else x[:4] for i, x in enumerate(a)]
+                b = [x if d[i][4] == 2 else x[:4] for i, x in enumerate(b)]
+            elif t == T_MERGE_INDEX:
+                # reported per CU in the reference (addValuesForCURecursively), flag taken from the same position
+                a, b = [x[:4] for x in a], [x[:4] for x in b]
+            assert a == b, (name, r["head"], "info type", t, next((x, y) for x, y in zip(a, b) if x != y))
+
+
+def _need():
+    if not (os.path.exists(TOOL) and os.path.exists(REF) and os.path.exists(OURS)):
+        pytest.skip("needs frontend/_build/hmdec_internals and oracle/_ref/liblibHMDecoderStatic.so (built where /root/reference exists)")
+
+
+@pytest.mark.parametrize("name", STREAMS)
+def test_host_side_reports_what_the_reference_reports(name, tmp_path):
+    """CPU: the drop-in with its record-dump back-end in the product's fast parse configuration (no reconstruction, so the
+    sample checksums are not compared here)."""
+    _need()
+    stream = os.path.join(GOLDEN, name + ".bin")
+    ref = _dump(REF, stream, str(tmp_path / "ref.txt"))
+    env = dict(os.environ, HMDUMP_RECORDS_ONLY="1", HMDEC_B200_QUIET="1")
+    got = _dump(OURS, stream, str(tmp_path / "ours.txt"), ("--backend", "1", "/dev/null"), env)
+    for r, g in zip(ref, got):
+        g["planes"] = r["planes"]
+    _compare(ref, got, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", STREAMS)
+def test_drop_in_on_the_gpu_reports_what_the_reference_reports(name, tmp_path):
+    """GPU: the product configuration — every visible sample and every internals block list equals the reference wrapper's."""
+    _need()
+    stream = os.path.join(GOLDEN, name + ".bin")
+    ref = _dump(REF, stream, str(tmp_path / "ref.txt"))
+    got = _dump(OURS, stream, str(tmp_path / "ours.txt"), env=dict(os.environ, HMDEC_B200_QUIET="1"))
+    _compare(ref, got, name)
