@@ -17,10 +17,12 @@
 
 #define RS_THREADS 128
 
-__constant__ int16_t c_T32[32][32];
+// 32-bit entries: an IMAD then takes the matrix element straight from the constant bank (c[bank][imm]); with int16 entries
+// every MAC paid a uniform load plus a sign-extending permute on top (3 instructions per MAC, 190 KB of code)
+__constant__ int c_T32[32][32];
 static const int16_t h_cosTab[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
                                       61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
-__constant__ int16_t c_dst4[4][4] = { {29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29} };
+__constant__ int c_dst4[4][4] = { {29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29} };
 __constant__ int c_invq[6] = { 40, 45, 51, 57, 64, 72 };
 static bool g_resid_tables_uploaded[64] = {false};
 
@@ -28,14 +30,14 @@ static bool g_resid_tables_uploaded[64] = {false};
 static void upload_tables(int device)
 {
   if (device < 64 && g_resid_tables_uploaded[device]) return;
-  static int16_t T[32][32];
+  static int T[32][32];
   for (int k = 0; k < 32; k++)
     for (int n = 0; n < 32; n++)
     {
       if (k == 0) { T[k][n] = 64; continue; }
       int m = ((2 * n + 1) * k) & 127;
       if (m > 64) m = 128 - m;
-      T[k][n] = (int16_t)(m > 32 ? -h_cosTab[64 - m] : h_cosTab[m]);
+      T[k][n] = m > 32 ? -h_cosTab[64 - m] : h_cosTab[m];
     }
   cudaMemcpyToSymbol(c_T32, T, sizeof(T));
   if (device < 64) g_resid_tables_uploaded[device] = true;
