@@ -133,17 +133,21 @@ template <int NT> __device__ __forceinline__ int mc_odd(const int* w, const McTa
   return s;
 }
 
-// H pass over one staged window: rows 2*rp, 2*rp+1 x output columns 2*cp, 2*cp+1 per item; results packed (row 2rp | row 2rp+1 << 16)
-template <int NT>
-__device__ __forceinline__ void mc_hpass(const int16_t* s, uint32_t* tmp, int off, int rowPairs, int log2ColPairs,
+// H pass over one staged window: rows 2*rp, 2*rp+1 x output columns 2*cp, 2*cp+1 per item; results packed (row 2rp | row 2rp+1 << 16).
+// PAIR: two windows with the same geometry and phase (the Cb and Cr windows of an 8-wide chroma tile) in one sweep; the
+// second plane's results go to words 8..15 of each row pair.
+template <int NT, bool PAIR>
+__device__ __forceinline__ void mc_hpass(const int16_t* s, const int16_t* sB, uint32_t* tmp, int off, int rowPairs, int log2ColPairs,
                                          const McTaps<NT>& tx, int s1, int o1, int lane)
 {
-  const int nItems = rowPairs << log2ColPairs;
+  const int nItems = rowPairs << (log2ColPairs + (PAIR ? 1 : 0));
   const bool oddStart = off & 1;
   for (int it = lane; it < nItems; it += 32)
   {
-    const int cp = it & ((1 << log2ColPairs) - 1), rp = it >> log2ColPairs;
-    const int* r0 = (const int*)(s + 2 * rp * MC_PITCH) + (off >> 1) + cp;
+    const int cp = it & ((1 << log2ColPairs) - 1);
+    const int second = PAIR ? (it >> log2ColPairs) & 1 : 0;
+    const int rp = it >> (log2ColPairs + (PAIR ? 1 : 0));
+    const int* r0 = (const int*)((second ? sB : s) + 2 * rp * MC_PITCH) + (off >> 1) + cp;
     const int* r1 = r0 + MC_PITCH / 2;
     int w0[NT / 2 + 1], w1[NT / 2 + 1];
 #pragma unroll
@@ -155,7 +159,7 @@ __device__ __forceinline__ void mc_hpass(const int16_t* s, uint32_t* tmp, int of
     uint2 out;
     out.x = (uint32_t)(a0 & 0xffff) | ((uint32_t)b0 << 16);
     out.y = (uint32_t)(a1 & 0xffff) | ((uint32_t)b1 << 16);
-    *(uint2*)(tmp + rp * MC_TMPW + 2 * cp) = out;
+    *(uint2*)(tmp + rp * MC_TMPW + 8 * second + 2 * cp) = out;
   }
 }
 
@@ -176,9 +180,11 @@ __device__ __forceinline__ void mc_vpass(const uint32_t* tmp, int x4, int yg, co
 
 // refIdx = refIdx of list 0 | list 1 << 4 (explicit weighted prediction only: TComWeightPrediction::addWeightUni / addWeightBi,
 // TComWeightPrediction.cpp:44-53,75-196 — both cases start from the 14-bit intermediates, like bi-prediction)
-template <int NT>
+// PAIR (8-wide chroma tiles, i.e. 4:2:0 and 4:2:2): planes `comp` and `comp + 1` together — the first half of the active lanes
+// owns Cb, the second half Cr (same geometry, phases and offsets; windows srefB), which halves the instructions of a chroma tile.
+template <int NT, bool PAIR>
 __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu& t, int comp, int cx, int cy, int16_t* const sref[2],
-                                             const int offs[2], uint32_t* tmp, int lane, int refIdx)
+                                             int16_t* const srefB[2], const int offs[2], uint32_t* tmp, int lane, int refIdx)
 {
   const int tw = 16 >> cx, th = 16 >> cy;                    // full tile in this component
   const int x0 = t.x >> cx, y0 = t.y >> cy, w = t.w >> cx, h = t.h >> cy;
@@ -187,21 +193,25 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
   const int s1 = 6 - headroom, o1 = -(8192 << s1);
   const bool bi = t.lists == (HMR_PU_L0 | HMR_PU_L1);
   const bool wpOn = P.wp != nullptr;
+  const int second = PAIR ? (lane >= ((tw >> 2) * (th >> 1)) ? 1 : 0) : 0;
+  const int laneInPlane = lane - second * ((tw >> 2) * (th >> 1));
+  const int myComp = comp + second;
   int wpW[2] = {0, 0}, wpO[2] = {0, 0}, wpD = 0;
   if (wpOn)
   {
     for (int l = 0; l < 2; l++)
     {
       if (!(t.lists & (1 << l))) continue;
-      const hmr_wp q = P.wp[(l * 16 + ((refIdx >> (4 * l)) & 15)) * 3 + comp];
+      const hmr_wp q = P.wp[(l * 16 + ((refIdx >> (4 * l)) & 15)) * 3 + myComp];
       wpW[l] = q.weight; wpO[l] = q.offset;
       if (l == 0 || !(t.lists & HMR_PU_L0)) wpD = q.log2_denom;          // bi uses the list-0 denominator (getWpScaling)
     }
   }
   const int rowPairs = (th + NT) >> 1;                       // th + NT - 1 rows, rounded up to even
   const int log2ColPairs = tw == 16 ? 3 : 2;
-  const int nV = (tw >> 2) * (th >> 1);                      // V items: 4 columns x 2 rows each (<= 32)
-  const int x4 = lane & ((tw >> 2) - 1), yg = lane / (tw >> 2);
+  const int nV1 = (tw >> 2) * (th >> 1);                     // V items of one plane: 4 columns x 2 rows each
+  const int nV = PAIR ? 2 * nV1 : nV1;                       // <= 32
+  const int x4 = laneInPlane & ((tw >> 2) - 1), yg = laneInPlane / (tw >> 2);
   int acc[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) acc[i] = 0;
@@ -216,7 +226,7 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
       // TComInterpolationFilter::filterCopy (TComInterpolationFilter.cpp:94-148): the staged window IS the block
       if (lane < nV)
       {
-        const int16_t* src = sref[list] + 2 * yg * MC_PITCH + offs[list] + 4 * x4;
+        const int16_t* src = (second ? srefB[list] : sref[list]) + 2 * yg * MC_PITCH + offs[list] + 4 * x4;
 #pragma unroll
         for (int i = 0; i < 8; i++)
         {
@@ -230,12 +240,12 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
     }
     const McTaps<NT> tx = mc_load_taps<NT>(NT == 8 ? fx : fx << (1 - cx));
     const McTaps<NT> ty = mc_load_taps<NT>(NT == 8 ? fy : fy << (1 - cy));
-    mc_hpass<NT>(sref[list], tmp, offs[list], rowPairs, log2ColPairs, tx, s1, o1, lane);
+    mc_hpass<NT, PAIR>(sref[list], PAIR ? srefB[list] : nullptr, tmp, offs[list], rowPairs, log2ColPairs, tx, s1, o1, lane);
     __syncwarp();
     if (lane < nV)
     {
       int v[8];
-      mc_vpass<NT>(tmp, x4, yg, ty, v);
+      mc_vpass<NT>(tmp + 8 * second, x4, yg, ty, v);
       if (wpOn)
       {
 #pragma unroll
@@ -277,12 +287,13 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = clip3i(0, maxv, (acc[i] + off) >> sh);
   }
-  int16_t* dst = P.work.p[comp] + (size_t)(y0 + 2 * yg) * P.work.pitch[comp] + x0 + 4 * x4;
+  const int dpitch = P.work.pitch[myComp];
+  int16_t* dst = P.work.p[myComp] + (size_t)(y0 + 2 * yg) * dpitch + x0 + 4 * x4;
 #pragma unroll
   for (int r = 0; r < 2; r++)
   {
     if (2 * yg + r >= h) break;
-    int16_t* d = dst + (size_t)r * P.work.pitch[comp];
+    int16_t* d = dst + (size_t)r * dpitch;
     const uint32_t lo = (uint32_t)(acc[4 * r] & 0xffff) | ((uint32_t)acc[4 * r + 1] << 16);
     const uint32_t hi = (uint32_t)(acc[4 * r + 2] & 0xffff) | ((uint32_t)acc[4 * r + 3] << 16);
     if (4 * x4 + 4 <= w && (((x0 + 4 * x4) & 3) == 0)) *(uint2*)d = make_uint2(lo, hi);
@@ -342,11 +353,12 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
   mc_cp_async_wait<0>();
   __syncwarp();
   const int refIdx = P.wp ? (int)P.mc_tile_refidx[tile] : 0;
-  if (LUMA) mc_component<8>(P, t, 0, 0, 0, sref[0], offs[0], tmp, lane, refIdx);
+  if (LUMA) mc_component<8, false>(P, t, 0, 0, 0, sref[0], sref[0], offs[0], tmp, lane, refIdx);
+  else if (P.csx) mc_component<4, true>(P, t, 1, 1, P.csy, sref[1], sref[2], offs[1], tmp, lane, refIdx);   // 8-wide tiles: Cb and Cr together
   else
   {
-    mc_component<4>(P, t, 1, P.csx, P.csy, sref[1], offs[1], tmp, lane, refIdx);
-    mc_component<4>(P, t, 2, P.csx, P.csy, sref[2], offs[2], tmp, lane, refIdx);
+    mc_component<4, false>(P, t, 1, 0, P.csy, sref[1], sref[1], offs[1], tmp, lane, refIdx);
+    mc_component<4, false>(P, t, 2, 0, P.csy, sref[2], sref[2], offs[2], tmp, lane, refIdx);
   }
 }
 
