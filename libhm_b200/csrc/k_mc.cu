@@ -105,6 +105,33 @@ __device__ __forceinline__ void mc_stage(int16_t* s, const int16_t* __restrict__
   }
 }
 
+// The Cb and Cr windows of a tile have the same geometry: lanes 0-15 stage Cb, lanes 16-31 Cr (4 rows x 4 vectors per round).
+__device__ __forceinline__ void mc_stage_pair(int16_t* sCb, int16_t* sCr, const int16_t* __restrict__ refCb, const int16_t* __restrict__ refCr,
+                                              int rpitch, int Wc, int Hc, int ix, int iy, int xa, int rows, int cols, int nvec, int lane)
+{
+  const bool inside = iy >= 0 && iy + rows <= Hc && ix >= 0 && ix + cols <= Wc && xa + 32 <= rpitch;
+  const int l16 = lane & 15;
+  const int16_t* __restrict__ ref = (lane & 16) ? refCr : refCb;
+  int16_t* s = (lane & 16) ? sCr : sCb;
+  if (inside)
+  {
+    const int16_t* g = ref + (size_t)(iy + (l16 >> 2)) * rpitch + xa + 8 * (l16 & 3);
+    int16_t* d = s + (l16 >> 2) * MC_PITCH + 8 * (l16 & 3);
+    if ((l16 & 3) < nvec)
+      for (int r = l16 >> 2; r < rows; r += 4, g += 4 * (size_t)rpitch, d += 4 * MC_PITCH) mc_cp_async16(d, g);
+  }
+  else
+  {
+    const int n = 8 * nvec;
+    for (int i = l16; i < rows * n; i += 16)
+    {
+      const int r = i / n, c = i - r * n;
+      const int yy = clip3i(0, Hc - 1, iy + r), xx = clip3i(0, Wc - 1, xa + c);
+      s[r * MC_PITCH + c] = ref[(size_t)yy * rpitch + xx];
+    }
+  }
+}
+
 template <int NT> struct McTaps { int e[NT / 2]; int o[NT / 2 + 1]; };
 
 template <int NT>
@@ -326,7 +353,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
 
   // ---- stage all windows of this launch's component(s), all copies in flight together ----
 #pragma unroll
-  for (int comp = LUMA ? 0 : 1; comp < (LUMA ? 1 : 3); comp++)
+  for (int comp = LUMA ? 0 : 1; comp < (LUMA ? 1 : 2); comp++)     // chroma: Cb and Cr are staged together
   {
     const int cx = comp ? P.csx : 0, cy = comp ? P.csy : 0;
     const int nt = comp ? 4 : 8, half = nt / 2 - 1;
@@ -335,9 +362,10 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
 #pragma unroll
     for (int list = 0; list < 2; list++)
     {
-      int16_t* s = comp == 0 ? win + list * 24 * MC_PITCH : win + ((comp - 1) * 2 + list) * chromaRows * MC_PITCH;
+      int16_t* s = comp == 0 ? win + list * 24 * MC_PITCH : win + list * chromaRows * MC_PITCH;
       sref[comp][list] = s;
       offs[comp][list] = 0;
+      if (!LUMA) { sref[2][list] = win + (2 + list) * chromaRows * MC_PITCH; offs[2][list] = 0; }
       if (!(t.lists & (1 << list))) continue;
       const int slot = list ? (t.slots >> 4) : (t.slots & 15);
       // integer-sample motion (HM's filterCopy case): only the block itself is needed, no filter support around it
@@ -346,7 +374,12 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant
       const int xa = ix & ~7, off = ix - xa;
       offs[comp][list] = off;
       const int wrows = whole ? th : rows, wcols = whole ? tw : cols;
-      mc_stage(s, P.dpb[slot].p[comp], P.dpb[slot].pitch[comp], P.w[comp], P.h[comp], ix, iy, xa, wrows, wcols, (off + wcols + 7) >> 3, lane);
+      if (LUMA) mc_stage(s, P.dpb[slot].p[0], P.dpb[slot].pitch[0], P.w[0], P.h[0], ix, iy, xa, wrows, wcols, (off + wcols + 7) >> 3, lane);
+      else
+      {
+        offs[2][list] = off;
+        mc_stage_pair(s, sref[2][list], P.dpb[slot].p[1], P.dpb[slot].p[2], P.dpb[slot].pitch[1], P.w[1], P.h[1], ix, iy, xa, wrows, wcols, (off + wcols + 7) >> 3, lane);
+      }
     }
   }
   mc_cp_async_commit();
