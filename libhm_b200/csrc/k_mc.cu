@@ -90,8 +90,13 @@ __device__ __forceinline__ void mc_stage(int16_t* s, const int16_t* __restrict__
     // up to 4 x 16 bytes per row (only the vectors the window touches): 8 rows per round, pointers only advance
     const int16_t* g = ref + (size_t)(iy + (lane >> 2)) * rpitch + xa + 8 * (lane & 3);
     int16_t* d = s + (lane >> 2) * MC_PITCH + 8 * (lane & 3);
+    // rows <= 24: at most 3 rounds of 8 rows, unrolled with a row predicate (no loop-carried 64-bit pointer updates)
     if ((lane & 3) < nvec)
-      for (int r = lane >> 2; r < rows; r += 8, g += 8 * (size_t)rpitch, d += 8 * MC_PITCH) mc_cp_async16(d, g);
+    {
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        if ((lane >> 2) + 8 * k < rows) mc_cp_async16(d + 8 * k * MC_PITCH, g + (size_t)(8 * k) * rpitch);
+    }
   }
   else
   {
@@ -117,8 +122,13 @@ __device__ __forceinline__ void mc_stage_pair(int16_t* sCb, int16_t* sCr, const 
   {
     const int16_t* g = ref + (size_t)(iy + (l16 >> 2)) * rpitch + xa + 8 * (l16 & 3);
     int16_t* d = s + (l16 >> 2) * MC_PITCH + 8 * (l16 & 3);
+    // rows <= 20 (4:2:2 tile: 16 + 4): at most 5 rounds of 4 rows, unrolled with a row predicate
     if ((l16 & 3) < nvec)
-      for (int r = l16 >> 2; r < rows; r += 4, g += 4 * (size_t)rpitch, d += 4 * MC_PITCH) mc_cp_async16(d, g);
+    {
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        if ((l16 >> 2) + 4 * k < rows) mc_cp_async16(d + 4 * k * MC_PITCH, g + (size_t)(4 * k) * rpitch);
+    }
   }
   else
   {
@@ -259,7 +269,7 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
         {
           const int smp = src[(i >> 2) * MC_PITCH + (i & 3)];
           if (wpOn)    acc[i] += wpW[list] * (smp << headroom);                     // (P + IF_INTERNAL_OFFS), P = (s << headroom) - 8192
-          else if (bi) acc[i] += (int)(int16_t)((smp << headroom) - 8192);
+          else if (bi) acc[i] += (smp << headroom) - 8192;                          // fits Pel for bit depths <= 12 (engine limit): no wrap
           else         acc[i] = smp;
         }
       }
