@@ -132,10 +132,18 @@ def algorithmic_bytes(fr):
         out["intra"] = 2.0 * float((n * n).sum()) + 2.0 * float((n * n)[has_res].sum()) + 2.0 * float((4 * n + 1).sum()) + 16.0 * len(it)
     else:
         out["intra"] = 0.0
-    deb = (2.0 * S_b + w4 * h4 + w8 * h8) if (int(h["flags"]) & 2) else 0.0
-    out["deblock_v"] = deb
-    out["deblock_h"] = deb
-    out["sao"] = 2.0 * S_b + 36.0 * int(h["n_ctu"])
+    # deblocking: what a pass must READ — the 4 lines x 8 samples around every edge segment with BS > 0 on the 8x8 grid, the
+    # chroma lines of BS-2 segments on the chroma grid, and the BS map itself (writes are data dependent and not counted)
+    out["deblock_v"] = out["deblock_h"] = 0.0
+    if (int(h["flags"]) & 2) and fr.bs is not None and len(fr.bs):
+        bs = np.asarray(fr.bs).reshape(h4, w4)
+        sx, sy = (1, 1) if fmt == 1 else ((1, 0) if fmt == 2 else (0, 0))
+        for name, seg, grid_sel, nlines in (("deblock_v", bs[:, ::2] & 3, np.arange(0, w4, 2) % (2 << sx) == 0, 4 >> sy),
+                                            ("deblock_h", (bs[::2, :] >> 2) & 3, np.arange(0, h4, 2) % (2 << sy) == 0, 4 >> sx)):
+            strong = seg == 2
+            n_chroma = int(strong[:, grid_sel].sum()) if name == "deblock_v" else int(strong[grid_sel, :].sum())
+            out[name] = 64.0 * int((seg != 0).sum()) + 2 * nlines * 8.0 * n_chroma + float(w4 * h4)
+    out["sao"] = (2.0 * S_b + 36.0 * int(h["n_ctu"])) if (int(h["flags"]) & 4) else 0.0     # pictures without SAO launch nothing
     return out
 
 
