@@ -11,6 +11,7 @@
 #include <thread>
 #include <vector>
 #include <pthread.h>
+#include <sys/resource.h>
 #include "libHMDecoder_api.h"
 #include "annexb.h"
 
@@ -101,11 +102,18 @@ int main(int argc, char** argv)
   if (startAt > 0)
     while (std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count() < startAt) std::this_thread::sleep_for(std::chrono::microseconds(200));
   const double wallStart = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
+  struct rusage ru0, ru1;
+  getrusage(RUSAGE_SELF, &ru0);
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   sh.go = true;
   for (size_t t = 0; t < pool.size(); t++) pool[t].join();
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  printf("{\"threads\": %d, \"repeat\": %d, \"pictures\": %ld, \"seconds\": %.6f, \"fps\": %.3f, \"hash\": %s, \"planes\": %s, \"failures\": %d, \"t_start\": %.6f, \"t_end\": %.6f}\n",
-         threads, repeat, sh.pictures.load(), sec, sh.pictures.load() / sec, hash ? "true" : "false", planes ? "true" : "false", sh.failures.load(), wallStart, wallStart + sec);
+  getrusage(RUSAGE_SELF, &ru1);
+  const double user = (ru1.ru_utime.tv_sec - ru0.ru_utime.tv_sec) + 1e-6 * (ru1.ru_utime.tv_usec - ru0.ru_utime.tv_usec);
+  const double sys = (ru1.ru_stime.tv_sec - ru0.ru_stime.tv_sec) + 1e-6 * (ru1.ru_stime.tv_usec - ru0.ru_stime.tv_usec);
+  printf("{\"threads\": %d, \"repeat\": %d, \"pictures\": %ld, \"seconds\": %.6f, \"fps\": %.3f, \"hash\": %s, \"planes\": %s, \"failures\": %d, \"t_start\": %.6f, \"t_end\": %.6f, "
+         "\"cpu_user_s\": %.3f, \"cpu_sys_s\": %.3f, \"minor_faults\": %ld, \"ctx_switches_invol\": %ld}\n",
+         threads, repeat, sh.pictures.load(), sec, sh.pictures.load() / sec, hash ? "true" : "false", planes ? "true" : "false", sh.failures.load(), wallStart, wallStart + sec,
+         user, sys, (long)(ru1.ru_minflt - ru0.ru_minflt), (long)(ru1.ru_nivcsw - ru0.ru_nivcsw));
   return sh.failures.load() ? 1 : 0;
 }
