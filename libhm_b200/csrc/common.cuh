@@ -40,6 +40,9 @@ struct FrameParams
   uint4*                     intra_ops;       // [n_intra] decoded intra TUs           } scratch written by k_intra.cu's pre-pass
   uint16_t*                  intra_tab;       // [3][n_ctu][4352] reference-address tables }
   uint4*                     intra_prep;      // [3][n_ctu] residual span / table length   }
+  int                        intra_max_rec;   // largest number of intra records of one (component, CTU) of this picture   } shared-memory
+  int                        intra_max_addr;  // largest reference-address table of one (component, CTU), entries           } capacities of
+  int                        intra_res_span;  // largest residual span of one (component, CTU), samples                      } intra_kernel
   unsigned long long*        intra_progress;  // [3][ctus_h], (epoch << 32) | CTUs finished in that row
   unsigned long long         epoch;
 };
@@ -55,5 +58,7 @@ void launch_sao(const FrameParams& P, cudaStream_t s);
 void launch_hash(const PlaneSet& pic, const int w[3], const int h[3], const int bd[3], int type, uint32_t* d_out, uint32_t* d_scratch, cudaStream_t s);
 int  intra_max_coresident_blocks(int device);
 size_t intra_table_bytes(int nctu);
+struct IntraSizes { int maxRec, maxAddr, resSpan; };
+IntraSizes intra_sizes_host(const hmr_frame_hdr& h, const hmr_intra* rec, const hmr_ctu_intra_range* range);
 size_t launch_pack(const PlaneSet& pic, const int w[3], const int h[3], int csx, int csy, int ncomp, const int bdInternal[3], const int bdOut[3],
                    const int crop[4], uint8_t* d_dst, cudaStream_t s);

@@ -31,6 +31,7 @@ struct hmr_resident_frame
   hmr_frame_hdr hdr;
   Layout lay;
   bool hasBs, hasCuf;
+  IntraSizes intra;
 };
 
 struct FrameEvents { cudaEvent_t ev[HMR_T_COUNT + 1]; bool used[HMR_T_COUNT + 1]; };
@@ -286,6 +287,7 @@ static void fill_params(hmr_engine* e, FrameParams& P, const hmr_frame_hdr& h, c
   P.mc_tile_refidx = e->mcTileRef;
   P.intra_progress = e->progress;
   P.intra_ops = e->intraOps; P.intra_tab = e->intraTab; P.intra_prep = e->intraPrep;
+  P.intra_max_rec = P.intra_max_addr = P.intra_res_span = 0;      // 0 = worst case; the callers fill in what the records say
   P.epoch = e->epoch;
 }
 
@@ -488,6 +490,8 @@ int hmr_submit_frame(hmr_engine* e, const hmr_frame_desc* f)
   CK(cudaMemcpyAsync(st.dev, st.host, L.total, cudaMemcpyHostToDevice, e->stream));
   FrameParams P;
   fill_params(e, P, h, L, st.dev, hasBs, hasCuf);
+  const IntraSizes iz = intra_sizes_host(h, f->intra, f->intra_range);
+  P.intra_max_rec = iz.maxRec; P.intra_max_addr = iz.maxAddr; P.intra_res_span = iz.resSpan;
   r = run_frame(e, P, fe);
   CK(cudaEventRecord(st.done, e->stream));
   st.inflight = true;
@@ -623,6 +627,7 @@ int hmr_upload_frame(hmr_engine* e, const hmr_frame_desc* f, hmr_resident_frame*
   rf->hdr = *f->hdr;
   rf->hasBs = f->bs != nullptr; rf->hasCuf = f->cu_flags != nullptr;
   rf->lay = make_layout(rf->hdr, rf->hasBs, rf->hasCuf, (rf->hdr.flags & HMR_FRM_SCALING_LIST) != 0);
+  rf->intra = intra_sizes_host(rf->hdr, f->intra, f->intra_range);
   std::vector<uint8_t> tmp(rf->lay.total);
   pack(tmp.data(), rf->lay, f);
   cudaError_t ce = cudaMalloc(&rf->dev, rf->lay.total);
@@ -641,6 +646,7 @@ int hmr_run_resident(hmr_engine* e, const hmr_resident_frame* f)
   if ((r = ensure_slot(e, f->hdr.out_slot))) return r;
   FrameParams P;
   fill_params(e, P, f->hdr, f->lay, f->dev, f->hasBs, f->hasCuf);
+  P.intra_max_rec = f->intra.maxRec; P.intra_max_addr = f->intra.maxAddr; P.intra_res_span = f->intra.resSpan;
   return run_frame(e, P, grab_events(e));
 }
 

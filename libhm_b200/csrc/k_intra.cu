@@ -436,19 +436,21 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) intra_prep_kernel(const __gri
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
-__global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant__ FrameParams P, const int resSamples)
+__global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant__ FrameParams P, const int resSamples, const int maxRec, const int maxAddr)
 {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   constexpr int TILE_PAD = (IN_TILE + 7) & ~7;
   int16_t* s_tileB = (int16_t*)s_dyn;                                        // [2][TILE_PAD]
   int16_t* s_resB = s_tileB + 2 * TILE_PAD;                                  // [2][resSamples] residuals of a CTU, compact layout relative to minoff
-  IntraOp* s_ops = (IntraOp*)(s_resB + 2 * resSamples);                      // [2][IN_MAXREC] decoded TUs of a CTU
-  uint16_t* s_addr = (uint16_t*)(s_ops + 2 * IN_MAXREC);                     // [2][IN_ADDR]
+  // capacities = the largest CTU of THIS picture (engine.cu measures the records): a resident CTA holds its shared memory for
+  // the whole wavefront, and at saturation that footprint is what other streams' kernels wait for
+  IntraOp* s_ops = (IntraOp*)(s_resB + 2 * resSamples);                      // [2][maxRec] decoded TUs of a CTU
+  uint16_t* s_addr = (uint16_t*)(s_ops + 2 * maxRec);                        // [2][maxAddr]
+  uint4* s_prep = (uint4*)(s_addr + 2 * maxAddr);                            // [ctus_w] per CTU of this row: x = first residual, y = residual span, z = table entries
+  uint32_t* s_first = (uint32_t*)(s_prep + P.ctus_w);                        // [ctus_w]
+  uint16_t* s_count = (uint16_t*)(s_first + P.ctus_w);                       // [ctus_w]
   __shared__ int s_refBuf[2][4 * 32 + 8]; // reference line of a TU: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right
                                           // (two copies, alternating per TU: the next TU may write while a slow lane still reads)
-  __shared__ uint32_t s_first[IN_MAXCOLS];
-  __shared__ uint16_t s_count[IN_MAXCOLS];
-  __shared__ uint4 s_prep[IN_MAXCOLS];    // per CTU of this row: x = first residual, y = residual span, z = table entries
   __shared__ int16_t s_col[IN_MAXCT];     // right-most column of the CTU the chain just finished (left neighbours of the next one)
   __shared__ __align__(8) unsigned long long s_mbar[2];   // one per buffer: completion of the TMA bulk copies
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -476,7 +478,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   {
     const hmr_ctu_intra_range rg = P.irange[row * ctusW + c];
     s_first[c] = rg.first[comp];
-    s_count[c] = (uint16_t)min(rg.count[comp], (uint32_t)IN_MAXREC);
+    s_count[c] = (uint16_t)min(rg.count[comp], (uint32_t)maxRec);
     s_prep[c] = P.intra_prep[(size_t)comp * ctusW * P.ctus_h + (size_t)row * ctusW + c];
   }
   if (tid == 0)
@@ -499,8 +501,8 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
     {
       const int b = n & 1;
       int16_t* tile = s_tileB + b * TILE_PAD;
-      const IntraOp* ops = s_ops + b * IN_MAXREC;
-      const uint16_t* addrTab = s_addr + b * IN_ADDR;
+      const IntraOp* ops = s_ops + b * maxRec;
+      const uint16_t* addrTab = s_addr + b * maxAddr;
       const int16_t* resB = s_resB + b * resSamples;
       const int count = s_count[c];
       const int ox = c * CTW;
@@ -544,8 +546,8 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   {
     const int b = n & 1;
     int16_t* tile = s_tileB + b * TILE_PAD;
-    IntraOp* ops = s_ops + b * IN_MAXREC;
-    uint16_t* addrTab = s_addr + b * IN_ADDR;
+    IntraOp* ops = s_ops + b * maxRec;
+    uint16_t* addrTab = s_addr + b * maxAddr;
     int16_t* resB = s_resB + b * resSamples;
     const int count = s_count[c];
     const uint32_t first = s_first[c];
@@ -668,9 +670,34 @@ static int intra_res_samples(const FrameParams& P)
   const int ct = 1 << P.hdr.log2_ctu;
   return ct * ct + 2 * ((ct >> P.csx) * (ct >> P.csy));
 }
-static size_t intra_dyn_smem(int resSamples)
+static size_t intra_dyn_smem(int resSamples, int maxRec, int maxAddr, int ctusW)
 {
-  return 2 * ((size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + IN_MAXREC * 16 + IN_ADDR * sizeof(uint16_t));
+  return 2 * ((size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + (size_t)maxRec * 16 + (size_t)maxAddr * sizeof(uint16_t)) +
+         (size_t)ctusW * (sizeof(uint4) + sizeof(uint32_t) + sizeof(uint16_t));
+}
+
+// Largest CTU of a picture, measured on the host records (the same quantities intra_prep_kernel derives per CTU on the device).
+IntraSizes intra_sizes_host(const hmr_frame_hdr& h, const hmr_intra* rec, const hmr_ctu_intra_range* range)
+{
+  IntraSizes z = { 1, 8, 8 };
+  if (!rec || !range) return z;
+  for (uint32_t ctu = 0; ctu < h.n_ctu; ctu++)
+    for (int c = 0; c < 3; c++)
+    {
+      const uint32_t first = range[ctu].first[c], count = range[ctu].count[c];
+      if (!count) continue;
+      unsigned tab = 0, mn = 0xffffffffu, mx = 0;
+      for (uint32_t k = 0; k < count; k++)
+      {
+        const hmr_intra& r = rec[first + k];
+        tab += (4u << r.log2_size) + 1;
+        if (r.resid_off != HMR_NO_OFFSET) { mn = r.resid_off < mn ? r.resid_off : mn; const unsigned e = r.resid_off + (1u << (2 * r.log2_size)); mx = e > mx ? e : mx; }
+      }
+      if ((int)count > z.maxRec) z.maxRec = (int)count;
+      if ((int)tab > z.maxAddr) z.maxAddr = (int)tab;
+      if (mx > mn && (int)(mx - mn) > z.resSpan) z.resSpan = (int)(mx - mn);
+    }
+  return z;
 }
 
 size_t intra_table_bytes(int nctu) { return (size_t)3 * nctu * IN_ADDR * sizeof(uint16_t); }
@@ -678,7 +705,7 @@ size_t intra_table_bytes(int nctu) { return (size_t)3 * nctu * IN_ADDR * sizeof(
 int intra_max_coresident_blocks(int device)
 {
   int perSm = 0, sms = 0;
-  const size_t worst = intra_dyn_smem(3 * IN_MAXCT * IN_MAXCT);
+  const size_t worst = intra_dyn_smem(3 * IN_MAXCT * IN_MAXCT, IN_MAXREC, IN_ADDR, IN_MAXCOLS);
   cudaFuncSetAttribute(intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, intra_kernel, IN_THREADS, worst);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -689,8 +716,12 @@ cudaError_t launch_intra(const FrameParams& P, cudaStream_t s)
 {
   if (P.hdr.n_intra == 0) return cudaSuccess;
   if (P.ctus_w > IN_MAXCOLS) return cudaErrorInvalidValue;
-  int resSamples = intra_res_samples(P);
+  // shared-memory capacities: this picture's largest CTU, rounded so that every buffer stays 16-byte aligned
+  const int full = intra_res_samples(P);
+  int resSamples = P.intra_res_span > 0 ? min(full, (P.intra_res_span + 7) & ~7) : full;
+  int maxRec = P.intra_max_rec > 0 ? min(IN_MAXREC, P.intra_max_rec) : IN_MAXREC;
+  int maxAddr = P.intra_max_addr > 0 ? min(IN_ADDR, (P.intra_max_addr + 7) & ~7) : IN_ADDR;
   intra_prep_kernel<<<(3 * P.ctus_w * P.ctus_h + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, s>>>(P);
-  void* args[] = { (void*)&P, (void*)&resSamples };
-  return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(3 * P.ctus_h), dim3(IN_THREADS), args, intra_dyn_smem(resSamples), s);
+  void* args[] = { (void*)&P, (void*)&resSamples, (void*)&maxRec, (void*)&maxAddr };
+  return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(3 * P.ctus_h), dim3(IN_THREADS), args, intra_dyn_smem(resSamples, maxRec, maxAddr, P.ctus_w), s);
 }

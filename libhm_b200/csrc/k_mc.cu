@@ -24,6 +24,9 @@
 #include "common.cuh"
 
 #define MC_WARPS 4
+#ifndef MC_MIN_BLOCKS
+#define MC_MIN_BLOCKS 9               // 56 registers.  Measured: 10 (<= 51 regs, 4-24 B spilled) 47.0 -> 48.8 us, 12 (<= 42 regs) 53.2 us; value unchanged
+#endif
 #define MC_PITCH 40                 // int16 per staged window row: up to 32 loaded + 8 pad (80 B: 16-byte aligned, conflict-free row pairs)
 #define MC_TMPW 16                  // words per row pair of the H-pass output
 
@@ -346,7 +349,7 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
 // components: each then needs half the shared memory per warp, which doubles the warps in flight per SM — and what this
 // kernel waits for is memory latency (ncu: issue slots idle on cp.async completion), not arithmetic.
 template <bool LUMA>
-__global__ void __launch_bounds__(MC_WARPS * 32) mc_kernel(const __grid_constant__ FrameParams P, const int warpBytes, const int chromaRows)
+__global__ void __launch_bounds__(MC_WARPS * 32, MC_MIN_BLOCKS) mc_kernel(const __grid_constant__ FrameParams P, const int warpBytes, const int chromaRows)
 {
   extern __shared__ __align__(16) uint8_t s_mc[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
