@@ -23,7 +23,9 @@
 // uses NT/2+1 with the taps shifted by one half-word (0,t0)(t1,t2)..(t7,0).  All sums are exact int32, as in HM.
 #include "common.cuh"
 
+#ifndef MC_WARPS
 #define MC_WARPS 4
+#endif
 #ifndef MC_MIN_BLOCKS
 #define MC_MIN_BLOCKS 9               // 56 registers.  Measured: 10 (<= 51 regs, 4-24 B spilled) 47.0 -> 48.8 us, 12 (<= 42 regs) 53.2 us; value unchanged
 #endif
