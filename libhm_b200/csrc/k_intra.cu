@@ -469,7 +469,6 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   const int CTW = g.CTW, CTH = g.CTH;
   const int W = P.w[comp], H = P.h[comp];
   const int ctusW = P.ctus_w;
-  const bool strongAllowed = P.hdr.flags & HMR_FRM_STRONG_INTRA_SMOOTHING;
   int16_t* plane = P.work.p[comp];
   const int pitch = P.work.pitch[comp];
   const int oy = row * CTH, ch = min(CTH, H - oy);
@@ -540,7 +539,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   }
 
   // ============================ stager warps: everything that touches global memory ============================
-  const int st = tid - 32, swarp = warp - 1;
+  const int st = tid - 32;
   int prev = -2, prevB = 0, n = 0;
   for (int c = c0; c < ctusW; n++)
   {

@@ -105,7 +105,6 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
   if (plainTransform)
   {
     const bool dst = (LOG2N == 2) && (t.flags & HMR_TU_DST);
-    const int shift2 = 20 - bd, rnd2 = 1 << (shift2 - 1);
 #pragma unroll
     for (int k = 0; k < N; k++) acc[k] = 0;
     for (int n = 0; n < N; n++)
