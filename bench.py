@@ -186,6 +186,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL's version banner, for one) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     rank, local_rank, world = _rank_env()
     rec_path, bin_path = _paths(a.workload)
     ncores = os.cpu_count() or 1
@@ -207,7 +214,7 @@ def main():
                 "dtype": "int16", "data": "synthetic", "config": dict(cfg, note="unmodified TAppDecoderStatic -d 0 (SEI MD5 check on), one process per host core, all cores; 1 warm-up pass at most"),
                 "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": ncores, "kind": "reference", "sample": f"{a.steps} pass(es) of the {nframes}-picture stream per core"},
                 "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ---------------------------------------------------------------- our arm
@@ -354,7 +361,7 @@ def main():
             "config": dict(cfg, streams_per_gpu=S, pictures_per_stream=F, l2="working set (DPB + work planes of all streams) > 126 MB L2; no explicit flush",
                            parallelism=f"{world} GPU x {S} independent streams, no collective"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kern, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
