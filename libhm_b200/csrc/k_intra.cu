@@ -685,10 +685,12 @@ IntraSizes intra_sizes_host(const hmr_frame_hdr& h, const hmr_intra* rec, const 
     {
       const uint32_t first = range[ctu].first[c], count = range[ctu].count[c];
       if (!count) continue;
+      if (first > h.n_intra || count > h.n_intra - first) { const IntraSizes worst = { 0, 0, 0 }; return worst; }   // inconsistent ranges: worst-case capacities
       unsigned tab = 0, mn = 0xffffffffu, mx = 0;
       for (uint32_t k = 0; k < count; k++)
       {
         const hmr_intra& r = rec[first + k];
+        if (r.log2_size < 2 || r.log2_size > 5) { const IntraSizes worst = { 0, 0, 0 }; return worst; }
         tab += (4u << r.log2_size) + 1;
         if (r.resid_off != HMR_NO_OFFSET) { mn = r.resid_off < mn ? r.resid_off : mn; const unsigned e = r.resid_off + (1u << (2 * r.log2_size)); mx = e > mx ? e : mx; }
       }
