@@ -59,6 +59,37 @@ def test_full_size_streams_pass_the_sei_md5_check(name):
         assert got == _md5s(open(ref_file).read())
 
 
+CORPUS = os.path.join(ROOT, "corpus")
+
+
+def test_config1_1080p_main8_random_access_64_pictures():
+    """BASELINE.json configs[1]: 1920x1080 Main 8-bit random access, 64 pictures (corpus/c2_ra8_1080p)."""
+    path = os.path.join(CORPUS, "c2_ra8_1080p.bin")
+    if not os.path.exists(CLI) or not os.path.exists(path):
+        pytest.skip("frontend or corpus stream not present")
+    r = subprocess.run([CLI, "-b", path, "--touch-planes"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "***ERROR***" not in r.stdout and "(unk)" not in r.stdout
+    got = _md5s(r.stdout)
+    assert len(got) == 64 and got == _md5s(open(os.path.join(CORPUS, "c2_ra8_1080p.md5")).read())
+
+
+def test_config4_eight_low_delay_streams_concurrently():
+    """BASELINE.json configs[4]: 8 independent 2160p Main10 low-delay-B streams decoded CONCURRENTLY on one GPU (8 processes
+    here; the threads-in-one-process form is what bench.py's e2e runs).  Every picture of every stream must carry the MD5
+    the unmodified TAppDecoder printed (corpus/c5_ld10_2160p_s5?.md5)."""
+    names = ["c5_ld10_2160p_s%d" % k for k in range(50, 58)]
+    if not os.path.exists(CLI) or not all(os.path.exists(os.path.join(CORPUS, n + ".bin")) for n in names):
+        pytest.skip("frontend or corpus streams not present")
+    procs = [subprocess.Popen([CLI, "-b", os.path.join(CORPUS, n + ".bin"), "--touch-planes"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for n in names]
+    for n, pr in zip(names, procs):
+        out, err = pr.communicate(timeout=600)
+        assert pr.returncode == 0, (n, err[-2000:])
+        assert "***ERROR***" not in out and "(unk)" not in out, n
+        got = _md5s(out)
+        assert len(got) == 17 and got == _md5s(open(os.path.join(CORPUS, n + ".md5")).read()), n
+
+
 def test_packed_output_equals_tappdecoder_o(tmp_path):
     """Output wire format: `hmdec_cli -o --packed [-d N]` = conformance-window crop + bit-depth conversion +
     8/16-bit packing on the GPU (hmr_read_packed) must give the very file `TAppDecoder -o [-d N]` writes.  The stream is
