@@ -607,6 +607,38 @@ void HmEmitter::intraBlk(CuCtx& c, int compIdx, void* pTu)
 
 // ---------------------------------------------------------------------------------------------
 // deblocking side info: TComLoopFilter::loopFilterPic / xDeblockCU (TComLoopFilter.cpp:130-234) without the filtering
+// Boundary strength of one 4x4 edge unit whose P side lies in the SAME CTU as its Q side (the common case: 15 of 16 unit columns /
+// rows): the rule of TComLoopFilter::xGetBoundaryStrengthSingle (TComLoopFilter.cpp:411-537) evaluated on the CTU's arrays directly.
+// HM's own routine goes through getPULeft / getPUAbove for every unit, whose slice / tile / picture-border logic only matters
+// when the neighbour is another CTU — those units still take HM's routine.  tuEdge = HM's pre-set TU-edge marker of the unit.
+static inline bool mvFar(const TComMv& a, const TComMv& b) { return abs(a.getHor() - b.getHor()) >= 4 || abs(a.getVer() - b.getVer()) >= 4; }
+
+static unsigned bsInsideCtu(TComDataCU* ctu, TComSlice* slice, unsigned partQ, unsigned partP, bool tuEdge)
+{
+  if (ctu->isIntra(partP) || ctu->isIntra(partQ)) return 2;
+  if (tuEdge && (ctu->getCbf(partQ, COMPONENT_Y, ctu->getTransformIdx(partQ)) != 0 || ctu->getCbf(partP, COMPONENT_Y, ctu->getTransformIdx(partP)) != 0)) return 1;
+  TComCUMvField* f0 = ctu->getCUMvField(REF_PIC_LIST_0);
+  int r = f0->getRefIdx(partP);
+  const TComPic* refP0 = r < 0 ? NULL : slice->getRefPic(REF_PIC_LIST_0, r);
+  r = f0->getRefIdx(partQ);
+  const TComPic* refQ0 = r < 0 ? NULL : slice->getRefPic(REF_PIC_LIST_0, r);
+  const TComMv zero;
+  const TComMv& mvP0 = refP0 ? f0->getMv(partP) : zero;
+  const TComMv& mvQ0 = refQ0 ? f0->getMv(partQ) : zero;
+  if (!slice->isInterB()) return (refP0 != refQ0 || mvFar(mvQ0, mvP0)) ? 1 : 0;
+  TComCUMvField* f1 = ctu->getCUMvField(REF_PIC_LIST_1);
+  r = f1->getRefIdx(partP);
+  const TComPic* refP1 = r < 0 ? NULL : slice->getRefPic(REF_PIC_LIST_1, r);
+  r = f1->getRefIdx(partQ);
+  const TComPic* refQ1 = r < 0 ? NULL : slice->getRefPic(REF_PIC_LIST_1, r);
+  const TComMv& mvP1 = refP1 ? f1->getMv(partP) : zero;
+  const TComMv& mvQ1 = refQ1 ? f1->getMv(partQ) : zero;
+  if (!((refP0 == refQ0 && refP1 == refQ1) || (refP0 == refQ1 && refP1 == refQ0))) return 1;     // different reference pictures
+  if (refP0 != refP1)                                                                              // two distinct pictures: match the lists up
+    return (refP0 == refQ0) ? ((mvFar(mvQ0, mvP0) || mvFar(mvQ1, mvP1)) ? 1 : 0) : ((mvFar(mvQ1, mvP0) || mvFar(mvQ0, mvP1)) ? 1 : 0);
+  return ((mvFar(mvQ0, mvP0) || mvFar(mvQ1, mvP1)) && (mvFar(mvQ1, mvP0) || mvFar(mvQ0, mvP1))) ? 1 : 0;   // both lists use the same picture
+}
+
 void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, TComLoopFilter* lf)
 {
   if (ctu->getPic() == 0 || ctu->getPartitionSize(absZorderIdx) == NUMBER_OF_PART_SIZES) return;
@@ -633,6 +665,9 @@ void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, T
   const int cuX = ctu->getCUPelX() + g_auiRasterToPelX[g_auiZscanToRaster[absZorderIdx]];
   const int cuY = ctu->getCUPelY() + g_auiRasterToPelY[g_auiZscanToRaster[absZorderIdx]];
   const int cuSize = g_uiMaxCUWidth >> depth;
+  static const bool fastBs = getenv("HMDEC_B200_HM_BS") == NULL;     // HMDEC_B200_HM_BS=1: HM's routine for every unit
+  TComSlice* slice = ctu->getSlice();
+  const unsigned numPartInWidth = pic->getNumPartInWidth();
   for (int dir = 0; dir < 2; dir++)
   {
     const Bool* edgeFlag = lf->m_aapbEdgeFilter[dir];
@@ -654,8 +689,14 @@ void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, T
       if (!onGrid) continue;
       if (lf->m_aapbEdgeFilter[dir][part])
       {
-        lf->xGetBoundaryStrengthSingle(ctu, DeblockEdgeDir(dir), part);
-        const unsigned bs = lf->m_aapucBS[dir][part];
+        unsigned bs;
+        const bool inside = fastBs && ((dir == EDGE_VER) ? ux > 0 : uy > 0);
+        if (inside) bs = bsInsideCtu(ctu, slice, part, g_auiRasterToZscan[raster - (dir == EDGE_VER ? 1 : numPartInWidth)], lf->m_aapucBS[dir][part] != 0);
+        else
+        {
+          lf->xGetBoundaryStrengthSingle(ctu, DeblockEdgeDir(dir), part);
+          bs = lf->m_aapucBS[dir][part];
+        }
         if (bs)
         {
           const int gx = (ctu->getCUPelX() >> 2) + ux, gy = (ctu->getCUPelY() >> 2) + uy;
