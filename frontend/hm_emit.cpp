@@ -59,7 +59,7 @@ struct HmEmitter::CuCtx
 };
 
 HmEmitter::HmEmitter(HmFrameSink* sink)
-  : m_sink(sink), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0), m_tCtu(0), m_tBs(0), m_tPic(0), m_tSink(0), m_nPic(0)
+  : m_sink(sink), m_lf(NULL), m_lfDepth(0), m_anyDeblock(false), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0), m_tCtu(0), m_tBs(0), m_tPic(0), m_tSink(0), m_nPic(0)
 {
   m_in422SubTu = false;
   // product path: HM's whole-CTU coefficient zero fills are skipped (hm_fast.cpp); verification / golden generation keep them
@@ -69,6 +69,7 @@ HmEmitter::HmEmitter(HmFrameSink* sink)
 
 HmEmitter::~HmEmitter()
 {
+  if (m_lf) { m_lf->destroy(); delete m_lf; }
   if (getenv("HMDEC_B200_STATS") && m_nPic)
     fprintf(stderr, "hm_emit stats: %d pictures; per picture: CTU record emission %.2f ms, BS/QP maps %.2f ms, SAO+pack %.2f ms, sink submit %.2f ms\n",
             m_nPic, 1e3 * m_tCtu / m_nPic, 1e3 * m_tBs / m_nPic, 1e3 * m_tPic / m_nPic, 1e3 * m_tSink / m_nPic);
@@ -101,6 +102,7 @@ void HmEmitter::beginFrame(TComPic* pic, TComDataCU* ctu)
   TComSPS*   sps   = slice->getSPS();
   TComPPS*   pps   = slice->getPPS();
   memset(&m_hdr, 0, sizeof(m_hdr));
+  m_anyDeblock = false;
   m_hdr.magic   = HMR_MAGIC;
   m_hdr.version = HMR_VERSION;
   m_hdr.width   = sps->getPicWidthInLumaSamples();
@@ -168,6 +170,8 @@ void HmEmitter::onCtuParsed(TComDataCU* ctu)
   static const bool prefetch = getenv("HMDEC_B200_NO_PREFETCH") == NULL;
   if (prefetch) hm_fast_prefetch_begin(m_prefetch, pic, ctu->getAddr() + 2);   // the parser is about to init + parse CTU addr+1
   walkCU(ctu, 0, 0);
+  static const bool bsAtEnd = getenv("HMDEC_B200_BS_AT_END") != NULL;   // A/B switch: derive the deblocking side info per picture, like HM
+  if (!bsAtEnd) deblockCtu(ctu);                                   // edge flags + boundary strengths while the CTU's arrays are hot
   m_prefetch.step(1 << 20);                                        // whatever the walk did not get to
   hmr_ctu_intra_range& r = m_range[ctu->getAddr()];
   for (int c = 0; c < 3; c++)
@@ -607,32 +611,37 @@ void HmEmitter::intraBlk(CuCtx& c, int compIdx, void* pTu)
 
 // ---------------------------------------------------------------------------------------------
 // deblocking side info: TComLoopFilter::loopFilterPic / xDeblockCU (TComLoopFilter.cpp:130-234) without the filtering
-// Boundary strength of one 4x4 edge unit whose P side lies in the SAME CTU as its Q side (the common case: 15 of 16 unit columns /
-// rows): the rule of TComLoopFilter::xGetBoundaryStrengthSingle (TComLoopFilter.cpp:411-537) evaluated on the CTU's arrays directly.
-// HM's own routine goes through getPULeft / getPUAbove for every unit, whose slice / tile / picture-border logic only matters
-// when the neighbour is another CTU — those units still take HM's routine.  tuEdge = HM's pre-set TU-edge marker of the unit.
+// Boundary strength of one 4x4 edge unit: the rule of TComLoopFilter::xGetBoundaryStrengthSingle (TComLoopFilter.cpp:411-537)
+// evaluated on the two CTUs' arrays directly.  HM's own routine finds the P side through getPULeft / getPUAbove for every unit;
+// here it is the raster neighbour inside the CTU, or the facing unit of the left / above CTU (TComDataCU.cpp:503,508,1243).  The
+// slice / tile / picture-border rules of those getters have already decided whether the edge exists at all
+// (xSetLoopfilterParam, TComLoopFilter.cpp:352-409): a unit that reaches this point has its P side.  tuEdge = HM's pre-set TU-edge marker.
 static inline bool mvFar(const TComMv& a, const TComMv& b) { return abs(a.getHor() - b.getHor()) >= 4 || abs(a.getVer() - b.getVer()) >= 4; }
 
-static unsigned bsInsideCtu(TComDataCU* ctu, TComSlice* slice, unsigned partQ, unsigned partP, bool tuEdge)
+static unsigned bsOfUnit(TComDataCU* cuP, unsigned partP, TComDataCU* cuQ, unsigned partQ, bool tuEdge)
 {
-  if (ctu->isIntra(partP) || ctu->isIntra(partQ)) return 2;
-  if (tuEdge && (ctu->getCbf(partQ, COMPONENT_Y, ctu->getTransformIdx(partQ)) != 0 || ctu->getCbf(partP, COMPONENT_Y, ctu->getTransformIdx(partP)) != 0)) return 1;
-  TComCUMvField* f0 = ctu->getCUMvField(REF_PIC_LIST_0);
-  int r = f0->getRefIdx(partP);
-  const TComPic* refP0 = r < 0 ? NULL : slice->getRefPic(REF_PIC_LIST_0, r);
-  r = f0->getRefIdx(partQ);
-  const TComPic* refQ0 = r < 0 ? NULL : slice->getRefPic(REF_PIC_LIST_0, r);
+  if (cuP->isIntra(partP) || cuQ->isIntra(partQ)) return 2;
+  if (tuEdge && (cuQ->getCbf(partQ, COMPONENT_Y, cuQ->getTransformIdx(partQ)) != 0 || cuP->getCbf(partP, COMPONENT_Y, cuP->getTransformIdx(partP)) != 0)) return 1;
+  TComSlice* sliceQ = cuQ->getSlice();
+  TComSlice* sliceP = cuP->getSlice();
+  TComCUMvField* fP0 = cuP->getCUMvField(REF_PIC_LIST_0);
+  TComCUMvField* fQ0 = cuQ->getCUMvField(REF_PIC_LIST_0);
+  int r = fP0->getRefIdx(partP);
+  const TComPic* refP0 = r < 0 ? NULL : sliceP->getRefPic(REF_PIC_LIST_0, r);
+  r = fQ0->getRefIdx(partQ);
+  const TComPic* refQ0 = r < 0 ? NULL : sliceQ->getRefPic(REF_PIC_LIST_0, r);
   const TComMv zero;
-  const TComMv& mvP0 = refP0 ? f0->getMv(partP) : zero;
-  const TComMv& mvQ0 = refQ0 ? f0->getMv(partQ) : zero;
-  if (!slice->isInterB()) return (refP0 != refQ0 || mvFar(mvQ0, mvP0)) ? 1 : 0;
-  TComCUMvField* f1 = ctu->getCUMvField(REF_PIC_LIST_1);
-  r = f1->getRefIdx(partP);
-  const TComPic* refP1 = r < 0 ? NULL : slice->getRefPic(REF_PIC_LIST_1, r);
-  r = f1->getRefIdx(partQ);
-  const TComPic* refQ1 = r < 0 ? NULL : slice->getRefPic(REF_PIC_LIST_1, r);
-  const TComMv& mvP1 = refP1 ? f1->getMv(partP) : zero;
-  const TComMv& mvQ1 = refQ1 ? f1->getMv(partQ) : zero;
+  const TComMv& mvP0 = refP0 ? fP0->getMv(partP) : zero;
+  const TComMv& mvQ0 = refQ0 ? fQ0->getMv(partQ) : zero;
+  if (!sliceQ->isInterB() && !sliceP->isInterB()) return (refP0 != refQ0 || mvFar(mvQ0, mvP0)) ? 1 : 0;
+  TComCUMvField* fP1 = cuP->getCUMvField(REF_PIC_LIST_1);
+  TComCUMvField* fQ1 = cuQ->getCUMvField(REF_PIC_LIST_1);
+  r = fP1->getRefIdx(partP);
+  const TComPic* refP1 = r < 0 ? NULL : sliceP->getRefPic(REF_PIC_LIST_1, r);
+  r = fQ1->getRefIdx(partQ);
+  const TComPic* refQ1 = r < 0 ? NULL : sliceQ->getRefPic(REF_PIC_LIST_1, r);
+  const TComMv& mvP1 = refP1 ? fP1->getMv(partP) : zero;
+  const TComMv& mvQ1 = refQ1 ? fQ1->getMv(partQ) : zero;
   if (!((refP0 == refQ0 && refP1 == refQ1) || (refP0 == refQ1 && refP1 == refQ0))) return 1;     // different reference pictures
   if (refP0 != refP1)                                                                              // two distinct pictures: match the lists up
     return (refP0 == refQ0) ? ((mvFar(mvQ0, mvP0) || mvFar(mvQ1, mvP1)) ? 1 : 0) : ((mvFar(mvQ1, mvP0) || mvFar(mvQ0, mvP1)) ? 1 : 0);
@@ -666,7 +675,6 @@ void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, T
   const int cuY = ctu->getCUPelY() + g_auiRasterToPelY[g_auiZscanToRaster[absZorderIdx]];
   const int cuSize = g_uiMaxCUWidth >> depth;
   static const bool fastBs = getenv("HMDEC_B200_HM_BS") == NULL;     // HMDEC_B200_HM_BS=1: HM's routine for every unit
-  TComSlice* slice = ctu->getSlice();
   const unsigned numPartInWidth = pic->getNumPartInWidth();
   for (int dir = 0; dir < 2; dir++)
   {
@@ -690,8 +698,22 @@ void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, T
       if (lf->m_aapbEdgeFilter[dir][part])
       {
         unsigned bs;
-        const bool inside = fastBs && ((dir == EDGE_VER) ? ux > 0 : uy > 0);
-        if (inside) bs = bsInsideCtu(ctu, slice, part, g_auiRasterToZscan[raster - (dir == EDGE_VER ? 1 : numPartInWidth)], lf->m_aapucBS[dir][part] != 0);
+        if (fastBs)
+        {
+          TComDataCU* cuP = ctu;
+          unsigned partP;
+          if (dir == EDGE_VER)
+          {
+            if (ux > 0) partP = g_auiRasterToZscan[raster - 1];
+            else { cuP = ctu->getCULeft(); partP = g_auiRasterToZscan[raster + numPartInWidth - 1]; }
+          }
+          else
+          {
+            if (uy > 0) partP = g_auiRasterToZscan[raster - numPartInWidth];
+            else { cuP = ctu->getCUAbove(); partP = g_auiRasterToZscan[raster + pic->getNumPartInCU() - numPartInWidth]; }
+          }
+          bs = bsOfUnit(cuP, partP, ctu, part, lf->m_aapucBS[dir][part] != 0);
+        }
         else
         {
           lf->xGetBoundaryStrengthSingle(ctu, DeblockEdgeDir(dir), part);
@@ -718,23 +740,31 @@ void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, T
     }
 }
 
-void HmEmitter::deblockInfo(TComPic* pic, TComLoopFilter* lf)
+// Deblocking side info of one CTU, right after it was parsed (HM derives it for the whole picture at the end, TComLoopFilter.cpp:
+// 130-155, when every CTU's arrays have long left the caches): edge flags with HM's own xSetLoopfilterParam / xSetEdgefilterTU /
+// xSetEdgefilterPU on an emitter-owned TComLoopFilter, strengths with bsOfUnit.  Only the left and the above CTU are consulted and
+// both precede this one in decoding order (also across tiles: the tile to the left / above is decoded first).
+void HmEmitter::deblockCtu(TComDataCU* ctu)
 {
-  bool any = false;
-  for (UInt a = 0; a < pic->getNumCUsInFrame(); a++)
+  if (!m_lf || m_lfDepth != g_uiMaxCUDepth)
   {
-    TComDataCU* ctu = pic->getCU(a);
-    ::memset(lf->m_aapucBS[EDGE_VER], 0, sizeof(UChar) * lf->m_uiNumPartitions);
-    ::memset(lf->m_aapbEdgeFilter[EDGE_VER], 0, sizeof(Bool) * lf->m_uiNumPartitions);
-    ::memset(lf->m_aapucBS[EDGE_HOR], 0, sizeof(UChar) * lf->m_uiNumPartitions);
-    ::memset(lf->m_aapbEdgeFilter[EDGE_HOR], 0, sizeof(Bool) * lf->m_uiNumPartitions);
-    bsWalk(ctu, 0, 0, lf);
-    TComSlice* s = ctu->getSlice();
-    m_ctu[a].beta_offset_div2 = (int8_t)s->getDeblockingFilterBetaOffsetDiv2();
-    m_ctu[a].tc_offset_div2   = (int8_t)s->getDeblockingFilterTcOffsetDiv2();
-    if (!s->getDeblockingFilterDisable()) any = true;
+    if (m_lf) { m_lf->destroy(); delete m_lf; }
+    m_lf = new TComLoopFilter;
+    m_lf->create(g_uiMaxCUDepth);
+    m_lfDepth = g_uiMaxCUDepth;
   }
-  if (any) m_hdr.flags |= HMR_FRM_DEBLOCK;
+  TComLoopFilter* lf = m_lf;
+  TComSlice* s = ctu->getSlice();
+  lf->setCfg(s->getPPS()->getLoopFilterAcrossTilesEnabledFlag());
+  ::memset(lf->m_aapucBS[EDGE_VER], 0, sizeof(UChar) * lf->m_uiNumPartitions);
+  ::memset(lf->m_aapbEdgeFilter[EDGE_VER], 0, sizeof(Bool) * lf->m_uiNumPartitions);
+  ::memset(lf->m_aapucBS[EDGE_HOR], 0, sizeof(UChar) * lf->m_uiNumPartitions);
+  ::memset(lf->m_aapbEdgeFilter[EDGE_HOR], 0, sizeof(Bool) * lf->m_uiNumPartitions);
+  bsWalk(ctu, 0, 0, lf);
+  const UInt a = ctu->getAddr();
+  m_ctu[a].beta_offset_div2 = (int8_t)s->getDeblockingFilterBetaOffsetDiv2();
+  m_ctu[a].tc_offset_div2   = (int8_t)s->getDeblockingFilterTcOffsetDiv2();
+  if (!s->getDeblockingFilterDisable()) m_anyDeblock = true;
 }
 
 // SAO side info: reconstructBlkSAOParams (TComSampleAdaptiveOffset.cpp:348-372) then per-CTU flattening
@@ -780,8 +810,8 @@ void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdap
   if (!m_open || pic != m_curPic) { fail("filterPicture for a picture with no parsed CTU"); return; }
   const double t0 = nowSec();
   TComSlice* slice = pic->getSlice(pic->getCurrSliceIdx());
-  lf->setCfg(lfCrossTiles);
-  deblockInfo(pic, lf);
+  if (getenv("HMDEC_B200_BS_AT_END")) for (UInt a = 0; a < pic->getNumCUsInFrame(); a++) deblockCtu(pic->getCU(a));
+  if (m_anyDeblock) m_hdr.flags |= HMR_FRM_DEBLOCK;              // the maps were filled CTU by CTU (deblockCtu)
   const double t1 = nowSec();
   if (slice->getSPS()->getUseSAO()) saoInfo(pic, sao);
   if (slice->getSPS()->getUsePCM()) { /* PCM CUs themselves are rejected in emitIntraCU */ }

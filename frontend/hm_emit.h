@@ -78,12 +78,15 @@ private:
   void intraQT(CuCtx& c, int chType, void* rTu);
   void intraBlk(CuCtx& c, int compID, void* rTu);
   uint32_t emitResidualTU(CuCtx& c, int compID, void* rTu, bool intra, bool coded, int alpha);
-  void deblockInfo(TComPic* pic, TComLoopFilter* lf);
+  void deblockCtu(TComDataCU* ctu);
   void bsWalk(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, TComLoopFilter* lf);
   void saoInfo(TComPic* pic, TComSampleAdaptiveOffset* sao);
   void fail(const char* what);
 
   HmFrameSink* m_sink;
+  TComLoopFilter* m_lf;              // own instance: HM's edge-flag machinery, run per CTU while the CTU is still in cache
+  unsigned     m_lfDepth;
+  bool         m_anyDeblock;
   TComPic*     m_curPic;
   bool         m_open;
   const char*  m_unsupported;
