@@ -29,7 +29,10 @@
 //     smoothing -> prediction (main-reference projection folded into the index) -> + residual -> back into the tile,
 //     with warp-level synchronisation only;
 //   * a tile is written back once, coalesced.  Cross-CTA reads go through L2 (ld.global.cg); the producer fences before
-//     publishing.
+//     publishing;
+//   * shared memory is sized by the largest CTU of the picture (records, address-table entries, residual span: measured
+//     on the host records, intra_sizes_host): a resident CTA holds its buffers for the whole wavefront while issuing
+//     almost nothing, and with several bitstreams on one GPU that footprint is what the other streams' kernels wait for.
 #include "common.cuh"
 
 #define IN_THREADS 128

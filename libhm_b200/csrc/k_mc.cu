@@ -4,15 +4,18 @@
 // (TComPrediction.cpp:514-698), TComInterpolationFilter::filter / filterCopy (TComInterpolationFilter.cpp:94-251)
 // and TComYuv::addAvg (TComYuv.cpp:336-391).
 //
-// Work unit: one 16x16-luma tile of a PU (plus the co-located chroma tiles), owned by ONE WARP — no block-level
-// synchronisation anywhere.  A tiny pre-pass (mc_expand_kernel) turns the PU records into one 16-byte record per tile
-// so that the main kernel needs a single dependent load before it can fetch samples.
+// Work unit: one 16x16-luma tile of a PU, owned by ONE WARP — no block-level synchronisation anywhere.  A tiny pre-pass
+// (mc_expand_kernel) turns the PU records into one 16-byte record per tile so that the main kernels need a single
+// dependent load before they can fetch samples.  Two main launches per picture: mc_kernel<true> predicts the luma tile,
+// mc_kernel<false> the two co-located chroma tiles (half the shared memory per warp each: the kernels wait on memory,
+// and warps in flight are what hides it).  Cb and Cr of an 8-wide chroma tile (4:2:0, 4:2:2) have the same geometry,
+// phases and taps: they are staged together (16 lanes each) and filtered together (half of the active lanes each).
 //
-// Per tile: every reference window (luma + 2 chroma, up to 2 lists = 6 windows) is fetched up front with 16-byte
-// cp.async copies that are all in flight together (rows start at the 16-byte boundary below the window; the
-// sub-alignment `off` is handled when reading shared memory).  Windows that touch the picture border are gathered with
-// clamped coordinates instead, which is exactly HM's replicated border (TComPicYuv::extendPicBorder,
-// TComPicYuv.cpp:173-217) without ever materialising it.
+// Per tile: every reference window (up to 2 lists; chroma: x 2 planes) is fetched up front with 16-byte cp.async copies
+// that are all in flight together — only the vectors the window touches, rounds unrolled and row-predicated (rows start
+// at the 16-byte boundary below the window; the sub-alignment `off` is handled when reading shared memory).  Windows
+// that touch the picture border are gathered with clamped coordinates instead, which is exactly HM's replicated
+// border (TComPicYuv::extendPicBorder, TComPicYuv.cpp:173-217) without ever materialising it.
 //
 // Arithmetic: every case of HM (copy / H only / V only / H+V, uni / bi) is ONE separable pipeline
 // H -> 14-bit intermediate -> V with the identity tap set for a zero fraction; that is bit-identical to HM's special
