@@ -3,11 +3,13 @@
 // libHMDEC_get_internal_info.  The library is dlopen'ed, so the same binary drives the reference wrapper
 // (oracle/_ref/liblibHMDecoderStatic.so) and this repository's drop-in; tests compare the two dumps byte for byte.
 //   hmdec_internals <library.so> <in.bin> <out.txt> [--backend N ARG]     (--backend: libHMDecB200_new_decoder_ex, drop-in only)
+// HMDEC_INTERNALS_TIME=1: do not print the block lists, report the time spent inside libHMDEC_get_internal_info instead.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <dlfcn.h>
+#include <chrono>
 #include "libHMDecoder_api.h"
 #include "annexb.h"
 
@@ -38,7 +40,9 @@ int main(int argc, char** argv)
   splitAnnexB(stream, nals);
   FILE* out = fopen(argv[3], "w");
   if (!out) { perror(argv[3]); return 2; }
-  long pictures = 0;
+  long pictures = 0, blocks = 0;
+  double secInfo = 0, secType[24] = {0};
+  const bool timeOnly = getenv("HMDEC_INTERNALS_TIME") != NULL;
   for (size_t k = 0; k < nals.size();)
   {
     bool newPicture = false, checkOutput = false;
@@ -60,9 +64,12 @@ int main(int argc, char** argv)
         }
         for (int type = LIBHMDEC_CTU_SLICE_INDEX; type <= LIBHMDEC_TU_COEFF_ENERGY_CR; type++)
         {
+          const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
           std::vector<libHMDec_BlockValue>* v = p_libHMDEC_get_internal_info(dec, pic, (libHMDec_info_type)type);
+          { const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); secInfo += dt; secType[type] += dt; }
+          if (v) blocks += (long)v->size();
           fprintf(out, " type %d n %ld\n", type, v ? (long)v->size() : -1L);
-          if (v) for (size_t i = 0; i < v->size(); i++)
+          if (v && !timeOnly) for (size_t i = 0; i < v->size(); i++)
           {
             const libHMDec_BlockValue& b = (*v)[i];
             // value2 is only defined for the motion-vector types (the reference leaves it uninitialised elsewhere)
@@ -76,6 +83,7 @@ int main(int argc, char** argv)
   }
   fclose(out);
   p_libHMDec_free_decoder(dec);
-  printf("%ld pictures\n", pictures);
+  printf("%ld pictures, %ld blocks reported, %.3f s inside libHMDEC_get_internal_info\n", pictures, blocks, secInfo);
+  if (timeOnly) { printf("ms per type:"); for (int t = 0; t < 24; t++) printf(" %d:%.1f", t, 1e3 * secType[t]); printf("\n"); }
   return 0;
 }

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <list>
 #include <iostream>
 #include "TLibCommon/CommonDef.h"
@@ -113,10 +114,14 @@ void tuEntries(Out& out, TComDataCU* ctu, UInt part, UInt depth, UInt trDepth, l
       // a partition's levels are defined iff its own leaf TU is coded: cbf bit at the leaf's transform depth (4:2:2 chroma:
       // one level deeper, the two square halves of a TU carry separate flags)
       const UInt deeper = (c != COMPONENT_Y && ctu->getPic()->getChromaFormat() == CHROMA_422) ? 1 : 0;
-      for (int i = 0; i < n; i++)
+      const UChar* cbf = ctu->getCbf(c);
+      const UChar* trIdx = ctu->getTransformIdx();
+      for (int p = 0; p * perPart < n; p++)                  // partition by partition: one flag test per 4x4 unit, not per level
       {
-        const UInt p = (UInt)(i / perPart);
-        if (ctu->getCbf(p, c, ctu->getTransformIdx(p) + deeper) != 0) e += (int64_t)(co[i] * co[i]);
+        if (((cbf[p] >> (trIdx[p] + deeper)) & 1) == 0) continue;
+        const TCoeff* q = co + p * perPart;
+        const int m = std::min(perPart, n - p * perPart);
+        for (int i = 0; i < m; i++) e += (int64_t)(q[i] * q[i]);
       }
       b.value = e > MAX_INT ? MAX_INT : (int)e;
       break;
