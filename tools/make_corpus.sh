@@ -35,6 +35,7 @@ JOBS=(
  "s_dqp_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 33 --MaxDeltaQP=3 --MaxCuDQPDepth=2 --CbQpOffset=3 --CrQpOffset=-2 --LoopFilterOffsetInPPS=1 --LoopFilterBetaOffset_div2=2 --LoopFilterTcOffset_div2=-1 -q 30"
  "s_ra444_240p       encoder_randomaccess_main_rext.cfg    416  240  9  8  444 34 --InternalBitDepth=8 -q 27"
  "s_nolf_240p        encoder_randomaccess_main.cfg         416  240  9  8  420 35 --SAO=0 --LoopFilterDisable=1 -q 30"
+ "s_tiles2_240p      encoder_randomaccess_main.cfg         640  256  9  8  420 36 --TileUniformSpacing=1 --NumTileColumnsMinus1=1 --NumTileRowsMinus1=1 --LFCrossTileBoundaryFlag=1 -q 30"
  "s_wpp_240p         encoder_lowdelay_P_main.cfg           416  240  9  8  420 23 --WeightedPredP=1 -q 30"
  "s_wpb_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 24 --WeightedPredB=1 --WeightedPredP=1 -q 30"
  "c2_ra8_1080p       encoder_randomaccess_main.cfg         1920 1080 64 8  420 2"
