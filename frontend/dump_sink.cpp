@@ -21,7 +21,13 @@ class DumpSink : public HmFrameSink
 public:
   // HMDUMP_RECORDS_ONLY=1: the product's fast parse path (no HM reconstruction, coefficient hygiene on), records only —
   // lets a CPU-only test prove that the fast path emits byte-identical records.
-  explicit DumpSink(const char* path) : m_fp(fopen(path, "wb")), m_planes(getenv("HMDUMP_PLANES") != NULL), m_recordsOnly(getenv("HMDUMP_RECORDS_ONLY") != NULL)
+  // The product library (no HMDEC_WITH_HM_RECON) cannot reconstruct on the CPU at all: its dumps are always records only.
+#ifdef HMDEC_WITH_HM_RECON
+#define HMDUMP_RECORDS_ONLY_DEFAULT (getenv("HMDUMP_RECORDS_ONLY") != NULL)
+#else
+#define HMDUMP_RECORDS_ONLY_DEFAULT true
+#endif
+  explicit DumpSink(const char* path) : m_fp(fopen(path, "wb")), m_planes(getenv("HMDUMP_PLANES") != NULL), m_recordsOnly(HMDUMP_RECORDS_ONLY_DEFAULT)
   {
     if (!m_fp) { perror(path); abort(); }
     fwrite("HMRDUMP1", 1, 8, m_fp);
@@ -40,7 +46,7 @@ public:
     if (n & 7) fwrite(zeros, 1, 8 - (n & 7), m_fp);
   }
 
-  virtual void frameReady(const hmr_frame_desc& d, TComPic*)
+  virtual bool frameReady(const hmr_frame_desc& d, TComPic*)
   {
     const hmr_frame_hdr& h = *d.hdr;
     const size_t nbs = (size_t)((h.width + 3) >> 2) * ((h.height + 3) >> 2);
@@ -59,6 +65,7 @@ public:
     if (d.scaling) section(TAG('S','C','A','L'), d.scaling, HMR_SCALING_BYTES);
     if (d.wp) { section(TAG('W','P',' ',' '), d.wp, sizeof(hmr_wp) * HMR_WP_ENTRIES); section(TAG('P','U','R','I'), d.pu_refidx, h.n_pu); }
     if (m_recordsOnly) { section(TAG('E','N','D',' '), NULL, 0); fflush(m_fp); }
+    return true;
   }
 
   virtual void fetchPicture(TComPic*) {}
@@ -103,7 +110,7 @@ HmFrameSink* hm_new_dump_sink(const char* path) { return new DumpSink(path); }
 class NullSink : public HmFrameSink
 {
 public:
-  virtual void frameReady(const hmr_frame_desc&, TComPic*) {}
+  virtual bool frameReady(const hmr_frame_desc&, TComPic*) { return true; }
   virtual void fetchPicture(TComPic*) {}
   virtual bool wantHmRecon() const { return false; }
 };

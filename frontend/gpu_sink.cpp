@@ -47,7 +47,13 @@ void pooledPinnedFree(void* p)
 class GpuSink : public HmFrameSink
 {
 public:
-  GpuSink() : m_eng(NULL), m_verify(getenv("HMDEC_B200_VERIFY") != NULL), m_eager(getenv("HMDEC_B200_LAZY_PLANES") == NULL),
+  // m_verify (HM's CPU reconstruction next to the engine) exists in libHMDecoder_b200_verify.so only; the product has no CPU reconstruction
+#ifdef HMDEC_WITH_HM_RECON
+#define HMDEC_VERIFY_REQUESTED (getenv("HMDEC_B200_VERIFY") != NULL)
+#else
+#define HMDEC_VERIFY_REQUESTED false
+#endif
+  GpuSink() : m_eng(NULL), m_verify(HMDEC_VERIFY_REQUESTED), m_eager(getenv("HMDEC_B200_LAZY_PLANES") == NULL),
               m_gpuMd5(getenv("HMDEC_B200_HOST_MD5") == NULL), m_mismatch(false), m_jobs(0)
   {
     int dev = 0;
@@ -62,13 +68,23 @@ public:
   ~GpuSink() { drainHashes(true); releaseHostBuffers(); if (m_eng) hmr_engine_destroy(m_eng); }
   bool ok() const { return m_eng != NULL; }
 
-  virtual void frameReady(const hmr_frame_desc& d, TComPic* pic)
+  // A failing engine call never takes the host process down: the sink latches the message (error()), the emitter stops
+  // submitting and libHMDec_push_nal_unit answers LIBHMDEC_ERROR from then on.
+  bool engineFailed(const char* call)
   {
-    if (hmr_submit_frame(m_eng, &d) != HMR_OK)
+    if (m_error.empty())
     {
-      fprintf(stderr, "hmdec_b200: hmr_submit_frame failed: %s\n", hmr_error_string(m_eng));
-      abort();
+      m_error = std::string(call) + ": " + hmr_error_string(m_eng);
+      fprintf(stderr, "hmdec_b200: %s\n", m_error.c_str());
     }
+    return false;
+  }
+  virtual const char* error() const { return m_error.empty() ? NULL : m_error.c_str(); }
+
+  virtual bool frameReady(const hmr_frame_desc& d, TComPic* pic)
+  {
+    if (!m_error.empty()) return false;
+    if (hmr_submit_frame(m_eng, &d) != HMR_OK) return engineFailed("hmr_submit_frame");
     State& s = m_state[pic];
     s.slot = d.hdr->out_slot;
     s.hostStale = true;
@@ -90,6 +106,7 @@ public:
     }
     // the engine clamps coordinates instead of padding: spare HM the per-reference extendPicBorder() (TComSlice.cpp:350-376)
     if (!m_verify) pic->getPicYuvRec()->setBorderExtension(true);   // (HM's own CPU MC in verify mode needs the real border)
+    return true;
   }
 
   virtual void fetchPicture(TComPic* pic)
@@ -98,7 +115,7 @@ public:
     if (it == m_state.end() || !it->second.hostStale) return;
     if (it->second.copyIssued)
     {
-      if (hmr_marker_wait(m_eng, it->second.marker) != HMR_OK) { fprintf(stderr, "hmdec_b200: hmr_marker_wait failed: %s\n", hmr_error_string(m_eng)); abort(); }
+      if (hmr_marker_wait(m_eng, it->second.marker) != HMR_OK) { engineFailed("hmr_marker_wait"); return; }
       it->second.hostStale = false;
       return;
     }
@@ -109,11 +126,7 @@ public:
       const ComponentID id = ComponentID(c);
       const int w = rec->getWidth(id), h = rec->getHeight(id), st = rec->getStride(id);
       if (m_verify) { keep.resize((size_t)w * h); for (int y = 0; y < h; y++) memcpy(&keep[(size_t)y * w], rec->getAddr(id) + (size_t)y * st, sizeof(Pel) * w); }
-      if (hmr_read_plane(m_eng, it->second.slot, c, rec->getAddr(id), (size_t)st) != HMR_OK)
-      {
-        fprintf(stderr, "hmdec_b200: hmr_read_plane failed: %s\n", hmr_error_string(m_eng));
-        abort();
-      }
+      if (hmr_read_plane(m_eng, it->second.slot, c, rec->getAddr(id), (size_t)st) != HMR_OK) { engineFailed("hmr_read_plane"); return; }
       if (m_verify)
         for (int y = 0; y < h; y++)
           if (memcmp(&keep[(size_t)y * w], rec->getAddr(id) + (size_t)y * st, sizeof(Pel) * w))
@@ -181,8 +194,16 @@ private:
       unsigned char got[48];
       const int r = hmr_md5_result(m_eng, p.job, got, wait ? 1 : 0);
       if (r == HMR_PENDING) return false;
-      if (r != HMR_OK) { fprintf(stderr, "hmdec_b200: hmr_md5_result failed: %s\n", hmr_error_string(m_eng)); abort(); }
       m_jobs--;
+      if (r != HMR_OK)
+      {
+        // the digest was lost (device error): the picture cannot be verified — report it like a mismatch, keep the order
+        engineFailed("hmr_md5_result");
+        m_mismatch = true;
+        if (!p.quiet) printf("%s[MD5:<device error>,(***ERROR***)] \n", p.line.c_str());
+        m_pending.pop_front();
+        return true;
+      }
       TComDigest dg, rx;
       dg.hash.assign(got, got + 16 * p.ncomp);
       rx.hash = p.expected;
@@ -203,6 +224,7 @@ private:
   hmr_engine* m_eng;
   bool m_verify;
   bool m_eager, m_gpuMd5, m_mismatch;
+  std::string m_error;
   int m_jobs;
   std::map<TComPic*, State> m_state;
   std::deque<Pending> m_pending;

@@ -48,6 +48,7 @@ Int  isBelowLeftAvailable ( TComDataCU* pcCU, UInt uiPartIdxLT, UInt uiPartIdxLB
 static thread_local HmEmitter* t_current = NULL;
 void       hm_emit_set_current(HmEmitter* e) { t_current = e; }
 HmEmitter* hm_emit_current()                 { return t_current; }
+void       hm_emit_release_slot(TComPic* pic) { if (t_current) t_current->releaseSlot(pic); }
 
 struct HmEmitter::CuCtx
 {
@@ -84,14 +85,27 @@ void HmEmitter::fail(const char* what)
   }
 }
 
+// DPB slot of a picture buffer.  A slot lives as long as the TComPic it was handed to: hm_fast.cpp reports every buffer it
+// destroys (stale geometry after a resolution switch) through releaseSlot(), and the number goes back on a free list.
+// More than HMR_MAX_SLOTS live buffers is a hard decode error (the decoder stops; LIBHMDEC_ERROR), never an alias.
 int HmEmitter::slotOf(TComPic* pic)
 {
   std::map<TComPic*, int>::iterator it = m_slots.find(pic);
   if (it != m_slots.end()) return it->second;
-  int s = (int)m_slots.size();
-  if (s >= HMR_MAX_SLOTS) { fail("more than HMR_MAX_SLOTS DPB entries"); s = HMR_MAX_SLOTS - 1; }
+  int s;
+  if (!m_freeSlots.empty()) { s = m_freeSlots.back(); m_freeSlots.pop_back(); }
+  else s = (int)m_slots.size();
+  if (s >= HMR_MAX_SLOTS) { fail("more than HMR_MAX_SLOTS DPB entries"); return HMR_MAX_SLOTS - 1; }   // not recorded: nothing is submitted any more
   m_slots[pic] = s;
   return s;
+}
+
+void HmEmitter::releaseSlot(TComPic* pic)
+{
+  std::map<TComPic*, int>::iterator it = m_slots.find(pic);
+  if (it == m_slots.end()) return;
+  m_freeSlots.push_back(it->second);
+  m_slots.erase(it);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -851,7 +865,12 @@ void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdap
   d.qp = m_qp.data();
   d.cu_flags = (m_hdr.flags & HMR_FRM_HAS_NOFILTER) ? m_cuFlags.data() : NULL;
   const double t2 = nowSec();
-  m_sink->frameReady(d, pic);
+  // once anything was flagged the records may be wrong: nothing reaches the engine any more, push_nal_unit reports LIBHMDEC_ERROR
+  if (!m_unsupported && !m_sink->frameReady(d, pic))
+  {
+    m_failText = std::string("the reconstruction engine rejected the picture: ") + (m_sink->error() ? m_sink->error() : "unknown error");
+    fail(m_failText.c_str());
+  }
   const double t3 = nowSec();
   m_tBs += t1 - t0; m_tPic += t2 - t1; m_tSink += t3 - t2; m_nPic++;
   m_open = false;

@@ -24,7 +24,10 @@ struct HmFrameSink
 {
   virtual ~HmFrameSink() {}
   // Called once all CTUs of the picture are parsed and the loop-filter side info is known.
-  virtual void frameReady(const hmr_frame_desc& desc, TComPic* pic) = 0;
+  // false = the sink could not take the picture (error() says why); the decoder then stops and reports LIBHMDEC_ERROR.
+  virtual bool frameReady(const hmr_frame_desc& desc, TComPic* pic) = 0;
+  // NULL, or why the sink stopped working (device error, rejected picture).  Sticky.
+  virtual const char* error() const { return NULL; }
   // Make HM's own TComPicYuv of `pic` hold the final reconstruction (D2H for the GPU sink; no-op when
   // HM reconstructed on the CPU).  Needed before the SEI hash check / plane access.
   virtual void fetchPicture(TComPic* pic) = 0;
@@ -63,6 +66,7 @@ public:
   void onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdaptiveOffset* sao, bool lfCrossTiles); // splice at TDecGop.cpp:157
   HmFrameSink* sink() { return m_sink; }
   int  slotOf(TComPic* pic);
+  void releaseSlot(TComPic* pic);                                         // the picture buffer is gone (hm_fast.cpp): its DPB slot is free again
   const char* unsupported() const { return m_unsupported; }
   bool cleanCoeffs() const { return m_cleanCoeffs; }
   HmPrefetchCursor m_prefetch;                                            // CTU metadata prefetch (hm_fast.h)
@@ -91,6 +95,8 @@ private:
   bool         m_open;
   const char*  m_unsupported;
   std::map<TComPic*, int> m_slots;
+  std::vector<int> m_freeSlots;      // slot numbers whose picture buffer was destroyed
+  std::string  m_failText;
 
   hmr_frame_hdr                    m_hdr;
   std::vector<hmr_tu>              m_tu;
@@ -117,6 +123,7 @@ private:
 // The emitter the hooks (TDecCu::decompressCU / TDecGop::filterPicture replacements) talk to.
 // Set by the wrapper around every TDecTop call; one decoder per thread.
 void       hm_emit_set_current(HmEmitter* e);
+void       hm_emit_release_slot(TComPic* pic);   // no-op without a current emitter
 HmEmitter* hm_emit_current();
 
 #endif

@@ -44,6 +44,7 @@
 #include "TLibDecoder/TDecTop.h"
 #undef private
 #undef protected
+#include "hm_emit.h"
 #include "hm_fast.h"
 
 static thread_local bool t_skipCoeffFill = false;
@@ -215,18 +216,41 @@ static void remember(TDecTop* dec, TComPic* pic)
   g_created[dec].push_back(pic);
 }
 
-// A picture of this decoder that is no longer in its DPB list (dropped by a flush), or NULL.
-static TComPic* findOrphan(TDecTop* dec, TComList<TComPic*>& list)
+static bool sameGeometry(TComPic* pic, TComSPS* sps);
+
+// A picture of this decoder that is no longer in its DPB list (dropped by a flush) and has the geometry of `sps`, or NULL.
+// Orphans of ANOTHER geometry (the stream switched resolution at an IRAP) can never be reused by this decoder again: they are
+// destroyed here, their planes go back to the pool and their DPB slot is released (HmEmitter::releaseSlot), so a stream that
+// keeps switching neither leaks picture buffers nor runs out of slots.
+static TComPic* findOrphan(TDecTop* dec, TComList<TComPic*>& list, TComSPS* sps)
 {
-  std::lock_guard<std::mutex> g(g_createdLock);
-  std::vector<TComPic*>& v = g_created[dec];
-  for (size_t i = 0; i < v.size(); i++)
+  std::vector<TComPic*> stale;
+  TComPic* hit = NULL;
   {
-    bool listed = false;
-    for (TComList<TComPic*>::iterator it = list.begin(); it != list.end() && !listed; ++it) listed = (*it == v[i]);
-    if (!listed) return v[i];
+    std::lock_guard<std::mutex> g(g_createdLock);
+    std::vector<TComPic*>& v = g_created[dec];
+    for (size_t i = 0; i < v.size() && !hit;)
+    {
+      bool listed = false;
+      for (TComList<TComPic*>::iterator it = list.begin(); it != list.end() && !listed; ++it) listed = (*it == v[i]);
+      if (listed) { i++; continue; }
+      if (sameGeometry(v[i], sps)) { hit = v[i]; break; }
+      stale.push_back(v[i]);
+      v.erase(v.begin() + i);
+    }
   }
-  return NULL;
+  if (!stale.empty())
+    if (HmEmitter* e = hm_emit_current()) e->sink()->releaseHostBuffers();   // no DMA may still target the planes given back below
+  for (size_t i = 0; i < stale.size(); i++)
+  {
+    TComPic* pic = stale[i];
+    forgetMotion(pic);
+    hm_emit_release_slot(pic);
+    if (pic->getPicYuvRec()) releasePlanes(pic->getPicYuvRec());
+    pic->destroy();
+    delete pic;
+  }
+  return hit;
 }
 
 void hm_fast_release_decoder(TDecTop* dec)
@@ -306,8 +330,8 @@ Void TDecTop::xGetNewPicBuffer(TComSlice* pcSlice, TComPic*& rpcPic)
   m_iMaxRefPicNum = sps->getMaxDecPicBuffering(pcSlice->getTLayer());   // includes the picture being decoded
   if (m_cListPic.size() < (UInt)m_iMaxRefPicNum)
   {
-    rpcPic = findOrphan(this, m_cListPic);                   // a buffer the last flush dropped from the list
-    if (rpcPic && sameGeometry(rpcPic, sps))
+    rpcPic = findOrphan(this, m_cListPic, sps);              // a buffer the last flush dropped from the list
+    if (rpcPic)
     {
       rpcPic->setOutputMark(false); rpcPic->setReconMark(false);
       resetPicture(rpcPic, conf, disp, reorder);

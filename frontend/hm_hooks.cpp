@@ -20,8 +20,10 @@
 #include "hm_emit.h"
 #include "hm_fast.h"
 
-extern Bool g_md5_mismatch;
-void hm_call_original_decompressCU(TDecCu* dec, TComDataCU* ctu);
+extern thread_local Bool g_md5_mismatch;
+#ifdef HMDEC_WITH_HM_RECON
+void hm_call_original_decompressCU(TDecCu* dec, TComDataCU* ctu);     // hm_shim.cpp (libHMDecoder_b200_verify.so only)
+#endif
 
 static HmEmitter* requireEmitter()
 {
@@ -38,7 +40,9 @@ Void TDecCu::decompressCU(TComDataCU* pcCU)
 {
   HmEmitter* e = requireEmitter();
   e->onCtuParsed(pcCU);
+#ifdef HMDEC_WITH_HM_RECON
   if (e->sink()->wantHmRecon()) hm_call_original_decompressCU(this, pcCU);
+#endif
 }
 
 // Status line + SEI hash check, same text as TDecGop::filterPicture / calcAndPrintHashStatus (TDecGop.cpp:176-289).
@@ -124,6 +128,7 @@ Void TDecGop::filterPicture(TComPic*& rpcPic)
   // boundary strengths need the full-resolution motion field => before compressMotion()
   e->onPictureParsed(rpcPic, m_pcLoopFilter, m_pcSAO, lfCrossTiles);
 
+#ifdef HMDEC_WITH_HM_RECON
   if (e->sink()->wantHmRecon())
   {
     // verification / golden generation: HM's own CPU filters, stage by stage (TDecGop.cpp:165-174)
@@ -139,6 +144,7 @@ Void TDecGop::filterPicture(TComPic*& rpcPic)
     }
     e->sink()->hmStage(2, rpcPic);
   }
+#endif
 
   // TMVP storage (TDecGop.cpp:176): never rewritten — xGetColMVP reads the uncompressed field at the 16x16 run start
   // (hm_fast_memset.h: hm_fast_col_part); only libHMDEC_get_internal_info compresses, on demand

@@ -25,17 +25,19 @@
 #include <malloc.h>
 #define private public
 #include "TLibCommon/TComSlice.h"
-#undef private
 #include "TLibCommon/CommonDef.h"
 #include "TLibCommon/TComTU.h"
 #include "TLibDecoder/TDecTop.h"
+#undef private
 #include "TLibDecoder/NALread.h"
 #include "libHMDecoder_api.h"
 #include "hm_emit.h"
 #include "hm_fast.h"
+#include "hm_threadsafe.h"
 
-// HM keeps the "hash mismatch seen" flag in a global that the application must define (TDecGop.cpp:48).
-bool g_md5_mismatch = false;
+// HM keeps the "hash mismatch seen" flag in a global that the application must define (TDecGop.cpp:48); thread_local in this
+// build (frontend/Makefile patches the declaration), saved and restored per decoder around every HM call.
+thread_local bool g_md5_mismatch = false;
 
 HmFrameSink* hm_new_dump_sink(const char* path);
 HmFrameSink* hm_new_null_sink();
@@ -67,13 +69,15 @@ struct Decoder
   bool  flushing;            // output everything that is marked, regardless of the bumping rule
   bool  flushAfterThisPass;  // eof: one normal pass, then a flush pass
   bool  hashMismatch;
+  bool  failed;              // sticky: an unsupported feature or an engine error was reported through LIBHMDEC_ERROR
   Int   prevTid0POC;         // per-decoder copy of TComSlice::m_prevTid0POC (thread_local in this build)
+  HmGeomKey geom;            // SPS-dependent HM globals this decoder runs under (hm_threadsafe.cpp); invalid before the first activation
   std::vector<libHMDec_BlockValue> internals;
 
   Decoder(HmFrameSink* s)
     : sink(s), emitter(new HmEmitter(s)), maxTemporalLayer(-1), lastDisplayedPoc(-MAX_INT), skipFrames(0), dpb(NULL),
       cursor(0), pendingOutput(0), dpbFullness(0), reorderLimit(0), bufferingLimit(0), loopFilterDone(false),
-      flushing(false), flushAfterThisPass(false), hashMismatch(false), prevTid0POC(0)
+      flushing(false), flushAfterThisPass(false), hashMismatch(false), failed(false), prevTid0POC(0)
   {
     top.create();
     top.init();
@@ -86,12 +90,14 @@ struct Decoder
       for (std::map<const void*, Decoder*>::iterator it = g_picOwner.begin(); it != g_picOwner.end();)
         if (it->second == this) g_picOwner.erase(it++); else ++it;
     }
+    if (geom.valid) hm_geom_enter(geom);        // HM's teardown walks structures sized by the CTU geometry
     hm_emit_set_current(emitter);
     sink->drainHashes(true);
     sink->releaseHostBuffers();          // nothing may still be DMA-ing into HM's planes
     hm_fast_release_decoder(&top);       // pooled planes go back; buffers dropped by a flush are freed
     top.destroy();
     hm_emit_set_current(NULL);
+    if (geom.valid) hm_geom_leave(geom);
     delete emitter;
     delete sink;
   }
@@ -122,6 +128,41 @@ struct Decoder
 };
 
 inline Decoder* D(libHMDec_context* c) { return (Decoder*)c; }
+
+// The geometry key of the last decoder this thread drove into HM: what the ctx-less libHMDEC_get_internal_bit_depth answers.
+thread_local HmGeomKey t_lastGeom;
+
+// The key a slice NAL is going to run under: first_slice_segment_in_pic_flag u(1), no_output_of_prior_pics_flag u(1) for IRAP
+// types, slice_pic_parameter_set_id ue(v) (7.3.6.1; at most 15 bits: no emulation-prevention byte can occur that early because
+// the second NAL header byte is never 0) -> PPS -> SPS, looked up where TDecTop keeps what it has parsed so far.
+HmGeomKey peekSliceGeometry(Decoder* d, const InputNALUnit& nalu, const std::vector<uint8_t>& bytes)
+{
+  if (bytes.size() < 4) return d->geom;
+  const unsigned w = ((unsigned)bytes[2] << 8) | bytes[3];
+  int pos = 15 - 1;                                                     // bit 15 = first_slice_segment_in_pic_flag
+  if (nalu.m_nalUnitType >= NAL_UNIT_CODED_SLICE_BLA_W_LP && nalu.m_nalUnitType <= NAL_UNIT_RESERVED_IRAP_VCL23) pos--;
+  int zeros = 0;
+  while (pos >= 0 && !((w >> pos) & 1)) { zeros++; pos--; }
+  if (pos < zeros) return d->geom;                                      // longer than 16 bits: not a legal PPS id
+  const unsigned id = ((w >> (pos - zeros)) & ((1u << (zeros + 1)) - 1)) - 1;
+  TComPPS* pps = id < 64 ? d->top.m_parameterSetManagerDecoder.getPrefetchedPPS((Int)id) : NULL;
+  TComSPS* sps = pps ? d->top.m_parameterSetManagerDecoder.getPrefetchedSPS(pps->getSPSId()) : NULL;
+  return sps ? hm_geom_key_of(sps) : d->geom;
+}
+
+struct GeomScope
+{
+  Decoder* d; bool entered;
+  GeomScope(Decoder* dec, const HmGeomKey& k, bool needed) : d(dec), entered(needed) { if (entered) hm_geom_enter(k); }
+  ~GeomScope()
+  {
+    if (!entered) return;
+    TComSPS* sps = d->top.getActiveSPS();
+    if (sps) d->geom = hm_geom_key_of(sps);
+    t_lastGeom = d->geom;
+    hm_geom_leave(d->geom);
+  }
+};
 inline bool isIrapFlushType(NalUnitType t)
 {
   return t == NAL_UNIT_CODED_SLICE_IDR_W_RADL || t == NAL_UNIT_CODED_SLICE_IDR_N_LP || t == NAL_UNIT_CODED_SLICE_BLA_N_LP ||
@@ -229,8 +270,18 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
   std::vector<uint8_t> bytes(p + skip, p + length);
   if (bytes.size() < 2) return LIBHMDEC_ERROR_READ_ERROR;
 
+  // an unsupported stream feature or an engine error is reported through the reference ABI and is final for this decoder
+  if (d->failed || d->emitter->unsupported() || d->sink->error()) { d->failed = true; return LIBHMDEC_ERROR; }
+
   InputNALUnit nalu;
   read(nalu, bytes);                                   // NALread.cpp:144-154
+
+  const bool vcl = nalu.m_nalUnitType <= NAL_UNIT_RESERVED_VCL31;
+  const bool completes = eof || nalu.m_nalUnitType == NAL_UNIT_EOS;                  // may run the loop-filter hook without parsing a slice
+  // Parameter sets are activated by the first slice of a picture only (TDecTop.cpp:505); a slice that arrives while a picture is
+  // open either belongs to it or merely ends it (bNewPicture, nothing activated, the finished picture is filtered under ITS key).
+  const bool activates = vcl && d->top.m_bFirstSliceInPicture;
+  GeomScope gate(d, activates ? peekSliceGeometry(d, nalu, bytes) : d->geom, vcl || (completes && d->geom.valid));
 
   hm_emit_set_current(d->emitter);
   hm_fast_set_skip_coeff_fill(d->emitter->cleanCoeffs());
@@ -273,6 +324,7 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
   }
   if (eof) { checkOutputPictures = true; d->flushAfterThisPass = true; }
   if (checkOutputPictures) d->cursor = 0;
+  if (d->emitter->unsupported() || d->sink->error()) { d->failed = true; return LIBHMDEC_ERROR; }
   return LIBHMDEC_OK;
 }
 
@@ -350,7 +402,11 @@ short* libHMDEC_get_image_plane(libHMDec_picture* pic, libHMDec_ColorComponent c
     std::map<const void*, Decoder*>::iterator it = g_picOwner.find(pic);
     if (it != g_picOwner.end()) owner = it->second;
   }
-  if (owner) owner->sink->fetchPicture((TComPic*)pic);   // device -> HM's padded host plane, once per picture
+  if (owner)
+  {
+    owner->sink->fetchPicture((TComPic*)pic);            // device -> HM's padded host plane, once per picture
+    if (owner->sink->error()) return NULL;               // the samples never arrived
+  }
   return ((TComPic*)pic)->getPicYuvRec()->getAddr(id);
 }
 
@@ -367,11 +423,13 @@ libHMDec_ChromaFormat libHMDEC_get_chroma_format(libHMDec_picture* pic)
   }
 }
 
+// The reference reads HM's global (libHMDecoder.cpp: no ctx argument).  With several decoders in the process the global belongs to
+// whoever ran last, so the answer is the bit depth of the decoder THIS thread drove last; before that, the global like the reference.
 int libHMDEC_get_internal_bit_depth(libHMDec_ColorComponent c)
 {
-  if (c == LIBHMDEC_LUMA) return g_bitDepth[CHANNEL_TYPE_LUMA];
-  if (c == LIBHMDEC_CHROMA_U || c == LIBHMDEC_CHROMA_V) return g_bitDepth[CHANNEL_TYPE_CHROMA];
-  return -1;
+  if (c != LIBHMDEC_LUMA && c != LIBHMDEC_CHROMA_U && c != LIBHMDEC_CHROMA_V) return -1;
+  const int ch = c == LIBHMDEC_LUMA ? CHANNEL_TYPE_LUMA : CHANNEL_TYPE_CHROMA;
+  return t_lastGeom.valid ? t_lastGeom.bitDepth[ch] : g_bitDepth[ch];
 }
 
 std::vector<libHMDec_BlockValue>* libHMDEC_get_internal_info(libHMDec_context* decCtx, libHMDec_picture* pic, libHMDec_info_type type)
@@ -380,6 +438,7 @@ std::vector<libHMDec_BlockValue>* libHMDEC_get_internal_info(libHMDec_context* d
   if (!d) return NULL;
   d->internals.clear();
   if (!pic) return NULL;
+  GeomScope gate(d, d->geom, d->geom.valid);           // the walk indexes the z-scan tables of this decoder's CTU geometry
   return hm_collect_internals(d->internals, (TComPic*)pic, type);
 }
 

@@ -88,6 +88,13 @@ int  hmr_host_unregister(void* p);
 int  hmr_marker_record(hmr_engine* e, uint64_t* id);
 int  hmr_marker_wait(hmr_engine* e, uint64_t id);
 
+/* How much of a submitted / uploaded frame is checked before any kernel sees it.  Level 1 (default): header, geometry, array
+ * presence, n_ctu / n_mc_tiles / tile-prefix consistency, every CTU's intra range inside n_intra — O(CTUs).  Level 2: in
+ * addition every TU, intra and PU record (coefficient / residual offsets inside n_coef, block inside the picture, tile
+ * prefix matching the PU sizes) — O(records); for callers that feed records they did not produce themselves (dump files).  A frame that fails
+ * is rejected with HMR_ERR_FORMAT and nothing is launched. */
+int  hmr_set_validation(hmr_engine* e, int level);
+
 /* ---- measurement / test hooks ---- */
 int  hmr_set_stage_mask(hmr_engine* e, int mask);
 /* Enable CUDA-event timing of every stage of every submitted frame (adds events only, no syncs). */

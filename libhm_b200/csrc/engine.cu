@@ -59,6 +59,7 @@ struct hmr_engine
   uint4* intraOps; size_t intraOpsCap; uint16_t* intraTab; size_t intraTabBytes; uint4* intraPrep; size_t intraPrepBytes;
   unsigned long long epoch;
   int stageMask;
+  int validation;
   bool timing;
   std::vector<FrameEvents> pending, freeEvents;
   float accMs[HMR_T_COUNT];
@@ -85,35 +86,81 @@ struct hmr_engine
 static std::mutex g_poolLock;
 static std::multimap<std::pair<int, size_t>, void*> g_devPool, g_hostPool;
 
+static size_t g_devPooled[16] = {0}, g_hostPooled = 0;       // bytes parked, per device / page-locked
+static size_t pool_cap(bool host)
+{
+  // parked bytes above the cap go back to the driver (HMR_POOL_CAP_MB / HMR_HOST_POOL_CAP_MB; defaults 48 GiB of 180 GiB HBM, 16 GiB pinned)
+  static const size_t dev = (getenv("HMR_POOL_CAP_MB") ? (size_t)atoll(getenv("HMR_POOL_CAP_MB")) : (size_t)48 * 1024) << 20;
+  static const size_t hst = (getenv("HMR_HOST_POOL_CAP_MB") ? (size_t)atoll(getenv("HMR_HOST_POOL_CAP_MB")) : (size_t)16 * 1024) << 20;
+  return host ? hst : dev;
+}
+// Give every parked buffer of `device` (host: the page-locked ones) back to the driver.  Called when an allocation fails.
+static void pool_trim(int device, bool host)
+{
+  std::vector<void*> victims;
+  {
+    std::lock_guard<std::mutex> g(g_poolLock);
+    auto& pool = host ? g_hostPool : g_devPool;
+    for (auto it = pool.begin(); it != pool.end();)
+      if (host || it->first.first == device) { victims.push_back(it->second); (host ? g_hostPooled : g_devPooled[device & 15]) -= it->first.second; it = pool.erase(it); }
+      else ++it;
+  }
+  for (void* v : victims) { if (host) cudaFreeHost(v); else cudaFree(v); }
+}
 static cudaError_t pool_malloc(int device, void** p, size_t bytes)
 {
   {
     std::lock_guard<std::mutex> g(g_poolLock);
     auto it = g_devPool.find(std::make_pair(device, bytes));
-    if (it != g_devPool.end()) { *p = it->second; g_devPool.erase(it); return cudaSuccess; }
+    if (it != g_devPool.end()) { *p = it->second; g_devPool.erase(it); g_devPooled[device & 15] -= bytes; return cudaSuccess; }
   }
-  return cudaMalloc(p, bytes);
+  cudaError_t r = cudaMalloc(p, bytes);
+  if (r == cudaErrorMemoryAllocation)
+  {
+    cudaGetLastError();
+    pool_trim(device, false);                       // buffers of other sizes (other resolutions decoded earlier) are in the way
+    r = cudaMalloc(p, bytes);
+  }
+  return r;
 }
 static void pool_free(int device, void* p, size_t bytes)
 {
   if (!p) return;
-  std::lock_guard<std::mutex> g(g_poolLock);
-  g_devPool.insert(std::make_pair(std::make_pair(device, bytes), p));
+  {
+    std::lock_guard<std::mutex> g(g_poolLock);
+    if (g_devPooled[device & 15] + bytes <= pool_cap(false))
+    {
+      g_devPool.insert(std::make_pair(std::make_pair(device, bytes), p));
+      g_devPooled[device & 15] += bytes;
+      return;
+    }
+  }
+  cudaFree(p);
 }
 static cudaError_t pool_malloc_host(void** p, size_t bytes)
 {
   {
     std::lock_guard<std::mutex> g(g_poolLock);
     auto it = g_hostPool.find(std::make_pair(0, bytes));
-    if (it != g_hostPool.end()) { *p = it->second; g_hostPool.erase(it); return cudaSuccess; }
+    if (it != g_hostPool.end()) { *p = it->second; g_hostPool.erase(it); g_hostPooled -= bytes; return cudaSuccess; }
   }
-  return cudaMallocHost(p, bytes);
+  cudaError_t r = cudaMallocHost(p, bytes);
+  if (r == cudaErrorMemoryAllocation) { cudaGetLastError(); pool_trim(0, true); r = cudaMallocHost(p, bytes); }
+  return r;
 }
 static void pool_free_host(void* p, size_t bytes)
 {
   if (!p) return;
-  std::lock_guard<std::mutex> g(g_poolLock);
-  g_hostPool.insert(std::make_pair(std::make_pair(0, bytes), p));
+  {
+    std::lock_guard<std::mutex> g(g_poolLock);
+    if (g_hostPooled + bytes <= pool_cap(true))
+    {
+      g_hostPool.insert(std::make_pair(std::make_pair(0, bytes), p));
+      g_hostPooled += bytes;
+      return;
+    }
+  }
+  cudaFreeHost(p);
 }
 
 static int fail(hmr_engine* e, int code, const std::string& msg) { if (e) e->err = msg; return code; }
@@ -179,6 +226,47 @@ static int validate(hmr_engine* e, const hmr_frame_desc* f)
   if ((h.flags & HMR_FRM_DEBLOCK) && !f->bs) return fail(e, HMR_ERR_ARG, "HMR_FRM_DEBLOCK without a BS map");
   if ((h.flags & HMR_FRM_SCALING_LIST) && !f->scaling) return fail(e, HMR_ERR_ARG, "HMR_FRM_SCALING_LIST without scaling factors");
   if ((h.flags & HMR_FRM_WEIGHTED_PRED) && (!f->wp || (h.n_pu && !f->pu_refidx))) return fail(e, HMR_ERR_ARG, "HMR_FRM_WEIGHTED_PRED without weights");
+  // consistency the kernels rely on without re-checking (they index irange[row * ctusW + c], intra[first + k], tiles by prefix)
+  const uint32_t ctusW = (uint32_t)((h.width + (1 << h.log2_ctu) - 1) >> h.log2_ctu), ctusH = (uint32_t)((h.height + (1 << h.log2_ctu) - 1) >> h.log2_ctu);
+  if (h.n_ctu != ctusW * ctusH) return fail(e, HMR_ERR_FORMAT, "n_ctu does not match the picture size and CTU size");
+  if (f->pu_tile_prefix[0] != 0 || f->pu_tile_prefix[h.n_pu] != h.n_mc_tiles) return fail(e, HMR_ERR_FORMAT, "pu_tile_prefix does not end at n_mc_tiles");
+  if (h.n_coef & 15) return fail(e, HMR_ERR_FORMAT, "n_coef must be a multiple of 16");
+  for (int k = 0; k < 4; k++) if (h.tu_first[k] > h.tu_first[k + 1]) return fail(e, HMR_ERR_FORMAT, "tu_first not ascending");
+  for (uint32_t a = 0; a < h.n_ctu; a++)
+    for (int c = 0; c < 3; c++)
+    {
+      const uint32_t first = f->intra_range[a].first[c], count = f->intra_range[a].count[c];
+      if (count && (first > h.n_intra || count > h.n_intra - first)) return fail(e, HMR_ERR_FORMAT, "intra_range outside the intra records");
+    }
+  if (e->validation >= 2)
+  {
+    const int csx = (h.chroma_format == HMR_CHROMA_420 || h.chroma_format == HMR_CHROMA_422) ? 1 : 0, csy = h.chroma_format == HMR_CHROMA_420 ? 1 : 0;
+    auto inside = [&](int comp, unsigned x, unsigned y, unsigned n) {
+      const unsigned w = comp ? h.width >> csx : h.width, hh = comp ? h.height >> csy : h.height;
+      return comp <= 2 && x + n <= w && y + n <= hh;
+    };
+    for (uint32_t i = 0; i < h.n_tu; i++)
+    {
+      const hmr_tu& t = f->tu[i];
+      const unsigned n = 1u << t.log2_size;
+      if (t.log2_size < 2 || t.log2_size > 5 || !inside(t.comp, t.x, t.y, n)) return fail(e, HMR_ERR_FORMAT, "TU record outside the picture");
+      if ((size_t)t.coef_off + (size_t)n * n > h.n_coef) return fail(e, HMR_ERR_FORMAT, "TU coef_off outside the coefficient buffer");
+      if (t.luma_off != HMR_NO_OFFSET && (size_t)t.luma_off + (size_t)n * n > h.n_coef) return fail(e, HMR_ERR_FORMAT, "TU luma_off outside the coefficient buffer");
+    }
+    for (uint32_t i = 0; i < h.n_intra; i++)
+    {
+      const hmr_intra& r = f->intra[i];
+      const unsigned n = 1u << r.log2_size;
+      if (r.log2_size < 2 || r.log2_size > 5 || !inside(r.comp, r.x, r.y, n)) return fail(e, HMR_ERR_FORMAT, "intra record outside the picture");
+      if (r.resid_off != HMR_NO_OFFSET && (size_t)r.resid_off + (size_t)n * n > h.n_coef) return fail(e, HMR_ERR_FORMAT, "intra resid_off outside the residual buffer");
+    }
+    for (uint32_t i = 0; i < h.n_pu; i++)
+    {
+      const hmr_pu& p = f->pu[i];
+      if (!p.w || !p.h || (unsigned)p.x + p.w > (unsigned)h.width || (unsigned)p.y + p.h > (unsigned)h.height || !(p.lists & 3)) return fail(e, HMR_ERR_FORMAT, "PU record outside the picture");
+      if (f->pu_tile_prefix[i + 1] - f->pu_tile_prefix[i] != (uint32_t)(((p.w + 15) >> 4) * ((p.h + 15) >> 4))) return fail(e, HMR_ERR_FORMAT, "pu_tile_prefix does not match the PU sizes");
+    }
+  }
   return HMR_OK;
 }
 
@@ -199,7 +287,16 @@ static void free_geometry(hmr_engine* e)
   cudaStreamSynchronize(e->stream);
   for (int s = 0; s < HMR_MAX_SLOTS; s++) if (e->slotAlloc[s]) { pool_free(e->device, e->slots[s].p[0], e->planeSetBytes); e->slotAlloc[s] = false; }
   if (e->workAlloc) { pool_free(e->device, e->work.p[0], e->planeSetBytes); e->workAlloc = false; }
-  for (int i = 0; i < MD5_RING; i++) while (e->auxInit && e->md5[i].busy && e->md5[i].done.load() == 0) std::this_thread::sleep_for(std::chrono::microseconds(200));
+  // digests in flight read their private copies: wait for the verdicts (the service always delivers one, -1 on failure); the
+  // deadline only guards against a wedged device — the copies are then leaked rather than handed to the next engine
+  bool md5Quiet = true;
+  for (int i = 0; i < MD5_RING && e->auxInit; i++)
+  {
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(20);
+    while (e->md5[i].busy && e->md5[i].done.load() == 0 && std::chrono::steady_clock::now() < deadline) std::this_thread::sleep_for(std::chrono::microseconds(200));
+    if (e->md5[i].busy && e->md5[i].done.load() == 0) md5Quiet = false;
+  }
+  if (!md5Quiet) { fprintf(stderr, "hmrecon: MD5 digests still in flight after 20 s; their buffers are not recycled\n"); for (int i = 0; i < MD5_RING; i++) e->md5[i].alloc = false; }
   for (int i = 0; i < MD5_RING; i++) if (e->md5[i].alloc) { pool_free(e->device, e->md5[i].pic.p[0], e->planeSetBytes); e->md5[i].alloc = false; }
   e->haveGeom = false;
 }
@@ -321,7 +418,6 @@ static int run_frame(hmr_engine* e, FrameParams& P, FrameEvents* fe)
     e->residCap = ALIGN_UP((size_t)h.n_coef * 3 / 2 + 4096, 1 << 20);
     CK(pool_malloc(e->device, (void**)&e->resid, e->residCap * sizeof(int16_t)));
     P.resid = e->resid;
-  P.mc_tiles = e->mcTiles;
   }
   if (h.n_intra > e->intraOpsCap)
   {
@@ -386,7 +482,10 @@ int hmr_engine_create(hmr_engine** out, int device)
 {
   if (!out) return HMR_ERR_ARG;
   *out = nullptr;
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);          // decoder streams should not share hardware queues (effective if CUDA is not initialised yet)
+  // decoder streams should not share hardware queues (effective if CUDA is not initialised yet); once, before any engine thread
+  // can race on the environment
+  static std::once_flag envOnce;
+  std::call_once(envOnce, [] { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); });
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
   {
@@ -400,7 +499,7 @@ int hmr_engine_create(hmr_engine** out, int device)
   memset(e->ring, 0, sizeof(e->ring));
   e->ringPos = 0; e->resid = nullptr; e->residCap = 0; e->mcTiles = nullptr; e->mcTilesCap = 0; e->mcTileRef = nullptr; e->packBuf = nullptr; e->packCap = 0; e->progress = nullptr; e->progressCap = 0; e->epoch = 1;
   e->intraOps = nullptr; e->intraOpsCap = 0; e->intraTab = nullptr; e->intraTabBytes = 0; e->intraPrep = nullptr; e->intraPrepBytes = 0;
-  e->stageMask = HMR_STAGE_ALL; e->timing = false;
+  e->stageMask = HMR_STAGE_ALL; e->timing = false; e->validation = 1;
   memset(e->accMs, 0, sizeof(e->accMs)); e->accFrames = e->accLaunches = 0;
   e->timerInit = false;
   e->planeSetBytes = 0; e->markerInit = false; e->markerNext = 0; e->auxInit = false; e->md5Next = 0;
@@ -600,6 +699,7 @@ int hmr_picture_hash(hmr_engine* e, int slot, int type, uint32_t out[3])
   return HMR_OK;
 }
 
+int hmr_set_validation(hmr_engine* e, int level) { if (!e) return HMR_ERR_ARG; e->validation = level; return HMR_OK; }
 int hmr_set_stage_mask(hmr_engine* e, int mask) { if (!e) return HMR_ERR_ARG; e->stageMask = mask; return HMR_OK; }
 int hmr_enable_timing(hmr_engine* e, int on) { if (!e) return HMR_ERR_ARG; if (!on) fold_timing(e); e->timing = on != 0; return HMR_OK; }
 

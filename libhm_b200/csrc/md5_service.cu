@@ -27,8 +27,8 @@ struct Service
   std::condition_variable cv;
   std::vector<Active> pending;
   bool running;                // a worker thread exists
-  bool failed;
-  Service() : device(0), running(false), failed(false) {}
+  int failures;                // workers that ended on a CUDA error (diagnostics; the service restarts on the next submit)
+  Service() : device(0), running(false), failures(0) {}
 };
 
 Service* const g_svc = new Service[16];   // never destroyed: a lingering worker may still hold its mutex at process exit
@@ -47,9 +47,10 @@ void worker(Service* sv)
   const int MAXJ = 512;
   Md5TickJob* table[2] = { nullptr, nullptr };
   cudaEvent_t ev[2];
+  bool evMade[2] = { false, false };
   bool ok = cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, lo) == cudaSuccess;
   for (int i = 0; i < 2 && ok; i++)
-    ok = cudaMallocHost(&table[i], sizeof(Md5TickJob) * MAXJ) == cudaSuccess && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;   // sleep, never spin: the cores belong to the parsers
+    ok = cudaMallocHost(&table[i], sizeof(Md5TickJob) * MAXJ) == cudaSuccess && (evMade[i] = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess);   // sleep, never spin: the cores belong to the parsers
   std::vector<Active> active;
   std::vector<std::atomic<int>*> finishing[2];                  // jobs whose last chunk was in tick t (signalled when tick t completes)
   unsigned long long t = 0;
@@ -57,7 +58,24 @@ void worker(Service* sv)
   {
     {
       std::unique_lock<std::mutex> lk(sv->mu);
-      if (!ok) { sv->failed = true; for (size_t i = 0; i < sv->pending.size(); i++) sv->pending[i].done->store(-1); sv->pending.clear(); sv->running = false; return; }
+      if (!ok)
+      {
+        // A CUDA call failed.  EVERY job this worker knows about gets its verdict (-1) — the ones still queued, the ones in
+        // flight and the ones whose last chunk was already launched — so nobody spins on a `done` flag forever
+        // (hmr_md5_result(wait), free_geometry).  The worker releases what it holds and ends; the next submit starts a fresh
+        // worker (a sticky device error will make that one fail the same way, job by job, instead of hanging).
+        for (size_t i = 0; i < sv->pending.size(); i++) sv->pending[i].done->store(-1);
+        sv->pending.clear();
+        for (size_t i = 0; i < active.size(); i++) active[i].done->store(-1);
+        for (int k = 0; k < 2; k++) for (size_t i = 0; i < finishing[k].size(); i++) finishing[k][i]->store(-1);
+        sv->failures++;
+        sv->running = false;
+        lk.unlock();
+        for (int i = 0; i < 2; i++) { if (table[i]) cudaFreeHost(table[i]); if (evMade[i]) cudaEventDestroy(ev[i]); }
+        if (stream) cudaStreamDestroy(stream);
+        cudaGetLastError();
+        return;
+      }
       if (active.empty() && sv->pending.empty() && finishing[0].empty() && finishing[1].empty())
       {
         // idle: linger a little, then let the thread end (a later submit starts a new one)
@@ -116,7 +134,6 @@ bool md5_service_submit(int device, const Md5Job& J, cudaEvent_t ready, std::ato
   a.J = J; a.chunk = 0; a.chunks = md5_chunks(J); a.done = done; a.ready = ready;
   done->store(0);
   std::lock_guard<std::mutex> g(sv.mu);
-  if (sv.failed) return false;
   sv.device = device;
   sv.pending.push_back(a);
   if (!sv.running)

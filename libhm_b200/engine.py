@@ -37,7 +37,7 @@ def load():
                            ("hmr_read_work_plane", [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
                            ("hmr_write_plane", [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
                            ("hmr_picture_hash", [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
-                           ("hmr_set_stage_mask", [C.c_void_p, C.c_int]), ("hmr_enable_timing", [C.c_void_p, C.c_int]),
+                           ("hmr_set_stage_mask", [C.c_void_p, C.c_int]), ("hmr_set_validation", [C.c_void_p, C.c_int]), ("hmr_enable_timing", [C.c_void_p, C.c_int]),
                            ("hmr_get_stage_times", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
                            ("hmr_upload_frame", [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
                            ("hmr_run_resident", [C.c_void_p, C.c_void_p]), ("hmr_free_resident", [C.c_void_p, C.c_void_p]),
@@ -64,6 +64,7 @@ class Engine:
             raise EngineError(f"hmr_engine_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback exists)")
         self.h = h
         self.sizes = None
+        self.lib.hmr_set_validation(self.h, 2)      # records come from dump files here: every record is bounds-checked before a kernel sees it
 
     def close(self):
         if getattr(self, "h", None):

@@ -5,14 +5,16 @@ import os
 import re
 import subprocess
 import pytest
-from conftest import GOLDEN, STREAMS, ROOT
+from conftest import GOLDEN, STREAMS, ROOT, hm_digests
 
 pytestmark = pytest.mark.gpu
 CLI = os.path.join(ROOT, "frontend", "_build", "hmdec_cli")
+CLI_VERIFY = os.path.join(ROOT, "frontend", "_build", "hmdec_cli_verify")   # links libHMDecoder_b200_verify.so (HM's CPU reconstruction next to the engine)
 
 
 def _md5s(text):
-    return [(int(m.group(1)), m.group(2)) for m in re.finditer(r"POC\s+(-?\d+).*?\[MD5:([0-9a-f,]+),\(OK\)\]", text)]
+    """(poc, kind, digests) of every picture whose hash check passed: MD5, CRC and checksum SEI methods alike."""
+    return hm_digests(text)
 
 
 @pytest.mark.parametrize("name", STREAMS)
@@ -28,11 +30,12 @@ def test_dropin_decoder_matches_tappdecoder(name):
 
 
 def test_dropin_decoder_selfcheck_against_hm_cpu_recon():
-    """HMDEC_B200_VERIFY=1 also runs HM's CPU reconstruction and compares every fetched plane byte for byte."""
-    if not os.path.exists(CLI):
+    """The verify build (libHMDecoder_b200_verify.so; the product library holds no CPU reconstruction) with HMDEC_B200_VERIFY=1
+    also runs HM's CPU reconstruction and compares every fetched plane byte for byte."""
+    if not os.path.exists(CLI_VERIFY):
         pytest.skip("frontend not built")
     env = dict(os.environ, HMDEC_B200_VERIFY="1")
-    r = subprocess.run([CLI, "-b", os.path.join(GOLDEN, "s_ra10_240p.bin"), "--touch-planes"], capture_output=True, text=True, timeout=300, env=env)
+    r = subprocess.run([CLI_VERIFY, "-b", os.path.join(GOLDEN, "s_ra10_240p.bin"), "--touch-planes"], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("(OK)") == 17
 

@@ -4,7 +4,7 @@ sample by sample, with the first differing sample reported.  Integer work: the b
 import os
 import numpy as np
 import pytest
-from conftest import GOLDEN, STREAMS, ROOT
+from conftest import GOLDEN, STREAMS, ROOT, hm_digests
 from libhm_b200 import records
 
 pytestmark = pytest.mark.gpu
@@ -55,26 +55,32 @@ def test_engine_matches_hm_and_oracle(name, eng_mod):
         eng.close()
 
 
-def test_picture_hashes_match_oracle(eng_mod):
-    """checksum / CRC kernels (SEI hash methods 3 and 2) against the oracle restatement of TComPicYuvMD5.cpp:87-175."""
+@pytest.mark.parametrize("name", ["s_crc_240p", "s_cksum_240p", "s_ra8_240p", "s_ra10_240p"])
+def test_picture_hashes_match_hm(name, eng_mod):
+    """checksum / CRC kernels (SEI hash methods 3 and 2, TComPicYuvMD5.cpp:87-175) against the digests the unmodified TAppDecoder
+    printed and verified against the SEI (s_crc_240p: method 2, s_cksum_240p: method 3, every picture), and — on the two MD5 streams,
+    for both methods — against the oracle functions that tests/test_oracle_golden.py pins to those same HM digests."""
     import ctypes as C
     from oracle import oracle
-    for name in ("s_ra8_240p", "s_ra10_240p"):
-        frames = records.read_dump(os.path.join(GOLDEN, name + ".hmr.gz"))
-        eng = eng_mod.Engine(0)
-        try:
-            for fr in frames[:3]:
-                eng.submit(fr)
-            fr = frames[2]
+    frames = records.read_dump(os.path.join(GOLDEN, name + ".hmr.gz"))
+    hm = {poc: (kind, [int(h, 16) for h in hx]) for poc, kind, hx in hm_digests(open(os.path.join(GOLDEN, name + ".md5")).read()) if kind != "MD5"}
+    eng = eng_mod.Engine(0)
+    try:
+        for fr in frames:
+            eng.submit(fr)
             slot = int(fr.h["out_slot"])
+            poc = int(fr.h["poc"])
+            if poc in hm:
+                kind, want = hm[poc]
+                assert eng.picture_hash(slot, 2 if kind == "CRC" else 3) == want, (name, poc, kind)
             planes = eng.read_picture(slot)
             for kind, fn in ((3, oracle.lib().orc_checksum_plane), (2, oracle.lib().orc_crc_plane)):
-                got = eng.picture_hash(slot, kind)
                 exp = [int(fn(p.ctypes.data_as(C.c_void_p), C.c_int(p.shape[1]), C.c_int(p.shape[0]), C.c_int(p.shape[1]), C.c_int(fr.bit_depth(c))))
                        for c, p in enumerate(planes)]
-                assert got == exp, (name, kind, got, exp)
-        finally:
-            eng.close()
+                assert eng.picture_hash(slot, kind) == exp, (name, poc, kind)
+        assert name not in ("s_crc_240p", "s_cksum_240p") or len(hm) == len(frames)
+    finally:
+        eng.close()
 
 
 def test_resident_replay_is_deterministic(eng_mod):

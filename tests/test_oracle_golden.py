@@ -5,28 +5,35 @@ import os
 import re
 import numpy as np
 import pytest
-from conftest import GOLDEN, STREAMS
+import ctypes as C
+from conftest import GOLDEN, STREAMS, hm_digests
 from libhm_b200 import records
 from oracle import oracle
 
 
-def _tappdecoder_md5(name):
-    out = {}
-    for line in open(os.path.join(GOLDEN, name + ".md5")):
-        m = re.search(r"POC\s+(-?\d+).*\[MD5:([0-9a-f]{32}),([0-9a-f]{32}),([0-9a-f]{32}),\(OK\)\]", line)
-        assert m, line
-        out[int(m.group(1))] = [bytes.fromhex(m.group(k)) for k in (2, 3, 4)]
+def _tappdecoder_digests(name):
+    """Per picture in decoding order: (poc, kind, [Y, Cb, Cr]) as the unmodified TAppDecoder printed (and verified against the SEI): MD5 digests as bytes,
+    CRC (method 2) / checksum (method 3) as integers (TDecGop.cpp:231-289)."""
+    lines = [l for l in open(os.path.join(GOLDEN, name + ".md5")) if l.strip()]
+    out = [(poc, kind, [bytes.fromhex(h) for h in hx] if kind == "MD5" else [int(h, 16) for h in hx]) for poc, kind, hx in hm_digests("".join(lines))]
+    assert len(out) == len(lines), name
     return out
+
+
+def _oracle_hash(kind, planes, bds):
+    fn = oracle.lib().orc_crc_plane if kind == "CRC" else oracle.lib().orc_checksum_plane
+    return [int(fn(p.ctypes.data_as(C.c_void_p), C.c_int(p.shape[1]), C.c_int(p.shape[0]), C.c_int(p.shape[1]), C.c_int(bds[c]))) for c, p in enumerate(planes)]
 
 
 @pytest.mark.parametrize("name", STREAMS)
 def test_oracle_matches_hm_all_stages(name):
     frames = records.read_dump(os.path.join(GOLDEN, name + ".hmr.gz"))
-    ref = _tappdecoder_md5(name)
+    ref = _tappdecoder_digests(name)
     assert len(frames) == len(ref)
     dec = oracle.Decoder()
     pre = oracle.STAGE_MC | oracle.STAGE_RESID | oracle.STAGE_INTRA
-    for fr in frames:
+    for fr, (poc, kind, want) in zip(frames, ref):
+        assert poc == int(fr.h["poc"])
         bds = [fr.bit_depth(c) for c in range(3)]
         dec.frame(fr, pre)
         assert (records.picture_md5(dec.work.planes, bds) == fr.gold[0]).all(), f"CU recon, POC {fr.h['poc']}"
@@ -35,7 +42,10 @@ def test_oracle_matches_hm_all_stages(name):
         out = dec.frame(fr)
         md5 = records.picture_md5(out.planes, bds)
         assert (md5 == fr.gold[2]).all(), f"SAO, POC {fr.h['poc']}"
-        assert [bytes(md5[c]) for c in range(3)] == ref[int(fr.h["poc"])], "final picture vs TAppDecoder/SEI MD5"
+        if kind == "MD5":
+            assert [bytes(md5[c]) for c in range(3)] == want, "final picture vs TAppDecoder/SEI MD5"
+        else:     # SEI hash methods 2 / 3: pins orc_crc_plane / orc_checksum_plane (TComPicYuvMD5.cpp:87-175) to HM's own digests
+            assert _oracle_hash(kind, out.planes, bds) == want, f"final picture vs TAppDecoder/SEI {kind}, POC {fr.h['poc']}"
 
 
 def test_fixtures_cover_the_tools():

@@ -73,7 +73,7 @@ def generate(path, width, height, frames, bitdepth, seed, chroma="420", pan=(3.0
                 if k:
                     p = p[::sy, ::sx]
                 planes.append(p.astype(dt))
-            for p in planes:
+            for p in planes[:1] if chroma == "400" else planes:      # 4:0:0: the luma plane only
                 fh.write(p.tobytes())
 
 

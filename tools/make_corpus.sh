@@ -52,8 +52,26 @@ JOBS=(
  "m_ra10_1080p       encoder_randomaccess_main10.cfg       1920 1080 17 10 420 5"
  "f_ra10_1080p       encoder_randomaccess_main10.cfg       1920 1080 17 10 420 6"
  "f_ra10_2160p       encoder_randomaccess_main10.cfg       3840 2160 33 10 420 7"
+ "q27_ra10_2160p     encoder_randomaccess_main10.cfg       3840 2160 33 10 420 3 -q 27"
+ "q22_ra8_1080p      encoder_randomaccess_main.cfg         1920 1080 33 8  420 2 -q 22"
+ "s_crc_240p         encoder_randomaccess_main.cfg         416  240  9  8  420 41 --SEIDecodedPictureHash=2 -q 30"
+ "s_slseg_240p       encoder_randomaccess_main.cfg         416  240  9  8  420 43 --SliceSegmentMode=1 --SliceSegmentArgument=7 -q 30"
+ "s_gray400_240p     encoder_randomaccess_main_rext.cfg    416  240  5  8  400 44 --InternalBitDepth=8 -q 30"
+ "s_cksum_240p       encoder_randomaccess_main10.cfg       416  240  9  10 420 42 --SEIDecodedPictureHash=3 -q 30"
 )
 WANT=$1
+# s_switch_240p: five coded video sequences back to back, every one starting with an IDR and four of the five activating an SPS of
+# another geometry (416x240 -> 200x136 -> 416x240 -> 208x120 lossless -> 416x240): resolution switches with DPB flushes in between.
+if [ "$WANT" == "s_switch_240p" ]; then
+  out=$ROOT/corpus/s_switch_240p
+  for s in s_ra8_240p s_ra8_odd s_ra8_240p_q22 s_lossless_240p; do [ -s "$ROOT/corpus/$s.bin" ] || "$0" $s; done
+  cat "$ROOT/corpus/s_ra8_240p.bin" "$ROOT/corpus/s_ra8_odd.bin" "$ROOT/corpus/s_ra8_240p_q22.bin" "$ROOT/corpus/s_lossless_240p.bin" "$ROOT/corpus/s_ra8_240p.bin" > "$out.bin"
+  "$DEC" -b "$out.bin" -d 0 -o "$TMP_YUV/s_switch.dec.yuv" > "$out.dec.log" 2>&1
+  grep -o 'POC.*' "$out.dec.log" | sed -E 's/\[DT +[0-9.]+\] //' > "$out.md5"
+  md5sum < "$TMP_YUV/s_switch.dec.yuv" | awk '{print $1}' > "$out.yuvmd5"
+  echo "s_switch_240p: done ($(stat -c %s "$out.bin") bytes, $(grep -c OK "$out.md5") pictures OK)"
+  exit 0
+fi
 if [ "$1" == "--list" ]; then for j in "${JOBS[@]}"; do echo "$j" | awk '{print $1}'; done; exit 0; fi
 for j in "${JOBS[@]}"; do
   set -- $j
