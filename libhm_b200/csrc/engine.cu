@@ -318,7 +318,7 @@ static int ensure_geometry(hmr_engine* e, const hmr_frame_hdr& h)
     }
     e->ctusW = (h.width + (1 << h.log2_ctu) - 1) >> h.log2_ctu;
     e->ctusH = (h.height + (1 << h.log2_ctu) - 1) >> h.log2_ctu;
-    if (3 * e->ctusH > e->coopLimit) return fail(e, HMR_ERR_FORMAT, "picture has more CTU rows than the intra wavefront can keep co-resident");
+    if (e->coopLimit < 1) return fail(e, HMR_ERR_CUDA, "the device cannot launch the intra wavefront cooperatively");
     const size_t need = (size_t)3 * e->ctusH;
     if (need > e->progressCap)
     {

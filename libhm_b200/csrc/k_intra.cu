@@ -7,35 +7,45 @@
 //
 // Dependencies: an intra TU reads unfiltered reconstructed samples left / above / above-right / below-left of
 // itself.  Inter samples are final before this kernel starts (k_mc + k_resid); intra samples are produced here in
-// decode order.  One persistent CTA per (component, CTU row), launched cooperatively so that all CTAs are
+// decode order.  One persistent CTA per (component, CTU row) job, launched cooperatively so that all CTAs are
 // co-resident; row r may process CTU c once row r-1 has published c+2 finished CTUs (the above-right CTU) — the
 // WPP dependency.  Progress counters carry an epoch so they never need clearing; a row publishes "all CTUs before
 // my next CTU that has intra TUs", so rows/CTUs without intra blocks cost nothing.
 //
-// The per-TU chain is the critical path (an I picture at 2160p is ~3300 dependent TU steps; a dataflow simulation over
-// real streams shows TU-level parallelism inside a CTU is < 1.2x, z-order makes every TU depend on its predecessor),
-// so the design minimises the latency of ONE warp walking the TUs:
-//   * the CTA is warp-specialised and double-buffered: warps 1-3 ("stagers") do everything that touches global
-//     memory for CTU n+1 while warp 0 ("chain") predicts CTU n — the CTU's current samples plus the row above
-//     (x = -1 .. CTU+31, after waiting for the row above) and the column to the left, the residuals of its TUs
-//     and its decoded TUs / address tables (TMA bulk copies for the contiguous spans, 16-byte cp.async for the tile
-//     rows, all in flight together) — then write CTU n back and publish the progress;
-//     hand-over through named barriers (bar.arrive / bar.sync), never a full __syncthreads;
+// The per-TU chain is the critical path (an I picture at 2160p is ~1560 dependent luma TUs per CTU row; a dataflow simulation over
+// real streams shows TU-level parallelism inside a CTU is < 1.2x, z-order makes every TU depend on its predecessor), and a warp
+// walking it is latency-bound (one dependent instruction every ~4.5 cycles, measured with -DINTRA_PROFILE / tools/intra_profile.py),
+// so the design keeps everything that does not need the PREVIOUS TU's samples off the chain:
 //   * a pre-pass kernel (intra_prep_kernel, fully parallel over the picture) turns the records into reference-address
 //     tables — for every TU, entry i = shared-memory position of reference sample i AFTER HM's substitution of
-//     unavailable samples (pure function of the record, no sample data) — and into decoded 16-byte micro-ops; the
-//     whole fillReferenceSamples logic and all mode decoding are off the critical path, the stagers only copy;
-//   * warp 0 ("chain") runs size-templated, fully unrolled code per TU: gather the line through the table -> optional
-//     smoothing -> prediction (main-reference projection folded into the index) -> + residual -> back into the tile,
-//     with warp-level synchronisation only;
+//     unavailable samples (pure function of the record, no sample data) — and into decoded 16-byte micro-ops;
+//   * the CTA is warp-specialised and double-buffered: two stager warps do everything that touches global memory for CTU n+1
+//     while the four CHAIN warps predict CTU n — the CTU's current samples plus the row above (x = -1 .. CTU+31, after waiting
+//     for the row above) and the column to the left, the residuals of its TUs and its decoded TUs / address tables (TMA bulk
+//     copies for the contiguous spans, 16-byte cp.async for the tile rows, all in flight together) — then write CTU n back and
+//     publish the progress; hand-over through named barriers (bar.arrive / bar.sync), never a full __syncthreads;
+//   * every predictor is evaluated as a TAP PROGRAM (tap_prep / tap_turn below): per sample up to four reference samples with
+//     weights.  The four chain warps take the 4x4 / 8x8 TUs of a CTU round robin: a warp PREPARES its TU (tile addresses of the
+//     taps through the address table, weights, destination, residual: no sample values needed) while the three TUs before it have
+//     their turns, waits for the token, takes its TURN — loads, multiply-adds, + residual, clip, store — and passes the token on
+//     (bar.arrive -> bar.sync of the next warp: ~95 cycles from "stored" to "first sample of the next TU loaded").  16x16 / 32x32
+//     TUs are predicted by all four warps together, a quarter of the samples each;
+//   * TUs whose reference line is smoothed first ([1 2 1] / strong filter) deposit the filtered line behind the tiles (line_phase:
+//     three loads per entry, the four warps sharing the entries of a large TU) and their taps address that line instead;
 //   * a tile is written back once, coalesced.  Cross-CTA reads go through L2 (ld.global.cg); the producer fences before
 //     publishing;
 //   * shared memory is sized by the largest CTU of the picture (records, address-table entries, residual span: measured
 //     on the host records, intra_sizes_host): a resident CTA holds its buffers for the whole wavefront while issuing
-//     almost nothing, and with several bitstreams on one GPU that footprint is what the other streams' kernels wait for.
+//     almost nothing, and with several bitstreams on one GPU that footprint is what the other streams' kernels wait for;
+//   * a CTA takes (component, row) jobs in ascending order, so pictures with more rows than co-resident CTAs still run.
+// Measured (2160p Main10 I picture, 139 410 intra TUs): 1.50 ms against 2.17 ms for the single-chain-warp version of round 1; the
+// rest is the wavefront itself: 34 rows, each ~26 us behind the one above (two CTUs + hand-over), 7 us per luma CTU.
 #include "common.cuh"
 
-#define IN_THREADS 128
+#define IN_CHAIN_WARPS 4                    // warps that share the TUs of a CTU (round robin; large TUs by all four together)
+#define IN_CHAIN (IN_CHAIN_WARPS * 32)
+#define IN_STAGERS 64                      // threads that do everything touching global memory
+#define IN_THREADS (IN_CHAIN + IN_STAGERS)
 #define IN_MAXCT 64
 #define IN_LD (8 + IN_MAXCT + 32)          // tile pitch: 8 columns of left margin (x = -1 lives at column 7), CTU, 32 above-right
 #define IN_TILE ((IN_MAXCT + 1) * IN_LD)   // row 0 = y -1; element 0 (y = -1, x = -8) holds the "nothing available" constant
@@ -185,193 +195,202 @@ __device__ __forceinline__ IntraOp intra_make_op(const hmr_intra& r, const Intra
 }
 
 #define IN_NJMAX 5      // (4*32 + 1 + 31) / 32 reference samples per lane at most
+#define IN_LINE 144     // int16 entries of the filtered reference line of one TU (4*32 + 1, plus the -1 / 4N+1 slots the 45-degree modes touch with weight 0)
 
-// Reference-sample addresses of a TU for this lane (entry lane + 32 j), ahead of the TU's turn.
-__device__ __forceinline__ void intra_fetch_addrs(const IntraOp& op, const uint16_t* __restrict__ addrTab, int lane, int a[IN_NJMAX])
+// ---- a TU as a TAP PROGRAM --------------------------------------------------------------------------------------------------
+// Every HM predictor is, per sample, a weighted sum of at most four reference samples (planar: LEFT(y), TOP(N), TOP(x), LEFT(N);
+// angular: the two neighbours on the main reference, the side reference projected in for negative angles; DC: the mean plus one
+// or two edge samples; pure horizontal / vertical: one sample plus the edge correction).  PREP (tap_prep: needs no sample values,
+// runs while other TUs have their turn) resolves, per lane and sample, WHERE those four samples are and their weights, the
+// destination and the residual.  "Where" is a tile index (0 = the constant slot, for taps of weight 0): either the reference sample itself, looked up in the TU's address table
+// (HM's substitution of unavailable samples is already resolved there), or — TUs whose reference line is smoothed first
+// (TComPrediction::filteringIntraReferenceSamples) — an entry of the filtered line the owner of the TU deposits behind the tiles
+// (line_phase).  The TURN (tap_turn) is then loads, multiply-adds, + residual, clip, store: the only part of a TU that has to
+// wait for its predecessor.  4x4 / 8x8 TUs are one warp's job (1 / 2 samples per lane); 16x16 / 32x32 TUs are shared by the four
+// chain warps (2 / 8 samples per lane each).
+enum { TV_GENERIC = 0, TV_DC = 1, TV_HVEDGE = 2 };
+template <int S> struct TapProg
 {
-  const int L = (4 << op_lg(op)) + 1;
-  const uint16_t* t = addrTab + op_slot(op);
-#pragma unroll
-  for (int j = 0; j < IN_NJMAX; j++)
-  {
-    const int i = lane + 32 * j;
-    a[j] = i < L ? (int)t[i] : 0;
-  }
-}
+  int aA[S], aB[S], aC[S], aD[S];               // tile indices (the filtered line lives at lineBase + i)
+  int wA[S], wB[S], wC[S], wD[S];
+  int dst[S], res[S];
+};
+template <int LG> struct TapShape { static constexpr int S = LG == 2 ? 1 : (LG == 5 ? 8 : 2); };   // samples per lane: 16 (half a warp) / 64 / 4 x 64 / 4 x 256
 
-// One TU on one warp, everything in shared memory / registers.  `a` = this lane's reference addresses (prefetched);
-// while the references are being gathered the addresses of the NEXT TU (`opn`) are fetched into `an`.
+// Program of samples first + lane + 32 j (j < S) of the TU.  rnd / sh: rounding and shift of the weighted sum (TV_GENERIC).
+// One loop per predictor class (the class is uniform over the TU): a sample costs a handful of integer operations plus the table
+// look-ups of its taps.  Taps a class does not use keep weight 0 and point at entry 0 of the tile (the constant slot): always readable.
 template <int LG>
-__device__ __forceinline__ void intra_tu(const IntraOp op, const int a[IN_NJMAX], const bool hasNext, const IntraOp opn, int an[IN_NJMAX],
-                                         const uint16_t* __restrict__ addrTab, int16_t* __restrict__ tile, const int16_t* __restrict__ resB,
-                                         int* __restrict__ sref, const int bd, const int lane)
+__device__ __forceinline__ void tap_prep(const IntraOp op, const uint16_t* __restrict__ addrTab, const int16_t* __restrict__ resB, const int lineBase,
+                                         const int first, const int lane, TapProg<TapShape<LG>::S>& g, int& variant, int& rnd, int& sh)
 {
-  constexpr int N = 1 << LG, N2 = 2 * N, L = 4 * N + 1, NJ = (L + 31) / 32, S = (N * N + 31) / 32;
-  const int maxv = (1 << bd) - 1;
-  // ---- gather the reference line: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right ----
-  int v[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; j++) v[j] = tile[a[j]];             // a[] is 0 (the constant slot) past the end of the line
-  if (hasNext) intra_fetch_addrs(opn, addrTab, lane, an);      // independent of the samples: overlaps the gather
-  const int flags = op_flags(op);
-  if (flags & OPF_FILTER)
-  {
-    // [1 2 1] / 4 smoothing (or the bilinear "strong" variant) of everything but the two end points, neighbours by shuffle
-    bool strong = false;
-    int bl = 0, tl = 0, tr = 0;
-    if (N == 32 && (flags & OPF_STRONG))
-    {
-      bl = __shfl_sync(0xffffffffu, v[0], 0); tl = __shfl_sync(0xffffffffu, v[2 % NJ], 0); tr = __shfl_sync(0xffffffffu, v[4 % NJ], 0);
-      const int mid0 = __shfl_sync(0xffffffffu, v[1 % NJ], 0), mid1 = __shfl_sync(0xffffffffu, v[3 % NJ], 0);     // line[N], line[3N]
-      const int thr = 1 << (bd - 5);
-      strong = abs(bl + tl - 2 * mid0) < thr && abs(tl + tr - 2 * mid1) < thr;
-    }
-    int f[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; j++)
-    {
-      const int i = lane + 32 * j;
-      int up = __shfl_up_sync(0xffffffffu, v[j], 1), dn = __shfl_down_sync(0xffffffffu, v[j], 1);
-      if (j > 0)      { const int w = __shfl_sync(0xffffffffu, v[j - 1], 31); if (lane == 0) up = w; }
-      if (j + 1 < NJ) { const int w = __shfl_sync(0xffffffffu, v[j + 1], 0);  if (lane == 31) dn = w; }
-      int r;
-      if (i == 0 || i >= 4 * N) r = v[j];
-      else if (strong) r = i < N2 ? ((N2 - i) * bl + i * tl + N) >> (LG + 1) : (i == N2 ? tl : ((N2 - (i - N2)) * tl + (i - N2) * tr + N) >> (LG + 1));
-      else r = (up + 2 * v[j] + dn + 2) >> 2;
-      f[j] = r;
-    }
-#pragma unroll
-    for (int j = 0; j < NJ; j++) v[j] = f[j];
-  }
-#pragma unroll
-  for (int j = 0; j < NJ; j++)
-  {
-    const int i = lane + 32 * j;
-    if (i < L) sref[i] = v[j];
-  }
-  __syncwarp();
-  const int* ref = sref;
-#define LEFT(y) ref[N2 - 1 - (y)]
-#define TOP(x)  ref[N2 + 1 + (x)]
-#define EMIT(i, y, x, v) dst[(y) * IN_LD + (x)] = (int16_t)clip3i(0, maxv, (int)(int16_t)(v) + (hasRes ? (int)res[i] : 0))
+  constexpr int N = 1 << LG, N2 = 2 * N, S = TapShape<LG>::S;
+  const uint16_t* t = addrTab + op_slot(op);
+  const int cls = op_cls(op), flags = op_flags(op);
+  const bool filtered = flags & OPF_FILTER;                  // taps read the smoothed line, not the tile
   const bool hasRes = op.y != HMR_NO_OFFSET;
+  const int org = op_org(op);
   const int16_t* res = resB + (hasRes ? op.y : 0u);
-  int16_t* dst = tile + op_org(op);
-  const int cls = op_cls(op);
+  auto at = [&](int idx) -> int { return filtered ? lineBase + idx : (int)t[idx]; };
+  variant = TV_GENERIC; rnd = 0; sh = 0;
+#pragma unroll
+  for (int j = 0; j < S; j++)
+  {
+    const int i = (first + lane + 32 * j) & (N * N - 1);     // 4x4: lanes 16-31 shadow lanes 0-15 (they never store)
+    g.aA[j] = g.aB[j] = g.aC[j] = g.aD[j] = 0;
+    g.wA[j] = g.wB[j] = g.wC[j] = g.wD[j] = 0;
+    g.dst[j] = org + (i >> LG) * IN_LD + (i & (N - 1));
+    g.res[j] = hasRes ? (int)res[i] : 0;
+  }
   if (cls == OP_PLANAR)
   {
-    const int tn = TOP(N), ln = LEFT(N);
+    rnd = N; sh = LG + 1;
+    const int aTN = at(N2 + 1 + N), aLN = at(N2 - 1 - N);    // TOP(N), LEFT(N): the same for every sample
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
-      const int i = lane + 32 * j;
-      if (N * N >= 32 || i < N * N)
-      {
-        const int y = i >> LG, x = i & (N - 1);
-        const int p = ((N - 1 - x) * LEFT(y) + (x + 1) * tn + (N - 1 - y) * TOP(x) + (y + 1) * ln + N) >> (LG + 1);
-        EMIT(i, y, x, p);
-      }
-    }
-  }
-  else if (cls == OP_PCM)
-  {
-#pragma unroll
-    for (int j = 0; j < S; j++)
-    {
-      const int i = lane + 32 * j;
-      if (N * N >= 32 || i < N * N) { const int y = i >> LG, x = i & (N - 1); EMIT(i, y, x, 0); }
+      const int i = (first + lane + 32 * j) & (N * N - 1), y = i >> LG, x = i & (N - 1);
+      g.aA[j] = at(N2 - 1 - y); g.wA[j] = N - 1 - x;       // LEFT(y)
+      g.aB[j] = aTN;            g.wB[j] = x + 1;
+      g.aC[j] = at(N2 + 1 + x); g.wC[j] = N - 1 - y;       // TOP(x)
+      g.aD[j] = aLN;            g.wD[j] = y + 1;
     }
   }
   else if (cls == OP_DC)
   {
-    const int part = lane < N ? TOP(lane) + LEFT(lane) : 0;
-    const int dc = (__reduce_add_sync(0xffffffffu, part) + N) >> (LG + 1);
+    variant = TV_DC;                                         // tap C carries the mean; edge samples: (A + B + wC * dc + 2) >> 2  (TComPrediction.cpp:746-835)
     const bool edge = flags & OPF_DCEDGE;
 #pragma unroll
     for (int j = 0; j < S; j++)
     {
-      const int i = lane + 32 * j;
-      if (N * N >= 32 || i < N * N)
+      const int i = (first + lane + 32 * j) & (N * N - 1), y = i >> LG, x = i & (N - 1);
+      g.wC[j] = 1;
+      if (edge && (x == 0 || y == 0))
       {
-        const int y = i >> LG, x = i & (N - 1);
-        int p = dc;
-        if (edge)
-        {
-          if (x == 0 && y == 0) p = (TOP(0) + LEFT(0) + 2 * dc + 2) >> 2;
-          else if (y == 0) p = (TOP(x) + 3 * dc + 2) >> 2;
-          else if (x == 0) p = (LEFT(y) + 3 * dc + 2) >> 2;
-        }
-        EMIT(i, y, x, p);
+        g.aA[j] = at(y == 0 ? N2 + 1 + x : N2 - 1 - y); g.wA[j] = 1; g.wC[j] = 3;
+        if (x == 0 && y == 0) { g.aB[j] = at(N2 - 1); g.wB[j] = 1; g.wC[j] = 2; }
       }
     }
+  }
+  else if (cls == OP_ANG0)
+  {
+    const bool ver = flags & OPF_VER, edge = flags & OPF_EDGE;
+    const int sgn = ver ? 1 : -1;
+    if (edge) variant = TV_HVEDGE;                           // wB marks the edge samples, C = corner
+    const int aCorner = edge ? at(N2) : 0;
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      const int i = (first + lane + 32 * j) & (N * N - 1), y = i >> LG, x = i & (N - 1);
+      const int yy = ver ? y : x, xx = ver ? x : y;
+      g.aA[j] = at(N2 + sgn * (xx + 1)); g.wA[j] = 1;
+      if (edge && xx == 0) { g.aB[j] = at(N2 - sgn * (yy + 1)); g.wB[j] = 1; g.aC[j] = aCorner; }
+    }
+  }
+  else if (cls == OP_ANGPOS || cls == OP_ANGNEG)
+  {
+    rnd = 16; sh = 5;
+    const bool ver = flags & OPF_VER;
+    const int sgn = ver ? 1 : -1, angle = op_angle(op), inv = op_inv(op);
+#pragma unroll
+    for (int j = 0; j < S; j++)
+    {
+      const int i = (first + lane + 32 * j) & (N * N - 1), y = i >> LG, x = i & (N - 1);
+      const int yy = ver ? y : x, xx = ver ? x : y;
+      const int pos = (yy + 1) * angle, di = pos >> 5, df = pos & 31;
+      const int k0 = xx + di + 1, k1 = k0 + 1;
+      // negative angle: rm[k < 0] is the side edge projected onto the main edge: side sample ((128 - k*inv) >> 8) - 1  (TComPrediction.cpp:396-404)
+      const int i0 = k0 >= 0 ? N2 + sgn * k0 : N2 - sgn * ((128 - k0 * inv) >> 8);
+      const int i1 = k1 >= 0 ? N2 + sgn * k1 : N2 - sgn * ((128 - k1 * inv) >> 8);
+      g.aA[j] = at(i0); g.wA[j] = 32 - df;
+      g.aB[j] = at(min(4 * N, max(0, i1))); g.wB[j] = df;  // df == 0 at the end of the line: weight 0, any valid entry will do
+    }
+  }
+  // OP_PCM: prediction 0, the samples arrive as the residual
+}
+
+// The turn proper.  Specialised per variant outside the sample loop: the common case is four loads and four multiply-adds per sample.
+template <int LG>
+__device__ __forceinline__ void tap_turn(const TapProg<TapShape<LG>::S>& g, const int variant, const int rnd, const int sh, const int dc,
+                                         int16_t* __restrict__ tile, const int bd, const int lane)
+{
+  constexpr int N = 1 << LG, S = TapShape<LG>::S;
+  const int maxv = (1 << bd) - 1;
+  int A[S], B[S], C[S], D[S], p[S];
+#pragma unroll
+  for (int j = 0; j < S; j++) { A[j] = tile[g.aA[j]]; B[j] = tile[g.aB[j]]; C[j] = tile[g.aC[j]]; D[j] = tile[g.aD[j]]; }
+  if (variant == TV_GENERIC)
+  {
+#pragma unroll
+    for (int j = 0; j < S; j++) p[j] = (g.wA[j] * A[j] + g.wB[j] * B[j] + g.wC[j] * C[j] + g.wD[j] * D[j] + rnd) >> sh;
+  }
+  else if (variant == TV_DC)
+  {
+#pragma unroll
+    for (int j = 0; j < S; j++) p[j] = g.wC[j] == 1 ? dc : (A[j] * g.wA[j] + B[j] * g.wB[j] + dc * g.wC[j] + 2) >> 2;
   }
   else
   {
-    const bool ver = flags & OPF_VER;
-    const int angle = op_angle(op);
-    const int sgn = ver ? 1 : -1;                          // main reference rm[j >= 0] = ref[N2 + sgn*j]
-    if (cls == OP_ANG0)
-    {
-      const bool edge = flags & OPF_EDGE;
-      const int corner = ref[N2];
 #pragma unroll
-      for (int j = 0; j < S; j++)
-      {
-        const int i = lane + 32 * j;
-        if (N * N >= 32 || i < N * N)
-        {
-          const int y = i >> LG, x = i & (N - 1);
-          const int yy = ver ? y : x, xx = ver ? x : y;
-          int p = ref[N2 + sgn * (xx + 1)];
-          if (edge && xx == 0) p = clip3i(0, maxv, p + ((ref[N2 - sgn * (yy + 1)] - corner) >> 1));
-          EMIT(i, y, x, p);
-        }
-      }
-    }
-    else if (cls == OP_ANGPOS)
-    {
-#pragma unroll
-      for (int j = 0; j < S; j++)
-      {
-        const int i = lane + 32 * j;
-        if (N * N >= 32 || i < N * N)
-        {
-          const int y = i >> LG, x = i & (N - 1);
-          const int yy = ver ? y : x, xx = ver ? x : y;
-          const int pos = (yy + 1) * angle, di = pos >> 5, df = pos & 31;
-          const int k = xx + di + 1;
-          const int pa = ref[N2 + sgn * k], pb = ref[N2 + sgn * (k + 1)];   // df == 0: pb has weight 0 (the index stays inside the padded line)
-          const int p = ((32 - df) * pa + df * pb + 16) >> 5;
-          EMIT(i, y, x, p);
-        }
-      }
-    }
-    else
-    {
-      const int inv = op_inv(op);
-      // negative angle: rm[k < 0] is the side edge projected onto the main edge: side sample ((128 - k*inv) >> 8) - 1  (TComPrediction.cpp:396-404)
-#pragma unroll
-      for (int j = 0; j < S; j++)
-      {
-        const int i = lane + 32 * j;
-        if (N * N >= 32 || i < N * N)
-        {
-          const int y = i >> LG, x = i & (N - 1);
-          const int yy = ver ? y : x, xx = ver ? x : y;
-          const int pos = (yy + 1) * angle, di = pos >> 5, df = pos & 31;
-          const int k0 = xx + di + 1, k1 = k0 + 1;
-          const int i0 = k0 >= 0 ? N2 + sgn * k0 : N2 - sgn * ((128 - k0 * inv) >> 8);
-          const int i1 = k1 >= 0 ? N2 + sgn * k1 : N2 - sgn * ((128 - k1 * inv) >> 8);
-          const int pa = ref[i0], pb = ref[i1];
-          const int p = ((32 - df) * pa + df * pb + 16) >> 5;
-          EMIT(i, y, x, p);
-        }
-      }
-    }
+    for (int j = 0; j < S; j++) p[j] = g.wB[j] ? clip3i(0, maxv, A[j] + ((B[j] - C[j]) >> 1)) : A[j];
   }
-#undef LEFT
-#undef TOP
-#undef EMIT
+#pragma unroll
+  for (int j = 0; j < S; j++)
+    if (N * N >= 32 || lane < N * N) tile[g.dst[j]] = (int16_t)clip3i(0, maxv, (int)(int16_t)p[j] + g.res[j]);
+}
+
+// Mean of the 2N nearest reference samples (predIntraGetPredValDC, TComPrediction.cpp:182-207); sT / sL: tile index of this lane's TOP / LEFT sample.
+template <int LG>
+__device__ __forceinline__ int dc_value(const int16_t* __restrict__ tile, const int sT, const int sL, const int lane)
+{
+  constexpr int N = 1 << LG;
+  const int part = (N >= 32 || lane < N) ? (int)tile[sT] + (int)tile[sL] : 0;
+  return (__reduce_add_sync(0xffffffffu, part) + N) >> (LG + 1);
+}
+
+// Smoothing of the reference line of a filtered TU ([0] bottom-most below-left ... [2N] corner ... [4N] last above-right), in the turn:
+// [1 2 1] / 4, or the bilinear "strong" variant of 32x32 luma blocks (TComPattern.cpp:219-306).  Entry i is one lane's job: three loads
+// through the TU's address table (fetched ahead of the turn: line_addrs), one store to line[i]; the participating warps split the entries
+// (4x4 / 8x8: one warp, 16x16 / 32x32: four).  PER = entries per lane.
+template <int LG> struct LineShape { static constexpr int PER = LG == 3 ? 2 : (LG == 5 ? 2 : 1); static constexpr int WARPS = LG >= 4 ? IN_CHAIN_WARPS : 1; };
+template <int LG>
+__device__ __forceinline__ void line_addrs(const IntraOp op, const uint16_t* __restrict__ addrTab, const int part, const int lane, int a[2][3])
+{
+  constexpr int N = 1 << LG, L = 4 * N + 1, PER = LineShape<LG>::PER;
+  const uint16_t* t = addrTab + op_slot(op);
+#pragma unroll
+  for (int j = 0; j < PER; j++)
+  {
+    const int i = min((part * PER + j) * 32 + lane, L - 1);  // lanes past the end repeat the last entry
+    const bool end = i == 0 || i == L - 1;                   // the two end points are copied ((v + 2v + v + 2) >> 2 == v)
+    a[j][0] = t[end ? i : i - 1]; a[j][1] = t[i]; a[j][2] = t[end ? i : i + 1];
+  }
+}
+template <int LG>
+__device__ __forceinline__ void line_phase(const IntraOp op, const uint16_t* __restrict__ addrTab, const int a[2][3], const int part, const int16_t* __restrict__ tile,
+                                           int16_t* __restrict__ line, const int bd, const int lane)
+{
+  constexpr int N = 1 << LG, N2 = 2 * N, L = 4 * N + 1, PER = LineShape<LG>::PER;
+  bool strong = false;
+  int bl = 0, tl = 0, tr = 0;
+  if (N == 32 && (op_flags(op) & OPF_STRONG))
+  {
+    const uint16_t* t = addrTab + op_slot(op);
+    bl = tile[t[0]]; tl = tile[t[N2]]; tr = tile[t[4 * N]];
+    const int mid0 = tile[t[N]], mid1 = tile[t[3 * N]];
+    const int thr = 1 << (bd - 5);
+    strong = abs(bl + tl - 2 * mid0) < thr && abs(tl + tr - 2 * mid1) < thr;
+  }
+#pragma unroll
+  for (int j = 0; j < PER; j++)
+  {
+    const int i = min((part * PER + j) * 32 + lane, L - 1);
+    const int up = tile[a[j][0]], v = tile[a[j][1]], dn = tile[a[j][2]];
+    int r = (up + 2 * v + dn + 2) >> 2;
+    if (strong && i > 0 && i < 4 * N)
+      r = i < N2 ? ((N2 - i) * bl + i * tl + N) >> (LG + 1) : (i == N2 ? tl : ((N2 - (i - N2)) * tl + (i - N2) * tr + N) >> (LG + 1));
+    line[i] = (int16_t)r;
+  }
 }
 
 // ---- pre-pass: everything about the intra TUs that does not depend on sample data, for the whole picture at once ----
@@ -431,20 +450,98 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) intra_prep_kernel(const __gri
   if (lane == 0) P.intra_prep[job] = make_uint4(mn, mx > mn ? mx - mn : 0u, (unsigned)running, 0u);
 }
 
+// -DINTRA_PROFILE: cycle counters of the chain warps (clock64 between the phases of chain_tu, per TU size), summed over the launch
+// into g_intraProf and read back by hmr_debug_intra_profile (tools/intra_profile.py).  Slot = 8 * (lg - 2) + phase.
+#ifdef INTRA_PROFILE
+__device__ unsigned long long g_intraProf[64];
+__device__ unsigned long long g_intraRows[3 * 128 * 4];     // per (component, row): globaltimer at job start, first CTU staged, last TU done, job end
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PROF_DECL long long pt_ = clock64(), pn_
+#define PROF_MARK(phase) do { pn_ = clock64(); prof[8 * (LG - 2) + (phase)] += (unsigned long long)(pn_ - pt_); pt_ = pn_; } while (0)
+#define PROF_ARG , unsigned long long* prof
+#define PROF_PASS , prof
+#else
+#define PROF_DECL
+#define PROF_MARK(phase)
+#define PROF_ARG
+#define PROF_PASS
+#endif
+
 // named barriers (id 0 is __syncthreads)
-#define BAR_FULL 1     // +buffer: stagers arrive, chain waits  -> "CTU staged"
-#define BAR_DONE 3     // +buffer: chain arrives, stagers wait  -> "CTU predicted"
-#define BAR_STAGE 5    // the three stager warps among themselves
-#define IN_STAGERS (IN_THREADS - 32)
+#define BAR_FULL 1     // +buffer: stagers arrive, chain warps wait  -> "CTU staged"
+#define BAR_DONE 3     // +buffer: chain warp 0 arrives, stagers wait -> "CTU predicted"
+#define BAR_STAGE 5    // the stager warps among themselves
+#define BAR_CHAIN 6    // the chain warps among themselves: every TU of the CTU is in the tile
+#define BAR_TOKEN 7    // + (k & 3): TU k is in the tile, the owner of TU k + 1 may take its turn
+#define BAR_COOP 11    // large filtered TU: the four chain warps have each smoothed their part of the reference line
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
+// One TU of the chain for this warp.  4x4 / 8x8 TUs belong to warp k & 3; 16x16 / 32x32 TUs are shared by all four chain warps, a
+// quarter of the samples (and of the reference line) each.  Order inside: PREP (no sample values) -> token -> smoothing of the line
+// (filtered TUs) -> TURN -> pass the token.  Token of TU k = named barrier BAR_TOKEN + (k & 3); who arrives and who waits depends on
+// whether TU k and TU k + 1 are small (S) or large (L):
+//     S -> S   owner(k) arrives, owner(k + 1) waits                                   (64 threads)
+//     S -> L   owner(k) comes straight to the large TU; all four warps wait there     (128)
+//     L -> S   the three warps that do not own k + 1 arrive, owner(k + 1) waits       (128)
+//     L -> L   all four warps wait at the beginning of TU k + 1                       (128)
+// Memory ordering comes from the barriers themselves (PTX ISA, bar: prior shared-memory accesses of the arriving threads are performed
+// relative to the waiting threads once the barrier completes; the producer / consumer pattern st.shared; bar.arrive ... bar.sync; ld.shared).
+template <int LG>
+__device__ __forceinline__ void chain_tu(const IntraOp op, const int k, const int count, const bool prevLarge, const bool nextLarge, const int warp, const int lane,
+                                         const uint16_t* __restrict__ addrTab, const int16_t* __restrict__ resB, int16_t* __restrict__ tile,
+                                         const int lineBase, const int bd PROF_ARG)
+{
+  constexpr int N = 1 << LG, N2 = 2 * N;
+  constexpr bool large = LG >= 4;
+  PROF_DECL;
+  const int flags = op_flags(op);
+  const bool filtered = flags & OPF_FILTER;
+  const int part = large ? warp : 0;
+  TapProg<TapShape<LG>::S> g;
+  int variant, rnd, sh, dc = 0;
+  tap_prep<LG>(op, addrTab, resB, lineBase, part * (N * N / 4), lane, g, variant, rnd, sh);
+  int la[2][3];
+  int sT = 0, sL = 0;
+  if (filtered) line_addrs<LG>(op, addrTab, part, lane, la);
+  if (variant == TV_DC)
+  {
+    const uint16_t* t = addrTab + op_slot(op);
+    const int l = lane & (N - 1);
+    if (filtered) { sT = lineBase + N2 + 1 + l; sL = lineBase + N2 - 1 - l; }      // (HM never smooths for DC; kept consistent with the taps)
+    else          { sT = t[N2 + 1 + l]; sL = t[N2 - 1 - l]; }
+  }
+  PROF_MARK(1);                                              // prep
+  if (k > 0) bar_sync(BAR_TOKEN + ((k - 1) & 3), (large || prevLarge) ? IN_CHAIN : 64);          // TU k - 1 is in the tile
+  PROF_MARK(2);                                              // token wait (nominal: the blocking is deferred to the first dependent access)
+  if (filtered)
+  {
+    line_phase<LG>(op, addrTab, la, part, tile, tile + lineBase, bd, lane);
+    if (large) bar_sync(BAR_COOP, IN_CHAIN); else __syncwarp();
+  }
+  if (variant == TV_DC) dc = dc_value<LG>(tile, sT, sL, lane);       // large TUs: every warp computes the mean itself
+  PROF_MARK(3);                                              // line / DC phase (+ the real token wait)
+  tap_turn<LG>(g, variant, rnd, sh, dc, tile, bd, lane);
+  __syncwarp();
+  PROF_MARK(5);                                              // turn
+#ifdef INTRA_PROFILE
+  prof[8 * (LG - 2)] += 1;
+#endif
+  if (k + 1 < count && !nextLarge)
+  {
+    if (!large) bar_arrive(BAR_TOKEN + (k & 3), 64);
+    else if (((k + 1) & 3) != warp) bar_arrive(BAR_TOKEN + (k & 3), IN_CHAIN);   // the next owner is one of us: it waits with count 128
+  }
+}
+
+// One persistent CTA per (component, CTU row) job; a CTA takes jobs blockIdx.x, blockIdx.x + gridDim.x, ... in ascending order, so
+// pictures with more rows than CTAs can be co-resident (2160p with 16x16 CTUs) still run: a job only waits for the job before it.
 __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant__ FrameParams P, const int resSamples, const int maxRec, const int maxAddr)
 {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   constexpr int TILE_PAD = (IN_TILE + 7) & ~7;
-  int16_t* s_tileB = (int16_t*)s_dyn;                                        // [2][TILE_PAD]
-  int16_t* s_resB = s_tileB + 2 * TILE_PAD;                                  // [2][resSamples] residuals of a CTU, compact layout relative to minoff
+  int16_t* s_tileB = (int16_t*)s_dyn;                                        // [2][TILE_PAD], then [IN_LINE]: the filtered reference line of the TU in flight
+  int16_t* s_resB = s_tileB + 2 * TILE_PAD + IN_LINE;                        // [2][resSamples] residuals of a CTU, compact layout relative to minoff
   // capacities = the largest CTU of THIS picture (engine.cu measures the records): a resident CTA holds its shared memory for
   // the whole wavefront, and at saturation that footprint is what other streams' kernels wait for
   IntraOp* s_ops = (IntraOp*)(s_resB + 2 * resSamples);                      // [2][maxRec] decoded TUs of a CTU
@@ -452,13 +549,21 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   uint4* s_prep = (uint4*)(s_addr + 2 * maxAddr);                            // [ctus_w] per CTU of this row: x = first residual, y = residual span, z = table entries
   uint32_t* s_first = (uint32_t*)(s_prep + P.ctus_w);                        // [ctus_w]
   uint16_t* s_count = (uint16_t*)(s_first + P.ctus_w);                       // [ctus_w]
-  __shared__ int s_refBuf[2][4 * 32 + 8]; // reference line of a TU: [0] bottom-most below-left ... [2N] corner ... [4N] last above-right
-                                          // (two copies, alternating per TU: the next TU may write while a slow lane still reads)
   __shared__ int16_t s_col[IN_MAXCT];     // right-most column of the CTU the chain just finished (left neighbours of the next one)
   __shared__ __align__(8) unsigned long long s_mbar[2];   // one per buffer: completion of the TMA bulk copies
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int comp = blockIdx.x / P.ctus_h, row = blockIdx.x % P.ctus_h;
-  if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) return;
+  const int ctusW = P.ctus_w;
+  if (tid == 0)
+  {
+    mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1);
+    fence_proxy_async();                                       // the barriers exist before the async proxy touches them
+  }
+  int n = 0;                                                   // CTUs staged so far by this CTA (all jobs): buffer = n & 1, mbarrier phase = (n >> 1) & 1
+
+  for (int job = blockIdx.x; job < 3 * P.ctus_h; job += gridDim.x)
+  {
+  const int comp = job / P.ctus_h, row = job % P.ctus_h;
+  if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) break;
   unsigned long long* myProg = P.intra_progress + comp * P.ctus_h + row;
   const volatile unsigned long long* upProg = row > 0 ? P.intra_progress + comp * P.ctus_h + row - 1 : nullptr;
   const unsigned long long base = P.epoch << 32;
@@ -471,79 +576,108 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   g.oy = row * g.CTH; g.ox = 0;
   const int CTW = g.CTW, CTH = g.CTH;
   const int W = P.w[comp], H = P.h[comp];
-  const int ctusW = P.ctus_w;
   int16_t* plane = P.work.p[comp];
   const int pitch = P.work.pitch[comp];
   const int oy = row * CTH, ch = min(CTH, H - oy);
 
+  __syncthreads();                                             // the previous job's readers of the per-row arrays are gone
   for (int c = tid; c < ctusW; c += IN_THREADS)
   {
-    const hmr_ctu_intra_range rg = P.irange[row * ctusW + c];
-    s_first[c] = rg.first[comp];
-    s_count[c] = (uint16_t)min(rg.count[comp], (uint32_t)maxRec);
+    const hmr_ctu_intra_range* rg = P.irange + row * ctusW + c;
+    s_first[c] = rg->first[comp];
+    s_count[c] = (uint16_t)min(rg->count[comp], (uint32_t)maxRec);
     s_prep[c] = P.intra_prep[(size_t)comp * ctusW * P.ctus_h + (size_t)row * ctusW + c];
   }
-  if (tid == 0)
-  {
-    s_tileB[0] = s_tileB[TILE_PAD] = (int16_t)(1 << (bd - 1));
-    mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1);
-    fence_proxy_async();                                       // the barriers exist before the async proxy touches them
-  }
+  if (tid == 0) s_tileB[0] = s_tileB[TILE_PAD] = (int16_t)(1 << (bd - 1));   // the "nothing available" constant
   __syncthreads();
 
   const int c0 = next_intra_ctu(s_count, 0, ctusW, lane);
   if (tid == 0) *(volatile unsigned long long*)myProg = base + (unsigned long long)c0;   // nothing to do before CTU c0
-  if (c0 >= ctusW) return;
+  if (c0 >= ctusW) continue;
 
-  if (warp == 0)
+  if (warp < IN_CHAIN_WARPS)
   {
-    // ============================ chain warp: TU after TU, shared memory only ============================
-    int prev = -2, n = 0;
+    // ============================ chain warps: TU after TU, shared memory only ============================
+    int prev = -2;
+#ifdef INTRA_PROFILE
+    unsigned long long prof[40];
+    for (int i = 0; i < 40; i++) prof[i] = 0;
+    const long long tJob = clock64();
+    if (tid == 0 && row < 128) g_intraRows[(comp * 128 + row) * 4 + 0] = gtime();
+    bool firstCtu = true;
+#endif
     for (int c = c0; c < ctusW; c = next_intra_ctu(s_count, c + 1, ctusW, lane), n++)
     {
       const int b = n & 1;
       int16_t* tile = s_tileB + b * TILE_PAD;
+      const int lineBase = (2 - b) * TILE_PAD + 8;            // the line buffer behind the tiles, as an index of THIS tile (entries -1 .. 4N+1 valid)
       const IntraOp* ops = s_ops + b * maxRec;
       const uint16_t* addrTab = s_addr + b * maxAddr;
       const int16_t* resB = s_resB + b * resSamples;
       const int count = s_count[c];
       const int ox = c * CTW;
+#ifdef INTRA_PROFILE
+      const long long tf0 = clock64();
+#endif
       bar_sync(BAR_FULL + b, IN_THREADS);                    // staged: tile, decoded TUs, tables, residuals
       mbar_wait(&s_mbar[b], (n >> 1) & 1);                   // (already complete: makes the bulk-copied bytes visible to this warp)
-      if (prev == c - 1)                                     // left neighbours = what this warp produced a moment ago
+#ifdef INTRA_PROFILE
+      asm volatile("" :: "r"(ops[0].x) : "memory");
+      prof[32] += (unsigned long long)(clock64() - tf0); prof[33] += 1;
+      if (firstCtu && tid == 0 && row < 128) g_intraRows[(comp * 128 + row) * 4 + 1] = gtime();
+      firstCtu = false;
+#endif
+      if (warp == 0 && prev == c - 1)                        // left neighbours = what the chain produced a moment ago
+      {
         for (int y = lane; y < ch; y += 32) tile[TIDX(y, -1)] = s_col[y];
-      IntraOp op = ops[0];
-      int a[IN_NJMAX], an[IN_NJMAX];
-      intra_fetch_addrs(op, addrTab, lane, a);
-      __syncwarp();
+        __syncwarp();
+      }
+      bool prevLarge = false;
+      IntraOp opn = ops[0];
       for (int k = 0; k < count; k++)
       {
-        const bool hasNext = k + 1 < count;
-        const IntraOp opn = ops[hasNext ? k + 1 : k];
-        int* sref = &s_refBuf[0][2] + (k & 1) * (4 * 32 + 8);   // indices -1 and 4N+1 are touched (with weight 0) by the 45-degree modes
+        const IntraOp op = opn;
+        if (k + 1 < count) opn = ops[k + 1];
         const int lg = op_lg(op);                            // compare chain, most frequent first (a jump table costs an indirect branch per TU)
-        if (lg == 3)      intra_tu<3>(op, a, hasNext, opn, an, addrTab, tile, resB, sref, bd, lane);
-        else if (lg == 2) intra_tu<2>(op, a, hasNext, opn, an, addrTab, tile, resB, sref, bd, lane);
-        else if (lg == 4) intra_tu<4>(op, a, hasNext, opn, an, addrTab, tile, resB, sref, bd, lane);
-        else              intra_tu<5>(op, a, hasNext, opn, an, addrTab, tile, resB, sref, bd, lane);
-        __syncwarp();        // this TU's samples are in the tile before the next TU gathers its reference line
-        op = opn;
-#pragma unroll
-        for (int j = 0; j < IN_NJMAX; j++) a[j] = an[j];
+        const bool nextLarge = k + 1 < count && op_lg(opn) >= 4;
+        if (lg <= 3)
+        {
+          if ((k & 3) == warp)
+          {
+            if (lg == 3) chain_tu<3>(op, k, count, prevLarge, nextLarge, warp, lane, addrTab, resB, tile, lineBase, bd PROF_PASS);
+            else         chain_tu<2>(op, k, count, prevLarge, nextLarge, warp, lane, addrTab, resB, tile, lineBase, bd PROF_PASS);
+          }
+          prevLarge = false;
+        }
+        else
+        {
+          if (lg == 4) chain_tu<4>(op, k, count, prevLarge, nextLarge, warp, lane, addrTab, resB, tile, lineBase, bd PROF_PASS);
+          else         chain_tu<5>(op, k, count, prevLarge, nextLarge, warp, lane, addrTab, resB, tile, lineBase, bd PROF_PASS);
+          prevLarge = true;
+        }
       }
-      const int cwc = min(CTW, W - ox);
-      for (int y = lane; y < ch; y += 32) s_col[y] = tile[TIDX(y, cwc - 1)];
+      bar_sync(BAR_CHAIN, IN_CHAIN);                         // every TU of the CTU is in the tile
+      if (warp == 0)
+      {
+        const int cwc = min(CTW, W - ox);
+        for (int y = lane; y < ch; y += 32) s_col[y] = tile[TIDX(y, cwc - 1)];
+        __syncwarp();
+        __threadfence_block();
+        bar_arrive(BAR_DONE + b, 32 + IN_STAGERS);           // predicted: the stagers write it back and publish
+      }
       prev = c;
-      __syncwarp();
-      __threadfence_block();
-      bar_arrive(BAR_DONE + b, IN_THREADS);                  // predicted: the stagers write it back and publish
     }
-    return;
+#ifdef INTRA_PROFILE
+    if (tid == 0 && row < 128) g_intraRows[(comp * 128 + row) * 4 + 2] = gtime();
+    prof[34] += (unsigned long long)(clock64() - tJob);
+    if (lane == 0) for (int i = 0; i < 40; i++) if (prof[i]) atomicAdd(&g_intraProf[i], prof[i]);
+#endif
+    continue;
   }
 
   // ============================ stager warps: everything that touches global memory ============================
-  const int st = tid - 32;
-  int prev = -2, prevB = 0, n = 0;
+  const int st = tid - IN_CHAIN;
+  int prev = -2, prevB = 0;
   for (int c = c0; c < ctusW; n++)
   {
     const int b = n & 1;
@@ -597,7 +731,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
       if (st == 0)
       {
         const unsigned long long need = base + (unsigned long long)min(c + 2, ctusW);
-        while (*upProg < need) { }
+        while (*upProg < need) __nanosleep(20);              // back off: the SM's issue slots belong to the chain warps
         __threadfence();
       }
       bar_sync(BAR_STAGE, IN_STAGERS);
@@ -615,7 +749,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
     // ---- write back + publish the CTU the chain is finishing meanwhile ----
     if (prev >= 0)
     {
-      bar_sync(BAR_DONE + prevB, IN_THREADS);
+      bar_sync(BAR_DONE + prevB, 32 + IN_STAGERS);
       const int16_t* ptile = s_tileB + prevB * TILE_PAD;
       const int pox = prev * CTW, pcw = min(CTW, W - pox);
       if ((pcw & 7) == 0)
@@ -648,7 +782,7 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   }
   // ---- the last CTU of the row ----
   {
-    bar_sync(BAR_DONE + prevB, IN_THREADS);
+    bar_sync(BAR_DONE + prevB, 32 + IN_STAGERS);
     const int16_t* ptile = s_tileB + prevB * TILE_PAD;
     const int pox = prev * CTW, pcw = min(CTW, W - pox);
     const int unit = (pcw & 7) == 0 ? 8 : 4, vecPerRow = pcw / unit;
@@ -665,7 +799,10 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
       *(volatile unsigned long long*)myProg = base + (unsigned long long)ctusW;
     }
   }
+  }   // jobs
 }
+
+static int g_coopLimit[16] = {0};          // co-resident intra CTAs per device at worst-case shared memory (intra_max_coresident_blocks)
 
 static int intra_res_samples(const FrameParams& P)
 {
@@ -674,7 +811,7 @@ static int intra_res_samples(const FrameParams& P)
 }
 static size_t intra_dyn_smem(int resSamples, int maxRec, int maxAddr, int ctusW)
 {
-  return 2 * ((size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + (size_t)maxRec * 16 + (size_t)maxAddr * sizeof(uint16_t)) +
+  return (size_t)IN_LINE * 2 + 2 * ((size_t)((IN_TILE + 7) & ~7) * 2 + (size_t)resSamples * 2 + (size_t)maxRec * 16 + (size_t)maxAddr * sizeof(uint16_t)) +
          (size_t)ctusW * (sizeof(uint4) + sizeof(uint32_t) + sizeof(uint16_t));
 }
 
@@ -704,6 +841,27 @@ IntraSizes intra_sizes_host(const hmr_frame_hdr& h, const hmr_intra* rec, const 
   return z;
 }
 
+extern "C" int hmr_debug_intra_profile(unsigned long long out[64], int reset)
+{
+#ifdef INTRA_PROFILE
+  if (cudaMemcpyFromSymbol(out, g_intraProf, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_intraProf, z, sizeof(z)); }
+  return 0;
+#else
+  (void)out; (void)reset;
+  return -3;      // built without -DINTRA_PROFILE
+#endif
+}
+extern "C" int hmr_debug_intra_rows(unsigned long long out[3 * 128 * 4])
+{
+#ifdef INTRA_PROFILE
+  return cudaMemcpyFromSymbol(out, g_intraRows, sizeof(unsigned long long) * 3 * 128 * 4) == cudaSuccess ? 0 : -1;
+#else
+  (void)out;
+  return -3;      // built without -DINTRA_PROFILE
+#endif
+}
+
 size_t intra_table_bytes(int nctu) { return (size_t)3 * nctu * IN_ADDR * sizeof(uint16_t); }
 
 int intra_max_coresident_blocks(int device)
@@ -713,6 +871,7 @@ int intra_max_coresident_blocks(int device)
   cudaFuncSetAttribute(intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, intra_kernel, IN_THREADS, worst);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  g_coopLimit[device & 15] = perSm * sms;
   return perSm * sms;
 }
 
@@ -727,5 +886,9 @@ cudaError_t launch_intra(const FrameParams& P, cudaStream_t s)
   int maxAddr = P.intra_max_addr > 0 ? min(IN_ADDR, (P.intra_max_addr + 7) & ~7) : IN_ADDR;
   intra_prep_kernel<<<(3 * P.ctus_w * P.ctus_h + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, s>>>(P);
   void* args[] = { (void*)&P, (void*)&resSamples, (void*)&maxRec, (void*)&maxAddr };
-  return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(3 * P.ctus_h), dim3(IN_THREADS), args, intra_dyn_smem(resSamples, maxRec, maxAddr, P.ctus_w), s);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int limit = g_coopLimit[dev & 15] > 0 ? g_coopLimit[dev & 15] : 3 * P.ctus_h;
+  const int grid = min(3 * P.ctus_h, limit);                // more jobs than co-resident CTAs: a CTA takes several, in ascending order
+  return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(grid), dim3(IN_THREADS), args, intra_dyn_smem(resSamples, maxRec, maxAddr, P.ctus_w), s);
 }
