@@ -32,6 +32,7 @@ WORKLOAD = "c3_ra10_2160p"
 DATA = os.path.join(ROOT, "bench_data")
 TAPPDEC = os.path.join(ROOT, "oracle", "_ref", "TAppDecoderStatic")
 CLI = os.path.join(ROOT, "frontend", "_build", "hmdec_mt")
+DUMP_CLI = os.path.join(ROOT, "frontend", "_build", "hmdec_cli")
 
 
 def _paths(name):
@@ -156,9 +157,38 @@ def run_many(cmds, env=None):
     return time.perf_counter() - t0, rcs
 
 
-def count_frames(bitstream_records):
+def count_pictures(bitstream):
+    """Coded pictures of an Annex-B stream: VCL NAL units (type < 32) whose first_slice_segment_in_pic_flag is set."""
+    data = open(bitstream, "rb").read()
+    n, pos = 0, data.find(b"\x00\x00\x01")
+    while pos >= 0 and pos + 5 < len(data):
+        if ((data[pos + 3] >> 1) & 0x3f) < 32 and (data[pos + 5] & 0x80):
+            n += 1
+        pos = data.find(b"\x00\x00\x01", pos + 3)
+    return n
+
+
+_FRAMES = {}
+
+
+def load_frames(name):
+    """Per-picture records of a workload: the committed dump (bench_data/<name>.hmr.gz, with HM's golden MD5s), or — streams shipped
+    as bitstream only — a records-only dump made on the spot by the drop-in's own host parser (hmdec_cli --dump: no GPU, nothing reconstructed)."""
+    if name in _FRAMES:
+        return _FRAMES[name]
     from libhm_b200 import records
-    return len(records.read_dump(bitstream_records))
+    rec, bitstream = _paths(name)
+    if os.path.exists(rec):
+        fr = records.read_dump(rec)
+    else:
+        with tempfile.TemporaryDirectory() as td:
+            out = os.path.join(td, name + ".hmr")
+            subprocess.run([DUMP_CLI, "-b", bitstream, "--dump", out, "--no-hash"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=dict(os.environ, HMDEC_B200_QUIET="1"))
+            fr = records.read_dump(out)
+        for f in fr:
+            f.gold = None
+    _FRAMES[name] = fr
+    return fr
 
 
 def reference_pass(bitstream, nproc, passes=1):
@@ -185,6 +215,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the further workloads (configs[4] eight LD-B streams, fractional-pan, QP27)")
     a = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL's version banner, for one) goes to stderr
     real_stdout = os.dup(1)
@@ -203,8 +234,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        from libhm_b200 import records
-        nframes = len(records.read_dump(rec_path))
+        nframes = count_pictures(bin_path)
         for _ in range(min(a.warmup, 1)):
             reference_pass(bin_path, ncores)
         wall = reference_pass(bin_path, ncores, passes=a.steps)
@@ -228,51 +258,152 @@ def main():
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    frames = records.read_dump(rec_path)
-    F = len(frames)
-    S = a.streams
-    engines = [engine.Engine(local_rank) for _ in range(S)]
-    handles = [[e.upload(f) for f in frames] for e in engines]
-    rec_bytes = sum(f.nbytes() for f in frames)
-    plane_bytes = sum(2 * w * h for (w, h) in (frames[0].comp_size(c) for c in range(3)))
+    my_cores = sharding.host_cores_of_rank(ncores, world, local_rank)
+    cores_rank = len(my_cores)
 
-    def step():
-        for e, hs in zip(engines, handles):
-            e.run_resident_list(hs)
-
-    def barrier():
+    def barrier(engines):
         for e in engines:
             e.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    for _ in range(max(a.warmup, 3)):
-        step()
-    barrier()
-    # parity guard inside the bench: the last picture of every stream must carry HM's MD5
-    for e in engines:
-        got = e.read_picture(int(frames[-1].h["out_slot"]))
-        assert (records.picture_md5(got, [frames[-1].bit_depth(c) for c in range(3)]) == frames[-1].gold[2]).all(), "bench: GPU picture != HM golden MD5"
-    for e in engines:
-        e.stage_times()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    engines[0].timer_begin()
-    for _ in range(a.steps):
-        step()
-    for e in engines[1:]:
-        engines[0].timer_join(e)
-    ms = engines[0].timer_end()
-    barrier()
-    clocks = sampler.stop()
-    launches = sum(e.stage_times()[2] for e in engines)
-    frames_total, ms = sharding.reduce_measurement(S * F * a.steps, ms, device="cuda")     # frames summed, time = max over ranks
-    value = sharding.frames_per_second(frames_total, ms)
+    def check_last_picture(e, frames, name):
+        """Parity guard inside the bench: the last picture must carry the MD5 HM computed for it (GOLD section of the dump, or the
+        line the unmodified TAppDecoder printed: bench_data/<name>.md5, decoding order)."""
+        fr = frames[-1]
+        got = records.picture_md5(e.read_picture(int(fr.h["out_slot"])), [fr.bit_depth(c) for c in range(3)])
+        if fr.gold is not None:
+            want = fr.gold[2]
+        else:
+            last = [l for l in open(os.path.join(DATA, name + ".md5")) if "MD5:" in l][-1]
+            want = np.frombuffer(bytes.fromhex("".join(last.split("[MD5:")[1].split(",(")[0].split(","))), np.uint8).reshape(3, 16)
+        assert (got == want).all(), f"bench: GPU picture != HM's MD5 ({name})"
+
+    def resident_value(stream_names, steps, warmup, submit=False, sample_clocks=False):
+        """frames/s of this rank's engines, one engine (CUDA stream, DPB) per entry of stream_names, every engine reconstructing its
+        whole sequence once per step.  submit=False: records resident in HBM (hmr_run_resident).  submit=True: every picture's
+        records go from host memory through hmr_submit_frame — validation, packing into the page-locked ring and the H2D copy are
+        inside the timed region — fed by one host thread per engine.  Returns (frames per step, ms of the timed steps, launches, engines' frame lists)."""
+        from concurrent.futures import ThreadPoolExecutor
+        framesets = {n: load_frames(n) for n in set(stream_names)}
+        engines = [engine.Engine(local_rank) for _ in stream_names]
+        for e in engines:
+            e.lib.hmr_set_validation(e.h, 1)                 # the bench's records come from this repo's own emitter
+        if submit:
+            descs = [[f.desc() for f in framesets[n]] for n in stream_names]
+            pool = ThreadPoolExecutor(len(engines))
+
+            def feed(i):
+                e = engines[i]
+                for d in descs[i]:
+                    e.submit_desc(d)
+
+            def step():
+                list(pool.map(feed, range(len(engines))))
+        else:
+            handles = [[e.upload(f) for f in framesets[n]] for e, n in zip(engines, stream_names)]
+
+            def step():
+                for e, hs in zip(engines, handles):
+                    e.run_resident_list(hs)
+        for _ in range(max(warmup, 3)):
+            step()
+        barrier(engines)
+        for e, n in zip(engines, stream_names):
+            e.sizes = [framesets[n][0].comp_size(c) for c in range(3)]
+            check_last_picture(e, framesets[n], n)
+            e.stage_times()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier(engines)
+        t_wall = time.time()
+        engines[0].timer_begin()
+        for _ in range(steps):
+            step()
+        for e in engines[1:]:
+            engines[0].timer_join(e)
+        ms = engines[0].timer_end()
+        barrier(engines)
+        launches = sum(e.stage_times()[2] for e in engines)
+        if sampler:
+            # nvidia-smi reports every 200 ms: keep the same load running (untimed) until the sampler has seen it for >= 1.2 s
+            while time.time() - t_wall < 1.2:
+                step()
+                for e in engines:
+                    e.sync()
+            clock_box.append(sampler.stop())
+        per_step = sum(len(framesets[n]) for n in stream_names)
+        if submit:
+            pool.shutdown()
+        return per_step, ms, launches, engines, (None if submit else handles), framesets
+
+    def close_engines(engines, handles):
+        for i, e in enumerate(engines):
+            if handles:
+                for h in handles[i]:
+                    e.free_resident(h)
+            e.close()
+
+    def e2e_run(bins, thr, passes, extra_args=()):
+        """hmdec_mt (frontend/): ONE process per rank (one CUDA context, process-wide buffer pools and MD5 service), `thr` decoder threads,
+        thread t on stream t % len(bins), through the libHMDec_* entry points on the Annex-B bytes.  Returns (fps over all ranks, result of this rank)."""
+        env = dict(os.environ, HMDEC_B200_DEVICE=str(local_rank), HMDEC_B200_QUIET="1")
+        t0 = torch.tensor([time.time() + 12.0 + 0.4 * thr], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.broadcast(t0, 0)
+        cmd = [CLI] + [x for b in bins for x in ("-b", b)] + ["--threads", str(thr), "--repeat", str(passes), "--start-at", f"{float(t0.item()):.3f}"] + list(extra_args)
+        if world > 1:
+            cmd = ["taskset", "-c", f"{my_cores[0]}-{my_cores[0] + cores_rank - 1}"] + cmd
+        res, good = None, False
+        if bins:
+            pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+            try:
+                res = json.loads(pr.stdout.strip().splitlines()[-1])
+                good = res["failures"] == 0 and pr.returncode == 0
+            except Exception:
+                res, good = None, False
+            if not good:
+                sys.stderr.write(f"bench: hmdec_mt failed (rc {pr.returncode}): {' '.join(cmd)}\n{pr.stdout[-500:]}\n{pr.stderr[-1500:]}\n")
+        tt = torch.tensor([-res["t_start"] if good else 0.0, res["t_end"] if good else 1e30, float(res["pictures"]) if good else 0.0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            both = tt[:2].clone()
+            dist.all_reduce(both, op=dist.ReduceOp.MAX)          # latest end, earliest start (negated)
+            dist.all_reduce(tt[2:], op=dist.ReduceOp.SUM)
+            tt[:2] = both
+        wall = float(tt[1].item()) + float(tt[0].item())
+        return (float(tt[2].item()) / wall if wall < 1e20 and wall > 0 else None), res
+
+    def reference_fps(bins):
+        """The unmodified TAppDecoder, one process per host core, core i on stream i % len(bins); frames/s over all cores."""
+        if not os.path.exists(TAPPDEC):
+            return None
+        from libhm_b200 import records as _r
+        cmds = [["taskset", "-c", str(i), TAPPDEC, "-b", bins[i % len(bins)], "-d", "0"] for i in range(ncores)]
+        wall, rcs = run_many(cmds)
+        if any(rcs):
+            return None
+        pics = sum(count_pictures(bins[i % len(bins)]) for i in range(ncores))
+        return {"value": round(pics / wall, 3), "unit": "frames/s", "cores": ncores, "kind": "reference", "sample": "one pass per core, TAppDecoderStatic -d 0 (SEI MD5 check on)"}
+
+    thr = cores_rank + cores_rank // 2      # 1.5 decoder threads per host core: the surplus fills the ~0.13 s a finishing decoder waits for its last MD5 chains
+    have_cli = os.path.exists(CLI)
+
+    # ---- headline: `value` = 8 copies of the stream per GPU, records resident in HBM
+    S = a.streams
+    clock_box = []
+    per_step, ms, launches, engines, handles, framesets = resident_value([a.workload] * S, a.steps, a.warmup, sample_clocks=True)
+    clocks = clock_box[0]
+    frames = framesets[a.workload]
+    F = len(frames)
+    rec_bytes = sum(f.nbytes() for f in frames)
+    plane_bytes = sum(2 * w * h for (w, h) in (frames[0].comp_size(c) for c in range(3)))
+    frames_total, ms_all = sharding.reduce_measurement(per_step * a.steps, ms, device="cuda")     # frames summed, time = max over ranks
+    value = sharding.frames_per_second(frames_total, ms_all)
 
     # ---- per-kernel durations, single stream, CUDA events around every launch (live, same process)
     kern = {}
     roof = None
+    plane_sum_per_pass = None
     if rank == 0:
         e0 = engines[0]
         e0.enable_timing(True)
@@ -298,51 +429,43 @@ def main():
         traffic, traffic_src = ncu_traffic({"deblock_v": "deblock", "deblock_h": "deblock"}.get(top, top))
         roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": kern[top]["frac"],
                 "traffic": traffic, "traffic_source": (traffic_src + ": ncu --set full, the launch of the I picture (the heaviest launch of the pass; `achieved` averages all pictures)") if traffic_src else None,
-                "peak_source": peak_src, "note": "algorithmic bytes / CUDA-event duration, single-stream pass; all kernels in `kernels`; intra is bounded by its dependency chain, not by HBM (DESIGN.md K3)"}
-    for e, hs in zip(engines, handles):
-        for h in hs:
-            e.free_resident(h)
-        e.close()
+                "peak_source": peak_src, "single_stream_us_per_picture": round(1000 * tot / reps / F, 1),
+                "note": "algorithmic bytes / CUDA-event duration, single-stream pass; all kernels in `kernels`; intra is bounded by its dependency chain, not by HBM (DESIGN.md K3)"}
+        # what a caller that reads EVERY sample must find: sum over the pictures of one pass of (sample & 0xfff), from the engine's own planes
+        tot_sum = 0
+        for f, h in zip(frames, handles[0]):
+            e0.run_resident(h)
+            tot_sum += sum(int((p.astype(np.int64) & 0xfff).sum()) for p in e0.read_picture(int(f.h["out_slot"])))
+        plane_sum_per_pass = tot_sum
+    close_engines(engines, handles)
 
-    # ---- end to end through libHMDec_* on the bitstream bytes: one decoder process per host core of this rank
-    e2e = None
-    my_cores = sharding.host_cores_of_rank(ncores, world, local_rank)
-    cores_rank = len(my_cores)
-    if not a.no_e2e and os.path.exists(CLI) and os.path.exists(bin_path):
-        # decoder front ends: ONE process per rank (one CUDA context, process-wide buffer pools and MD5 service), 1.5 decoder
-        # threads per host core of this rank: the surplus threads fill the ~0.13 s a finishing decoder waits for its last
-        # MD5 chains
-        thr = cores_rank + cores_rank // 2
-        nproc = 1
+    # ---- value_submit: the same job with every picture's records coming from host memory through hmr_submit_frame (H2D in the timed region)
+    sub_steps = max(2, a.steps // 2)
+    ps2, ms2, _, eng2, _, _ = resident_value([a.workload] * S, sub_steps, 3, submit=True)
+    ft2, ms2 = sharding.reduce_measurement(ps2 * sub_steps, ms2, device="cuda")
+    value_submit = {"value": round(sharding.frames_per_second(ft2, ms2), 3), "unit": "frames/s", "h2d_bytes_per_step": int(rec_bytes * S), "steps": sub_steps,
+                    "note": f"records of every picture from host memory through hmr_submit_frame: validation + packing into the page-locked ring + cudaMemcpyAsync inside the timed region; {S} engines per GPU, one feeding host thread each; no parse, no D2H"}
+    close_engines(eng2, None)
+
+    # ---- end to end through libHMDec_* on the bitstream bytes
+    e2e = e2e_single = e2e_read = None
+    if not a.no_e2e and have_cli and os.path.exists(bin_path):
         passes = 3
-        env = dict(os.environ, HMDEC_B200_DEVICE=str(local_rank), HMDEC_B200_QUIET="1")
-        t0 = torch.tensor([time.time() + 20.0], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.broadcast(t0, 0)
-        start = float(t0.item())
-        first_core = my_cores[0]
-        cmd = [CLI, "-b", bin_path, "--threads", str(thr), "--repeat", str(passes), "--start-at", f"{start:.3f}"]
-        if world > 1:
-            cmd = ["taskset", "-c", f"{first_core}-{first_core + cores_rank - 1}"] + cmd
-        ps = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env) for p in range(nproc)]
-        outs = [p.communicate()[0] for p in ps]
-        try:
-            res = [json.loads(o.strip().splitlines()[-1]) for o in outs]
-            good = all(r["failures"] == 0 for r in res) and sum(r["pictures"] for r in res) == nproc * thr * passes * F and all(p.returncode == 0 for p in ps)
-            t_first, t_last = min(r["t_start"] for r in res), max(r["t_end"] for r in res)
-        except Exception:
-            good, t_first, t_last = False, 0.0, 0.0
-        tt = torch.tensor([-t_first if good else 0.0, t_last if good else 1e30], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)          # latest end, earliest start (negated)
-        wall = float(tt[1].item()) + float(tt[0].item())
-        if wall < 1e20:
-            e2e = {"value": round(world * nproc * thr * passes * F / wall, 3), "unit": "frames/s",
-                   "h2d_bytes_per_step": int(rec_bytes), "d2h_bytes_per_step": int(plane_bytes * F),
+        fps, res = e2e_run([bin_path], thr, passes)
+        if fps:
+            e2e = {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": int(rec_bytes), "d2h_bytes_per_step": int(plane_bytes * F),
                    "host_cores": cores_rank, "decoder_threads": thr,
-                   "note": f"libHMDec_* drop-in on Annex-B bytes: 1 process x {thr} decoder threads per GPU on {cores_rank} host cores; host CABAC parse (HM) + pinned H2D of records + kernels + DMA of every output picture into the planes libHMDEC_get_image_plane returns (caller touches all 3 planes of every picture) + SEI MD5 of every picture verified (device-side chains); a new decoder per pass, {passes} passes of the {F}-picture stream per thread after one warm-up pass, common start, wall clock to the last finisher"}
+                   "note": f"libHMDec_* drop-in on Annex-B bytes: 1 process x {thr} decoder threads per GPU on {cores_rank} host cores; host CABAC parse (HM) + pinned H2D of records + kernels + DMA of every output picture into the planes libHMDEC_get_image_plane returns + SEI MD5 of every picture verified on the GPU; {passes} passes of {F} pictures per thread after 1 warm-up pass; bytes are per stream pass"}
         else:
             e2e = {"value": None, "unit": "frames/s", "error": "hmdec_mt failed"}
+        if rank == 0 and world == 1:
+            # what ONE caller gets (a YUView-style player: one decoder, one thread), and the full rate with the caller reading every sample
+            fps1, _ = e2e_run([bin_path], 1, 2)
+            e2e_single = {"value": round(fps1, 3) if fps1 else None, "unit": "frames/s", "decoder_threads": 1, "note": "one decoder thread, one bitstream: parse-bound (HM's CABAC on one core)"}
+            fpsr, resr = e2e_run([bin_path], thr, 1, ["--sum-planes"])
+            ok = bool(resr) and plane_sum_per_pass is not None and int(resr["plane_sum"]) == plane_sum_per_pass * thr * 1
+            e2e_read = {"value": round(fpsr, 3) if fpsr else None, "unit": "frames/s", "decoder_threads": thr, "plane_sum_matches_engine": ok,
+                        "note": "as e2e, but the caller reads EVERY sample of every returned plane (64-bit sum); the sum equals the one computed from the engine's own planes"}
 
     # ---- CPU baseline: the reference decoder itself on this box's cores (rank 0, N = 1 only)
     cpu = None
@@ -351,16 +474,56 @@ def main():
         cpu = {"value": round(F * ncores / wall, 3), "unit": "frames/s", "cores": ncores, "kind": "reference",
                "sample": f"one pass of the {F}-picture stream per core, TAppDecoderStatic -d 0 (SEI MD5 check on), one process per core"}
 
+    # ---- further workloads (same method; their own e2e and reference numbers)
+    extra = {}
+    if not a.no_extra:
+        # BASELINE.json configs[4]: EIGHT DISTINCT 2160p Main10 low-delay-B streams, 8 / 4 / 2 / 1 per GPU on 1 / 2 / 4 / 8 GPUs (a fixed job: strong scaling)
+        c5 = [f"c5_ld10_2160p_s{k}" for k in range(50, 58)]
+        if all(os.path.exists(os.path.join(DATA, n + ".bin")) for n in c5):
+            mine = [c5[i] for i in sharding.assign_streams(len(c5), world, rank)] if world <= len(c5) else []
+            ent = {"config": {"workload": "c5_ld10_2160p_s50..57: BASELINE.json configs[4], eight distinct 3840x2160 Main10 low-delay-B streams (encoder_lowdelay_main10.cfg), 17 pictures each, decoded concurrently",
+                              "streams_total": len(c5), "streams_per_gpu": len(mine), "scaling": "strong"}}
+            if mine:
+                ps, msx, _, engx, hx, _ = resident_value(mine, a.steps, 3)
+                close_engines(engx, hx)
+            else:
+                ps, msx = 0, 0.0
+            ft, msx = sharding.reduce_measurement(ps * a.steps, msx, device="cuda")
+            ent["value"] = round(sharding.frames_per_second(ft, msx), 3)
+            if have_cli and not a.no_e2e:
+                fps, _ = e2e_run([os.path.join(DATA, n + ".bin") for n in mine], thr, 4)
+                ent["e2e"] = {"value": round(fps, 3) if fps else None, "unit": "frames/s", "decoder_threads": thr, "host_cores": cores_rank}
+            if rank == 0 and world == 1 and not a.no_cpu_baseline:
+                ent["reference"] = reference_fps([os.path.join(DATA, n + ".bin") for n in c5])
+            extra["c5_ld10_2160p"] = ent
+        if world == 1:
+            for name, what in (("f_ra10_2160p", "the headline configuration on a source that pans by 2.75 / 1.25 samples per picture: 70 % of the predicted luma area uses fractional motion vectors (the headline source pans by whole samples)"),
+                               ("q27_ra10_2160p", "the headline configuration at QP 27 (SURVEY.md §8d's second operating point): 4.6 MB for 33 pictures, 0.13 bit/pixel, 3.8x the bits of the QP32 stream")):
+                if not os.path.exists(os.path.join(DATA, name + ".bin")):
+                    continue
+                ent = {"config": {"workload": f"{name}: {what}", "streams_per_gpu": S}}
+                ps, msx, _, engx, hx, fsx = resident_value([name] * S, max(2, a.steps // 2), 3)
+                close_engines(engx, hx)
+                ent["value"] = round(sharding.frames_per_second(ps * max(2, a.steps // 2), msx), 3)
+                ent["record_MB_per_picture"] = round(sum(f.nbytes() for f in fsx[name]) / len(fsx[name]) / 1e6, 3)
+                if have_cli and not a.no_e2e:
+                    fps, _ = e2e_run([os.path.join(DATA, name + ".bin")], thr, 2)
+                    ent["e2e"] = {"value": round(fps, 3) if fps else None, "unit": "frames/s", "decoder_threads": thr, "host_cores": cores_rank}
+                if not a.no_cpu_baseline:
+                    ent["reference"] = reference_fps([os.path.join(DATA, name + ".bin")])
+                extra[name] = ent
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
     line = {"metric": "decoded frames/s", "value": round(value, 3), "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "ms_per_step": round(ms_all / a.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
             "config": dict(cfg, streams_per_gpu=S, pictures_per_stream=F, l2="working set (DPB + work planes of all streams) > 126 MB L2; no explicit flush",
                            parallelism=f"{world} GPU x {S} independent streams, no collective"),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kern, "cpu_baseline": cpu}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+            "value_submit": value_submit, "e2e_single_stream": e2e_single, "e2e_planes_read": e2e_read, "extra": extra}
     emit(line)
     return 0
 

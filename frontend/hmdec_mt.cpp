@@ -61,11 +61,12 @@ static libHMDec_context* decodePass(Shared& sh, int which, long& pictures, uint6
             const int st = libHMDEC_get_picture_stride(pic, (libHMDec_ColorComponent)c);
             for (int y = 0; y < h; y++, p += st)
             {
-              // four 16-bit lanes per 64-bit word, summed without carries between lanes for up to 2^16 words of 12-bit samples
-              uint64_t acc = 0;
+              // two accumulators of two 32-bit lanes each: the even and the odd 16-bit samples of every 64-bit word (no carries between
+              // lanes for rows of up to 2^20 samples of 12 bits)
+              uint64_t even = 0, odd = 0;
               int x = 0;
-              for (; x + 4 <= w; x += 4) { uint64_t v; memcpy(&v, p + x, 8); acc += v & 0x0fff0fff0fff0fffull; }
-              sink += (acc & 0xffff) + ((acc >> 16) & 0xffff) + ((acc >> 32) & 0xffff) + (acc >> 48);
+              for (; x + 4 <= w; x += 4) { uint64_t v; memcpy(&v, p + x, 8); v &= 0x0fff0fff0fff0fffull; even += v & 0x0000ffff0000ffffull; odd += (v >> 16) & 0x0000ffff0000ffffull; }
+              sink += (even & 0xffffffffull) + (even >> 32) + (odd & 0xffffffffull) + (odd >> 32);
               for (; x < w; x++) sink += (uint64_t)(p[x] & 0x0fff);
             }
           }
@@ -104,7 +105,7 @@ static void worker(Shared* sh, int core, int which)
   }
   if (collect(prev)) sh->failures++;
   prev = NULL;
-  pics = 0;
+  pics = 0; sink = 0;
   sh->ready++;
   while (!sh->go.load()) std::this_thread::yield();
   for (int r = 0; r < sh->repeat; r++)

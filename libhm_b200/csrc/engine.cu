@@ -319,7 +319,7 @@ static int ensure_geometry(hmr_engine* e, const hmr_frame_hdr& h)
     e->ctusW = (h.width + (1 << h.log2_ctu) - 1) >> h.log2_ctu;
     e->ctusH = (h.height + (1 << h.log2_ctu) - 1) >> h.log2_ctu;
     if (e->coopLimit < 1) return fail(e, HMR_ERR_CUDA, "the device cannot launch the intra wavefront cooperatively");
-    const size_t need = (size_t)3 * e->ctusH;
+    const size_t need = (size_t)3 * e->ctusH + 1;           // per (component, row) progress + the job counter of the wavefront
     if (need > e->progressCap)
     {
       pool_free(e->device, e->progress, e->progressCap * sizeof(unsigned long long));

@@ -40,6 +40,7 @@
 //   * a CTA takes (component, row) jobs in ascending order, so pictures with more rows than co-resident CTAs still run.
 // Measured (2160p Main10 I picture, 139 410 intra TUs): 1.50 ms against 2.17 ms for the single-chain-warp version of round 1; the
 // rest is the wavefront itself: 34 rows, each ~26 us behind the one above (two CTUs + hand-over), 7 us per luma CTU.
+#include <cstdlib>
 #include "common.cuh"
 
 #define IN_CHAIN_WARPS 4                    // warps that share the TUs of a CTU (round robin; large TUs by all four together)
@@ -194,6 +195,7 @@ __device__ __forceinline__ IntraOp intra_make_op(const hmr_intra& r, const Intra
   return op;
 }
 
+#define IN_MAX_CTAS 36  // CTAs of one wavefront launch (see intra_kernel; sweep on 2160p: 36 = 102 for a single stream, +14 % with 8 streams; HMR_INTRA_CTAS overrides)
 #define IN_NJMAX 5      // (4*32 + 1 + 31) / 32 reference samples per lane at most
 #define IN_LINE 144     // int16 entries of the filtered reference line of one TU (4*32 + 1, plus the -1 / 4N+1 slots the 45-degree modes touch with weight 0)
 
@@ -215,7 +217,9 @@ template <int S> struct TapProg
   int wA[S], wB[S], wC[S], wD[S];
   int dst[S], res[S];
 };
-template <int LG> struct TapShape { static constexpr int S = LG == 2 ? 1 : (LG == 5 ? 8 : 2); };   // samples per lane: 16 (half a warp) / 64 / 4 x 64 / 4 x 256
+// samples per lane and round: 4x4 = 16 samples (half a warp), 8x8 = 64 (one warp, 2 per lane), 16x16 = 4 warps x 64, 32x32 = 4 rounds of 4 warps x 64
+// (a program of 8 samples per lane would cost 80 registers; the CTA's register footprint is what other bitstreams' kernels wait for)
+template <int LG> struct TapShape { static constexpr int S = LG == 2 ? 1 : 2; static constexpr int ROUNDS = LG == 5 ? 4 : 1; };
 
 // Program of samples first + lane + 32 j (j < S) of the TU.  rnd / sh: rounding and shift of the weighted sum (TV_GENERIC).
 // One loop per predictor class (the class is uniform over the TU): a sample costs a handful of integer operations plus the table
@@ -485,8 +489,7 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 //     S -> L   owner(k) comes straight to the large TU; all four warps wait there     (128)
 //     L -> S   the three warps that do not own k + 1 arrive, owner(k + 1) waits       (128)
 //     L -> L   all four warps wait at the beginning of TU k + 1                       (128)
-// Memory ordering comes from the barriers themselves (PTX ISA, bar: prior shared-memory accesses of the arriving threads are performed
-// relative to the waiting threads once the barrier completes; the producer / consumer pattern st.shared; bar.arrive ... bar.sync; ld.shared).
+// Memory ordering: bar.sync orders like __syncthreads; in front of every bar.arrive there is a CTA-scope fence (see below).
 template <int LG>
 __device__ __forceinline__ void chain_tu(const IntraOp op, const int k, const int count, const bool prevLarge, const bool nextLarge, const int warp, const int lane,
                                          const uint16_t* __restrict__ addrTab, const int16_t* __restrict__ resB, int16_t* __restrict__ tile,
@@ -498,9 +501,10 @@ __device__ __forceinline__ void chain_tu(const IntraOp op, const int k, const in
   const int flags = op_flags(op);
   const bool filtered = flags & OPF_FILTER;
   const int part = large ? warp : 0;
+  constexpr int ROUNDS = TapShape<LG>::ROUNDS, PER_ROUND = N * N / ROUNDS;     // samples of one round, split over the participating warps
   TapProg<TapShape<LG>::S> g;
   int variant, rnd, sh, dc = 0;
-  tap_prep<LG>(op, addrTab, resB, lineBase, part * (N * N / 4), lane, g, variant, rnd, sh);
+  tap_prep<LG>(op, addrTab, resB, lineBase, part * (PER_ROUND / 4), lane, g, variant, rnd, sh);
   int la[2][3];
   int sT = 0, sL = 0;
   if (filtered) line_addrs<LG>(op, addrTab, part, lane, la);
@@ -522,6 +526,12 @@ __device__ __forceinline__ void chain_tu(const IntraOp op, const int k, const in
   if (variant == TV_DC) dc = dc_value<LG>(tile, sT, sL, lane);       // large TUs: every warp computes the mean itself
   PROF_MARK(3);                                              // line / DC phase (+ the real token wait)
   tap_turn<LG>(g, variant, rnd, sh, dc, tile, bd, lane);
+#pragma unroll 1
+  for (int r = 1; r < ROUNDS; r++)                           // 32x32: the remaining three quarters (nothing here reads what this TU writes)
+  {
+    tap_prep<LG>(op, addrTab, resB, lineBase, r * PER_ROUND + part * (PER_ROUND / 4), lane, g, variant, rnd, sh);
+    tap_turn<LG>(g, variant, rnd, sh, dc, tile, bd, lane);
+  }
   __syncwarp();
   PROF_MARK(5);                                              // turn
 #ifdef INTRA_PROFILE
@@ -529,14 +539,21 @@ __device__ __forceinline__ void chain_tu(const IntraOp op, const int k, const in
 #endif
   if (k + 1 < count && !nextLarge)
   {
+    // The stores of this turn must be PERFORMED before the token is passed: bar.arrive signals when it issues, and under load (other
+    // CTAs' traffic in the SM's shared-memory pipeline) the next warp's loads have been seen to overtake stores still queued — found by
+    // tools/multistream_check.py; a single bitstream never showed it.  The CTA-scope fence costs ~15 cycles here (measured).
+    __threadfence_block();
     if (!large) bar_arrive(BAR_TOKEN + (k & 3), 64);
     else if (((k + 1) & 3) != warp) bar_arrive(BAR_TOKEN + (k & 3), IN_CHAIN);   // the next owner is one of us: it waits with count 128
   }
 }
 
-// One persistent CTA per (component, CTU row) job; a CTA takes jobs blockIdx.x, blockIdx.x + gridDim.x, ... in ascending order, so
-// pictures with more rows than CTAs can be co-resident (2160p with 16x16 CTUs) still run: a job only waits for the job before it.
-__global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant__ FrameParams P, const int resSamples, const int maxRec, const int maxAddr)
+// Persistent CTAs take (CTU row, component) jobs from a queue, in ascending order (row-major: Y, Cb, Cr of row 0, then row 1, ...).
+// A job only waits for the job of the same component one row up, which was handed out earlier to a CTA that is resident (cooperative
+// launch): no deadlock however few CTAs there are.  A row lags the one above by two CTUs, so only ~a third of the rows of a 2160p
+// picture are ever active at once: the launcher starts IN_MAX_CTAS CTAs, not one per job — what a CTA holds (registers, shared memory)
+// while it waits for its turn is what other bitstreams' kernels on the same GPU wait for.
+__global__ void __launch_bounds__(IN_THREADS, 3) intra_kernel(const __grid_constant__ FrameParams P, const int resSamples, const int maxRec, const int maxAddr)
 {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   constexpr int TILE_PAD = (IN_TILE + 7) & ~7;
@@ -558,12 +575,30 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
     mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1);
     fence_proxy_async();                                       // the barriers exist before the async proxy touches them
   }
+  __shared__ int s_job;
   int n = 0;                                                   // CTUs staged so far by this CTA (all jobs): buffer = n & 1, mbarrier phase = (n >> 1) & 1
 
-  for (int job = blockIdx.x; job < 3 * P.ctus_h; job += gridDim.x)
+  for (;;)
   {
-  const int comp = job / P.ctus_h, row = job % P.ctus_h;
-  if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) break;
+  __syncthreads();                                             // the previous job's readers of the per-row arrays (and of s_job) are gone
+  if (tid == 0)
+  {
+    // next job: a counter tagged with the picture's epoch (never needs clearing), behind the per-row progress counters
+    unsigned long long* ctr = P.intra_progress + 3 * P.ctus_h;
+    unsigned long long seen = *(volatile unsigned long long*)ctr, assumed;
+    do
+    {
+      assumed = seen;
+      const unsigned long long cur = (assumed >> 32) == P.epoch ? assumed : (P.epoch << 32);
+      seen = atomicCAS(ctr, assumed, cur + 1);
+      if (seen == assumed) s_job = (int)(cur & 0xffffffffu);
+    } while (seen != assumed);
+  }
+  __syncthreads();
+  const int job = s_job;
+  if (job >= 3 * P.ctus_h) break;
+  const int row = job / 3, comp = job - 3 * row;
+  if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) continue;
   unsigned long long* myProg = P.intra_progress + comp * P.ctus_h + row;
   const volatile unsigned long long* upProg = row > 0 ? P.intra_progress + comp * P.ctus_h + row - 1 : nullptr;
   const unsigned long long base = P.epoch << 32;
@@ -580,7 +615,6 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
   const int pitch = P.work.pitch[comp];
   const int oy = row * CTH, ch = min(CTH, H - oy);
 
-  __syncthreads();                                             // the previous job's readers of the per-row arrays are gone
   for (int c = tid; c < ctusW; c += IN_THREADS)
   {
     const hmr_ctu_intra_range* rg = P.irange + row * ctusW + c;
@@ -627,8 +661,10 @@ __global__ void __launch_bounds__(IN_THREADS) intra_kernel(const __grid_constant
       if (firstCtu && tid == 0 && row < 128) g_intraRows[(comp * 128 + row) * 4 + 1] = gtime();
       firstCtu = false;
 #endif
-      if (warp == 0 && prev == c - 1)                        // left neighbours = what the chain produced a moment ago
+      if (prev == c - 1)                                     // left neighbours = what the chain produced a moment ago
       {
+        // EVERY chain warp writes the column (the same values): a large first TU is predicted by all four warps without a token, and a
+        // warp must not read the column before it is there (warp 0 alone doing it was a race that showed with several bitstreams per GPU)
         for (int y = lane; y < ch; y += 32) tile[TIDX(y, -1)] = s_col[y];
         __syncwarp();
       }
@@ -889,6 +925,11 @@ cudaError_t launch_intra(const FrameParams& P, cudaStream_t s)
   int dev = 0;
   cudaGetDevice(&dev);
   const int limit = g_coopLimit[dev & 15] > 0 ? g_coopLimit[dev & 15] : 3 * P.ctus_h;
-  const int grid = min(3 * P.ctus_h, limit);                // more jobs than co-resident CTAs: a CTA takes several, in ascending order
+#ifdef IN_EXP_FULLGRID
+  const int grid = min(3 * P.ctus_h, limit);
+#else
+  static const int maxCtas = getenv("HMR_INTRA_CTAS") ? max(1, atoi(getenv("HMR_INTRA_CTAS"))) : IN_MAX_CTAS;   // (tuning knob)
+  const int grid = min(min(3 * P.ctus_h, limit), maxCtas);      // the CTAs take the jobs from a queue, in ascending order
+#endif
   return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(grid), dim3(IN_THREADS), args, intra_dyn_smem(resSamples, maxRec, maxAddr, P.ctus_w), s);
 }

@@ -82,6 +82,10 @@ class Engine:
         self._ck(self.lib.hmr_submit_frame(self.h, C.byref(d)), "hmr_submit_frame")
         self.sizes = [frame.comp_size(c) for c in range(3)]
 
+    def submit_desc(self, desc):
+        """hmr_submit_frame on a prepared descriptor (records.Frame.desc(); the caller keeps the frame alive)."""
+        self._ck(self.lib.hmr_submit_frame(self.h, C.byref(desc)), "hmr_submit_frame")
+
     def sync(self):
         self._ck(self.lib.hmr_sync(self.h), "hmr_sync")
 

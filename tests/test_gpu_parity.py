@@ -120,3 +120,51 @@ def test_device_md5_matches_hm_golden(name, eng_mod):
             assert (eng.md5_result(job) == f.gold[2]).all(), (name, int(f.h["poc"]))
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("name", ["s_ra8_240p", "s_intra10_240p_q22", "s_rext444_240p"])
+def test_concurrent_streams_on_one_gpu_stay_bit_exact(name, eng_mod):
+    """Eight engines (CUDA streams) reconstruct the same sequence CONCURRENTLY, records resident in HBM, several passes: kernels of
+    different bitstreams then share the SMs, which changes every relative timing inside the intra wavefront's CTAs (that is how a
+    hand-over race was found that a single bitstream never showed).  Every picture of every engine must still carry HM's MD5."""
+    frames = records.read_dump(os.path.join(GOLDEN, name + ".hmr.gz"))
+    engs = [eng_mod.Engine(0) for _ in range(8)]
+    try:
+        handles = [[e.upload(f) for f in frames] for e in engs]
+        for rep in range(6):
+            for e, hs in zip(engs, handles):
+                e.run_resident_list(hs)
+        for e in engs:
+            e.sync()
+        # picture by picture, all engines in step, so that every picture can be checked before its slot is reused
+        for i, fr in enumerate(frames):
+            for e, hs in zip(engs, handles):
+                e.run_resident(hs[i])
+            for k, e in enumerate(engs):
+                got = e.read_picture(int(fr.h["out_slot"]))
+                assert (records.picture_md5(got, [fr.bit_depth(c) for c in range(3)]) == fr.gold[2]).all(), (name, k, int(fr.h["poc"]))
+    finally:
+        for e in engs:
+            e.close()
+
+
+def test_concurrent_full_size_streams_stay_bit_exact(eng_mod):
+    """The same at BASELINE.json's headline size (2160p Main10 random access, 8 streams x 4 passes): the last picture of every engine
+    depends on every picture before it."""
+    path = os.path.join(ROOT, "bench_data", "c3_ra10_2160p.hmr.gz")
+    if not os.path.exists(path):
+        pytest.skip("bench stream not present")
+    frames = records.read_dump(path)
+    engs = [eng_mod.Engine(0) for _ in range(8)]
+    try:
+        handles = [[e.upload(f) for f in frames] for e in engs]
+        fr = frames[-1]
+        for rep in range(4):
+            for e, hs in zip(engs, handles):
+                e.run_resident_list(hs)
+            for k, e in enumerate(engs):
+                got = e.read_picture(int(fr.h["out_slot"]))
+                assert (records.picture_md5(got, [fr.bit_depth(c) for c in range(3)]) == fr.gold[2]).all(), (rep, k)
+    finally:
+        for e in engs:
+            e.close()
