@@ -350,22 +350,92 @@ __device__ __forceinline__ void mc_component(const FrameParams& P, const hmr_pu&
   }
 }
 
+// ---- integer-sample motion: TComInterpolationFilter::filterCopy (TComInterpolationFilter.cpp:94-148) + TComYuv::addAvg -----------
+// When every list of a tile has a zero fraction in this component (HM's copy case) and no window leaves the picture, the tile never
+// goes through shared memory and the filter pipeline: a lane owns 8 (luma) / 4 (chroma 4:2:0) consecutive samples of one row, fetches
+// the two aligned 16-byte vectors that hold them straight from the DPB, realigns them with byte permutes and stores.  Bi-prediction of
+// two copies is the rounded average: HM's (P0 + P1 + offset) >> shift on the 14-bit intermediates ((s << h) - 8192 each, offset =
+// (1 << h) + 16384, shift = h + 1) equals (s0 + s1 + 1) >> 1 exactly, and is within the sample range by construction (no clip
+// needed): one __vavgu2 per two samples.
+// Word j (two samples) of the 8 samples that start `off` samples into the 16 samples q0|q1.
+__device__ __forceinline__ void mc_realign8(const uint4 q0, const uint4 q1, const int off, uint32_t out[4])
+{
+  const uint32_t s[9] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, 0u };
+  switch (off)
+  {
+#define MC_CASE(o) case o: _Pragma("unroll") for (int j = 0; j < 4; j++) out[j] = ((o) & 1) ? __funnelshift_r(s[((o) >> 1) + j], s[((o) >> 1) + j + 1], 16) : s[((o) >> 1) + j]; break;
+    MC_CASE(0) MC_CASE(1) MC_CASE(2) MC_CASE(3) MC_CASE(4) MC_CASE(5) MC_CASE(6) default: MC_CASE(7)
+#undef MC_CASE
+  }
+}
+// explicit store instructions: blocks start at multiples of 4 (luma) / 2 (chroma) samples and may be that narrow (8x4 / 4x8 PUs), and
+// the compiler was seen to fuse neighbouring narrow C++ stores into one wide (misaligned) store
+__device__ __forceinline__ void mc_st32(int16_t* p, uint32_t a) { asm volatile("st.global.b32 [%0], %1;" :: "l"(p), "r"(a) : "memory"); }
+__device__ __forceinline__ void mc_st64(int16_t* p, uint32_t a, uint32_t b) { asm volatile("st.global.v2.b32 [%0], {%1, %2};" :: "l"(p), "r"(a), "r"(b) : "memory"); }
+__device__ __forceinline__ void mc_st128(int16_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// true: the tile was predicted here.  PLANES = 1: component `comp` of a tile that is tw x th there (16x16 luma; 16x16 chroma in 4:4:4);
+// PLANES = 2: the 8x8 Cb and Cr tiles of 4:2:0 together (lanes 0-15 / 16-31).
+template <int PLANES>
+__device__ __forceinline__ bool mc_copy_tile(const FrameParams& P, const hmr_pu& t, const int comp, const int cx, const int cy, const int lane)
+{
+  const int tw = 16 >> cx;
+  const int x0 = t.x >> cx, y0 = t.y >> cy, w = t.w >> cx, h = t.h >> cy;
+  const int Wc = P.w[comp], Hc = P.h[comp];
+  int ix[2] = {0, 0}, iy[2] = {0, 0};
+#pragma unroll
+  for (int l = 0; l < 2; l++)
+  {
+    if (!(t.lists & (1 << l))) continue;
+    if ((t.mv[l][0] & ((4 << cx) - 1)) | (t.mv[l][1] & ((4 << cy) - 1))) return false;               // fractional: the filter path
+    ix[l] = x0 + (t.mv[l][0] >> (2 + cx)); iy[l] = y0 + (t.mv[l][1] >> (2 + cy));
+    const int pitch = P.dpb[l ? (t.slots >> 4) : (t.slots & 15)].pitch[comp];
+    if (ix[l] < 0 || iy[l] < 0 || ix[l] + tw > Wc || iy[l] + h > Hc || (ix[l] & ~7) + 32 > pitch) return false;   // border: the clamped gather
+  }
+  const int plane = PLANES == 2 ? comp + (lane >> 4) : comp;
+  const int li = PLANES == 2 ? (lane & 15) : lane;
+  const int per = PLANES == 2 ? 4 : 8;                       // samples per lane
+  const int row = li >> 1, c0 = (li & 1) * per;
+  const bool live = row < h && c0 < w;
+  uint32_t v[2][4];
+#pragma unroll
+  for (int l = 0; l < 2; l++)
+  {
+    if (!(t.lists & (1 << l))) continue;
+    const PlaneSet& ref = P.dpb[l ? (t.slots >> 4) : (t.slots & 15)];
+    const int sx = ix[l] + c0, xa = sx & ~7;
+    const int16_t* g = ref.p[plane] + (size_t)(iy[l] + (live ? row : 0)) * ref.pitch[plane] + xa;
+    const uint4 q0 = *(const uint4*)g, q1 = *(const uint4*)(g + 8);
+    mc_realign8(q0, q1, sx & 7, v[l]);                        // (4:2:0 pair: the two halves of a row differ by 4 in the offset — two cases per warp)
+  }
+  if (!live) return true;
+  uint32_t r[4];
+  const bool bi = t.lists == (HMR_PU_L0 | HMR_PU_L1);
+#pragma unroll
+  for (int j = 0; j < 4; j++) r[j] = bi ? __vavgu2(v[0][j], v[1][j]) : ((t.lists & HMR_PU_L0) ? v[0][j] : v[1][j]);
+  int16_t* d = P.work.p[plane] + (size_t)(y0 + row) * P.work.pitch[plane] + x0 + c0;
+  const int n = min(per, w - c0);                             // luma: 4 or 8 (12-wide tiles: 4 in the second half); 4:2:0 chroma: 2 or 4
+  const int al = x0 + c0;
+  if (PLANES == 2)
+  {
+    if (n >= 4 && (al & 3) == 0) mc_st64(d, r[0], r[1]);
+    else { mc_st32(d, r[0]); if (n >= 4) mc_st32(d + 2, r[1]); }
+  }
+  else if (n >= 8 && (al & 7) == 0) mc_st128(d, r[0], r[1], r[2], r[3]);
+  else { mc_st64(d, r[0], r[1]); if (n >= 8) mc_st64(d + 4, r[2], r[3]); }
+  return true;
+}
+
 // LUMA = true: the luma tile; false: the two co-located chroma tiles.  Two launches instead of one kernel doing all three
 // components: each then needs half the shared memory per warp, which doubles the warps in flight per SM — and what this
 // kernel waits for is memory latency (ncu: issue slots idle on cp.async completion), not arithmetic.
+// One tile through the general path (fractional vectors, windows across the picture border, explicit weighted prediction).
 template <bool LUMA>
-__global__ void __launch_bounds__(MC_WARPS * 32, MC_MIN_BLOCKS) mc_kernel(const __grid_constant__ FrameParams P, const int warpBytes, const int chromaRows)
+__device__ __forceinline__ void mc_general(const FrameParams& P, const hmr_pu& t, const uint32_t tile, uint32_t* tmp, int16_t* win, const int chromaRows, const int lane)
 {
-  extern __shared__ __align__(16) uint8_t s_mc[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t tile = blockIdx.x * MC_WARPS + warp;
-  if (tile >= P.hdr.n_mc_tiles) return;
-  uint8_t* base = s_mc + (size_t)warp * warpBytes;
-  uint32_t* tmp = (uint32_t*)base;                                        // 12 row pairs x 16 words
-  int16_t* win = (int16_t*)(base + 12 * MC_TMPW * 4);                     // luma: 2 lists x 24 rows; chroma: 2 planes x 2 lists x chromaRows
-
-  const uint4 raw = __ldg((const uint4*)(P.mc_tiles + tile));
-  const hmr_pu t = *(const hmr_pu*)&raw;
   int16_t* sref[3][2];
   int offs[3][2];
 
@@ -411,6 +481,30 @@ __global__ void __launch_bounds__(MC_WARPS * 32, MC_MIN_BLOCKS) mc_kernel(const 
     mc_component<4, false>(P, t, 1, 0, P.csy, sref[1], sref[1], offs[1], tmp, lane, refIdx);
     mc_component<4, false>(P, t, 2, 0, P.csy, sref[2], sref[2], offs[2], tmp, lane, refIdx);
   }
+}
+
+// One warp per tile, four tiles per CTA.  (Tried: a persistent grid whose warps walk the tiles with the next record prefetched — 44 -> 47 /
+// 51 / 57 us per 2160p picture at 6 / 8 / 9 CTAs per SM; two tiles per warp with their loads in flight together — no gain, spills at 56
+// registers.  The CTA scheduler hides the record -> samples round trips better than either.)
+template <bool LUMA>
+__global__ void __launch_bounds__(MC_WARPS * 32, MC_MIN_BLOCKS) mc_kernel(const __grid_constant__ FrameParams P, const int warpBytes, const int chromaRows)
+{
+  extern __shared__ __align__(16) uint8_t s_mc[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t tile = blockIdx.x * MC_WARPS + warp;
+  if (tile >= P.hdr.n_mc_tiles) return;
+  uint8_t* base = s_mc + (size_t)warp * warpBytes;
+  uint32_t* tmp = (uint32_t*)base;                                        // 12 row pairs x 16 words
+  int16_t* win = (int16_t*)(base + 12 * MC_TMPW * 4);                     // luma: 2 lists x 24 rows; chroma: 2 planes x 2 lists x chromaRows
+  const uint4 raw = __ldg((const uint4*)(P.mc_tiles + tile));
+  const hmr_pu t = *(const hmr_pu*)&raw;
+  if (!P.wp)                                                               // (explicit weighted prediction: the general path)
+  {
+    if (LUMA) { if (mc_copy_tile<1>(P, t, 0, 0, 0, lane)) return; }
+    else if (P.csx && P.csy) { if (mc_copy_tile<2>(P, t, 1, 1, 1, lane)) return; }
+    else if (!P.csx) { if (mc_copy_tile<1>(P, t, 1, 0, P.csy, lane) && mc_copy_tile<1>(P, t, 2, 0, P.csy, lane)) return; }
+  }
+  mc_general<LUMA>(P, t, tile, tmp, win, chromaRows, lane);
 }
 
 int launch_mc(const FrameParams& P, cudaStream_t s)
