@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include "hmr_records.h"
 
+#define HMR_INTRA_JOB_WORDS 16      // 512 (row, component) jobs: 170 CTU rows
+
 struct PlaneSet
 {
   int16_t* p[3];
@@ -43,7 +45,9 @@ struct FrameParams
   int                        intra_max_rec;   // largest number of intra records of one (component, CTU) of this picture   } shared-memory
   int                        intra_max_addr;  // largest reference-address table of one (component, CTU), entries           } capacities of
   int                        intra_res_span;  // largest residual span of one (component, CTU), samples                      } intra_kernel
-  unsigned long long*        intra_progress;  // [3][ctus_h], (epoch << 32) | CTUs finished in that row
+  unsigned long long*        intra_progress;  // [3][ctus_h], (epoch << 32) | CTUs finished in that row; [3 * ctus_h] = the job counter (zeroed by the pre-pass)
+  uint32_t                   intra_job_mask[HMR_INTRA_JOB_WORDS];   // bit 3 * row + comp: that CTU row of that component has intra TUs (a "job" of intra_kernel)
+  int                        intra_jobs;      // number of set bits; -1 = every (row, component) is a job (mask not filled in: more rows than it has bits, or records not inspected)
   unsigned long long         epoch;
 };
 
@@ -58,7 +62,7 @@ void launch_sao(const FrameParams& P, cudaStream_t s);
 void launch_hash(const PlaneSet& pic, const int w[3], const int h[3], const int bd[3], int type, uint32_t* d_out, uint32_t* d_scratch, cudaStream_t s);
 int  intra_max_coresident_blocks(int device);
 size_t intra_table_bytes(int nctu);
-struct IntraSizes { int maxRec, maxAddr, resSpan; };
+struct IntraSizes { int maxRec, maxAddr, resSpan; int jobs; uint32_t jobMask[HMR_INTRA_JOB_WORDS]; };
 IntraSizes intra_sizes_host(const hmr_frame_hdr& h, const hmr_intra* rec, const hmr_ctu_intra_range* range);
 size_t launch_pack(const PlaneSet& pic, const int w[3], const int h[3], int csx, int csy, int ncomp, const int bdInternal[3], const int bdOut[3],
                    const int crop[4], uint8_t* d_dst, cudaStream_t s);

@@ -385,6 +385,7 @@ static void fill_params(hmr_engine* e, FrameParams& P, const hmr_frame_hdr& h, c
   P.intra_progress = e->progress;
   P.intra_ops = e->intraOps; P.intra_tab = e->intraTab; P.intra_prep = e->intraPrep;
   P.intra_max_rec = P.intra_max_addr = P.intra_res_span = 0;      // 0 = worst case; the callers fill in what the records say
+  P.intra_jobs = -1;
   P.epoch = e->epoch;
 }
 
@@ -591,6 +592,7 @@ int hmr_submit_frame(hmr_engine* e, const hmr_frame_desc* f)
   fill_params(e, P, h, L, st.dev, hasBs, hasCuf);
   const IntraSizes iz = intra_sizes_host(h, f->intra, f->intra_range);
   P.intra_max_rec = iz.maxRec; P.intra_max_addr = iz.maxAddr; P.intra_res_span = iz.resSpan;
+  P.intra_jobs = iz.jobs; memcpy(P.intra_job_mask, iz.jobMask, sizeof(P.intra_job_mask));
   r = run_frame(e, P, fe);
   CK(cudaEventRecord(st.done, e->stream));
   st.inflight = true;
@@ -747,6 +749,7 @@ int hmr_run_resident(hmr_engine* e, const hmr_resident_frame* f)
   FrameParams P;
   fill_params(e, P, f->hdr, f->lay, f->dev, f->hasBs, f->hasCuf);
   P.intra_max_rec = f->intra.maxRec; P.intra_max_addr = f->intra.maxAddr; P.intra_res_span = f->intra.resSpan;
+  P.intra_jobs = f->intra.jobs; memcpy(P.intra_job_mask, f->intra.jobMask, sizeof(P.intra_job_mask));
   return run_frame(e, P, grab_events(e));
 }
 

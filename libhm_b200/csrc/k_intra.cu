@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) intra_prep_kernel(const __gri
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nctu = P.ctus_w * P.ctus_h;
   const int job = blockIdx.x * PREP_WARPS + warp;
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.intra_progress[3 * P.ctus_h] = 0ull;     // the job counter of the wavefront kernel that follows in the stream
   if (job >= 3 * nctu) return;
   const int comp = job / nctu, ctu = job - comp * nctu;
   if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) return;
@@ -472,12 +473,12 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #endif
 
 // named barriers (id 0 is __syncthreads)
-#define BAR_FULL 1     // +buffer: stagers arrive, chain warps wait  -> "CTU staged"
-#define BAR_DONE 3     // +buffer: chain warp 0 arrives, stagers wait -> "CTU predicted"
-#define BAR_STAGE 5    // the stager warps among themselves
+#define BAR_FULL 1     // +buffer: the fetcher warp arrives, chain warps wait  -> "CTU staged"
+#define BAR_DONE 3     // +buffer: chain warp 0 arrives, the writer warp waits -> "CTU predicted"
 #define BAR_CHAIN 6    // the chain warps among themselves: every TU of the CTU is in the tile
 #define BAR_TOKEN 7    // + (k & 3): TU k is in the tile, the owner of TU k + 1 may take its turn
 #define BAR_COOP 11    // large filtered TU: the four chain warps have each smoothed their part of the reference line
+#define BAR_FREE 12    // +buffer: the writer has written the CTU back, the fetcher may stage the next but one into the buffer
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
@@ -583,16 +584,23 @@ __global__ void __launch_bounds__(IN_THREADS, 3) intra_kernel(const __grid_const
   __syncthreads();                                             // the previous job's readers of the per-row arrays (and of s_job) are gone
   if (tid == 0)
   {
-    // next job: a counter tagged with the picture's epoch (never needs clearing), behind the per-row progress counters
-    unsigned long long* ctr = P.intra_progress + 3 * P.ctus_h;
-    unsigned long long seen = *(volatile unsigned long long*)ctr, assumed;
-    do
+    // next job: the k-th (row, component) that has intra TUs at all (bit mask from the host, which walks the records anyway).  One
+    // atomicAdd on a counter the pre-pass zeroed — a compare-and-swap loop on an epoch-tagged counter cost ~0.3 us per job under
+    // the contention of 36 CTAs: 30 us for the 102 jobs of a 2160p picture, most of a B picture's launch.
+    const int k = (int)atomicAdd((unsigned int*)(P.intra_progress + 3 * P.ctus_h), 1u);
+    int jb = 3 * P.ctus_h;
+    if (P.intra_jobs < 0) jb = min(k, jb);
+    else if (k < P.intra_jobs)
     {
-      assumed = seen;
-      const unsigned long long cur = (assumed >> 32) == P.epoch ? assumed : (P.epoch << 32);
-      seen = atomicCAS(ctr, assumed, cur + 1);
-      if (seen == assumed) s_job = (int)(cur & 0xffffffffu);
-    } while (seen != assumed);
+      int left = k;
+      for (int w = 0; w < HMR_INTRA_JOB_WORDS; w++)
+      {
+        const int pc = __popc(P.intra_job_mask[w]);
+        if (left < pc) { jb = 32 * w + __fns(P.intra_job_mask[w], 0, left + 1); break; }
+        left -= pc;
+      }
+    }
+    s_job = jb;
   }
   __syncthreads();
   const int job = s_job;
@@ -600,7 +608,9 @@ __global__ void __launch_bounds__(IN_THREADS, 3) intra_kernel(const __grid_const
   const int row = job / 3, comp = job - 3 * row;
   if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) continue;
   unsigned long long* myProg = P.intra_progress + comp * P.ctus_h + row;
-  const volatile unsigned long long* upProg = row > 0 ? P.intra_progress + comp * P.ctus_h + row - 1 : nullptr;
+  // the row above only has to be waited for if it is a job itself (without intra TUs its samples were final before the launch)
+  const bool upIsJob = row > 0 && (P.intra_jobs < 0 || ((P.intra_job_mask[(job - 3) >> 5] >> ((job - 3) & 31)) & 1));
+  const volatile unsigned long long* upProg = upIsJob ? P.intra_progress + comp * P.ctus_h + row - 1 : nullptr;
   const unsigned long long base = P.epoch << 32;
 
   const int bd = comp ? P.hdr.bit_depth_chroma : P.hdr.bit_depth_luma;
@@ -653,7 +663,7 @@ __global__ void __launch_bounds__(IN_THREADS, 3) intra_kernel(const __grid_const
 #ifdef INTRA_PROFILE
       const long long tf0 = clock64();
 #endif
-      bar_sync(BAR_FULL + b, IN_THREADS);                    // staged: tile, decoded TUs, tables, residuals
+      bar_sync(BAR_FULL + b, IN_CHAIN + 32);                 // staged (fetcher warp): tile, decoded TUs, tables, residuals
       mbar_wait(&s_mbar[b], (n >> 1) & 1);                   // (already complete: makes the bulk-copied bytes visible to this warp)
 #ifdef INTRA_PROFILE
       asm volatile("" :: "r"(ops[0].x) : "memory");
@@ -699,7 +709,7 @@ __global__ void __launch_bounds__(IN_THREADS, 3) intra_kernel(const __grid_const
         for (int y = lane; y < ch; y += 32) s_col[y] = tile[TIDX(y, cwc - 1)];
         __syncwarp();
         __threadfence_block();
-        bar_arrive(BAR_DONE + b, 32 + IN_STAGERS);           // predicted: the stagers write it back and publish
+        bar_arrive(BAR_DONE + b, 64);                        // predicted: the writer warp writes it back and publishes
       }
       prev = c;
     }
@@ -711,129 +721,124 @@ __global__ void __launch_bounds__(IN_THREADS, 3) intra_kernel(const __grid_const
     continue;
   }
 
-  // ============================ stager warps: everything that touches global memory ============================
-  const int st = tid - IN_CHAIN;
-  int prev = -2, prevB = 0;
-  for (int c = c0; c < ctusW; n++)
+  // ============================ fetcher warp: stages CTU n + 1 while the chain predicts CTU n ============================
+  if (warp == IN_CHAIN_WARPS)
   {
-    const int b = n & 1;
-    int16_t* tile = s_tileB + b * TILE_PAD;
-    IntraOp* ops = s_ops + b * maxRec;
-    uint16_t* addrTab = s_addr + b * maxAddr;
-    int16_t* resB = s_resB + b * resSamples;
-    const int count = s_count[c];
-    const uint32_t first = s_first[c];
-    const int cn = next_intra_ctu(s_count, c + 1, ctusW, lane);
-    const int ox = c * CTW;
-    const int cw = min(CTW, W - ox);
+    int prev = -2;
+    for (int c = c0; c < ctusW; n++)
+    {
+      const int b = n & 1;
+      int16_t* tile = s_tileB + b * TILE_PAD;
+      IntraOp* ops = s_ops + b * maxRec;
+      uint16_t* addrTab = s_addr + b * maxAddr;
+      int16_t* resB = s_resB + b * resSamples;
+      const int count = s_count[c];
+      const uint32_t first = s_first[c];
+      const int cn = next_intra_ctu(s_count, c + 1, ctusW, lane);
+      const int ox = c * CTW;
+      const int cw = min(CTW, W - ox);
+      if (n >= 2) bar_sync(BAR_FREE + b, 64);                // the writer has written back the buffer's previous tenant (CTU n - 2)
 
-    // ---- stage CTU c into buffer b (free: its previous tenant was written back in the last iteration) ----
-    if ((cw & 7) == 0)
-    {
-      const int vecPerRow = cw >> 3;
-      for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
+      // ---- stage CTU c into buffer b ----
+      if ((cw & 7) == 0)
       {
-        const int y = i / vecPerRow, v = i - y * vecPerRow;
-        cp_async16(&tile[TIDX(y, 8 * v)], plane + (size_t)(oy + y) * pitch + ox + 8 * v);
-      }
-    }
-    else
-    {
-      const int vecPerRow = cw >> 2;                         // widths are multiples of 4
-      for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
-      {
-        const int y = i / vecPerRow, v = i - y * vecPerRow;
-        cp_async8(&tile[TIDX(y, 4 * v)], plane + (size_t)(oy + y) * pitch + ox + 4 * v);
-      }
-    }
-    if (st == 0)
-    {
-      // contiguous spans by TMA bulk copy: decoded TUs, reference-address tables, the CTU's residual span
-      const uint4 prep = s_prep[c];
-      const unsigned opsBytes = 16u * count;
-      const unsigned tabBytes = 16u * (((unsigned)prep.z + 7) >> 3);
-      const unsigned resBytes = 16u * (min(prep.y, (unsigned)resSamples) >> 3);
-      fence_proxy_async();                                   // earlier generic-proxy reads of this buffer are ordered before the async writes
-      mbar_expect_tx(&s_mbar[b], opsBytes + tabBytes + resBytes);
-      bulk_copy_g2s(ops, P.intra_ops + first, opsBytes, &s_mbar[b]);
-      if (tabBytes) bulk_copy_g2s(addrTab, P.intra_tab + ((size_t)comp * ctusW * P.ctus_h + (size_t)row * ctusW + c) * IN_ADDR, tabBytes, &s_mbar[b]);
-      if (resBytes) bulk_copy_g2s(resB, P.resid + prep.x, resBytes, &s_mbar[b]);
-    }
-    if (ox > 0 && prev != c - 1)                             // left CTU has no intra blocks: its samples have been final since the kernel started
-      for (int y = st; y < ch; y += IN_STAGERS) tile[TIDX(y, -1)] = __ldcg(plane + (size_t)(oy + y) * pitch + ox - 1);
-    // the row above (x = -1 .. CTW+31) needs the CTU above-right to be final
-    if (upProg)
-    {
-      if (st == 0)
-      {
-        const unsigned long long need = base + (unsigned long long)min(c + 2, ctusW);
-        while (*upProg < need) __nanosleep(20);              // back off: the SM's issue slots belong to the chain warps
-        __threadfence();
-      }
-      bar_sync(BAR_STAGE, IN_STAGERS);
-      for (int x = st - 1; x < CTW + 32; x += IN_STAGERS)
-      {
-        const int gx = ox + x;
-        if (gx >= 0 && gx < W) tile[TIDX(-1, x)] = __ldcg(plane + (size_t)(oy - 1) * pitch + gx);
-      }
-    }
-    cp_async_wait_all();
-    mbar_wait(&s_mbar[b], (n >> 1) & 1);
-    __threadfence_block();
-    bar_arrive(BAR_FULL + b, IN_THREADS);
-
-    // ---- write back + publish the CTU the chain is finishing meanwhile ----
-    if (prev >= 0)
-    {
-      bar_sync(BAR_DONE + prevB, 32 + IN_STAGERS);
-      const int16_t* ptile = s_tileB + prevB * TILE_PAD;
-      const int pox = prev * CTW, pcw = min(CTW, W - pox);
-      if ((pcw & 7) == 0)
-      {
-        const int vecPerRow = pcw >> 3;
-        for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
+        const int vecPerRow = cw >> 3;
+        for (int i = lane; i < ch * vecPerRow; i += 32)
         {
           const int y = i / vecPerRow, v = i - y * vecPerRow;
-          *((uint4*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint4*)&ptile[TIDX(y, 8 * v)];
+          cp_async16(&tile[TIDX(y, 8 * v)], plane + (size_t)(oy + y) * pitch + ox + 8 * v);
         }
       }
       else
       {
-        const int vecPerRow = pcw >> 2;
-        for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
+        const int vecPerRow = cw >> 2;                       // widths are multiples of 4
+        for (int i = lane; i < ch * vecPerRow; i += 32)
         {
           const int y = i / vecPerRow, v = i - y * vecPerRow;
-          *((uint2*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint2*)&ptile[TIDX(y, 4 * v)];
+          cp_async8(&tile[TIDX(y, 4 * v)], plane + (size_t)(oy + y) * pitch + ox + 4 * v);
         }
       }
-      bar_sync(BAR_STAGE, IN_STAGERS);
-      if (st == 0)
+      if (lane == 0)
       {
-        __threadfence();
-        *(volatile unsigned long long*)myProg = base + (unsigned long long)c;    // every CTU before c (the next intra CTU) is final
+        // contiguous spans by TMA bulk copy: decoded TUs, reference-address tables, the CTU's residual span
+        const uint4 prep = s_prep[c];
+        const unsigned opsBytes = 16u * count;
+        const unsigned tabBytes = 16u * (((unsigned)prep.z + 7) >> 3);
+        const unsigned resBytes = 16u * (min(prep.y, (unsigned)resSamples) >> 3);
+        fence_proxy_async();                                 // earlier generic-proxy reads of this buffer are ordered before the async writes
+        mbar_expect_tx(&s_mbar[b], opsBytes + tabBytes + resBytes);
+        bulk_copy_g2s(ops, P.intra_ops + first, opsBytes, &s_mbar[b]);
+        if (tabBytes) bulk_copy_g2s(addrTab, P.intra_tab + ((size_t)comp * ctusW * P.ctus_h + (size_t)row * ctusW + c) * IN_ADDR, tabBytes, &s_mbar[b]);
+        if (resBytes) bulk_copy_g2s(resB, P.resid + prep.x, resBytes, &s_mbar[b]);
+      }
+      if (ox > 0 && prev != c - 1)                           // left CTU has no intra blocks: its samples have been final since the kernel started
+        for (int y = lane; y < ch; y += 32) tile[TIDX(y, -1)] = __ldcg(plane + (size_t)(oy + y) * pitch + ox - 1);
+      // the row above (x = -1 .. CTW+31) needs the CTU above-right to be final
+      if (row > 0)
+      {
+        if (upProg)
+        {
+          if (lane == 0)
+          {
+            const unsigned long long need = base + (unsigned long long)min(c + 2, ctusW);
+            while (*upProg < need) __nanosleep(20);          // back off: the SM's issue slots belong to the chain warps
+            __threadfence();
+          }
+          __syncwarp();
+        }
+        for (int x = lane - 1; x < CTW + 32; x += 32)
+        {
+          const int gx = ox + x;
+          if (gx >= 0 && gx < W) tile[TIDX(-1, x)] = __ldcg(plane + (size_t)(oy - 1) * pitch + gx);
+        }
+      }
+      cp_async_wait_all();
+      mbar_wait(&s_mbar[b], (n >> 1) & 1);
+      __threadfence_block();
+      bar_arrive(BAR_FULL + b, IN_CHAIN + 32);
+      prev = c;
+      c = cn;
+    }
+    continue;
+  }
+
+  // ============================ writer warp: writes CTU n back and publishes the row's progress as soon as the chain is done with it ====
+  // (its own warp: the write-back of CTU n must not wait behind the staging of CTU n + 1, which waits for the row above — that coupling
+  // made every row trail the one above by almost four CTU-times instead of two)
+  for (int c = c0; c < ctusW; n++)
+  {
+    const int b = n & 1;
+    const int cn = next_intra_ctu(s_count, c + 1, ctusW, lane);
+    bar_sync(BAR_DONE + b, 64);                              // the chain has predicted CTU c
+    const int16_t* ptile = s_tileB + b * TILE_PAD;
+    const int pox = c * CTW, pcw = min(CTW, W - pox);
+    if ((pcw & 7) == 0)
+    {
+      const int vecPerRow = pcw >> 3;
+      for (int i = lane; i < ch * vecPerRow; i += 32)
+      {
+        const int y = i / vecPerRow, v = i - y * vecPerRow;
+        *((uint4*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint4*)&ptile[TIDX(y, 8 * v)];
       }
     }
-    prev = c; prevB = b;
-    c = cn;
-  }
-  // ---- the last CTU of the row ----
-  {
-    bar_sync(BAR_DONE + prevB, 32 + IN_STAGERS);
-    const int16_t* ptile = s_tileB + prevB * TILE_PAD;
-    const int pox = prev * CTW, pcw = min(CTW, W - pox);
-    const int unit = (pcw & 7) == 0 ? 8 : 4, vecPerRow = pcw / unit;
-    for (int i = st; i < ch * vecPerRow; i += IN_STAGERS)
+    else
     {
-      const int y = i / vecPerRow, v = i - y * vecPerRow;
-      if (unit == 8) *((uint4*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint4*)&ptile[TIDX(y, 8 * v)];
-      else           *((uint2*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint2*)&ptile[TIDX(y, 4 * v)];
+      const int vecPerRow = pcw >> 2;
+      for (int i = lane; i < ch * vecPerRow; i += 32)
+      {
+        const int y = i / vecPerRow, v = i - y * vecPerRow;
+        *((uint2*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint2*)&ptile[TIDX(y, 4 * v)];
+      }
     }
-    bar_sync(BAR_STAGE, IN_STAGERS);
-    if (st == 0)
+    __syncwarp();
+    if (lane == 0)
     {
       __threadfence();
-      *(volatile unsigned long long*)myProg = base + (unsigned long long)ctusW;
+      *(volatile unsigned long long*)myProg = base + (unsigned long long)cn;    // every CTU before cn (the next intra CTU, or the end of the row) is final
     }
+    __threadfence_block();
+    bar_arrive(BAR_FREE + b, 64);                            // the fetcher may reuse the buffer (CTU n + 2)
+    c = cn;
   }
   }   // jobs
 }
@@ -854,19 +859,27 @@ static size_t intra_dyn_smem(int resSamples, int maxRec, int maxAddr, int ctusW)
 // Largest CTU of a picture, measured on the host records (the same quantities intra_prep_kernel derives per CTU on the device).
 IntraSizes intra_sizes_host(const hmr_frame_hdr& h, const hmr_intra* rec, const hmr_ctu_intra_range* range)
 {
-  IntraSizes z = { 1, 8, 8 };
-  if (!rec || !range) return z;
+  IntraSizes z;
+  memset(&z, 0, sizeof(z));
+  z.maxRec = 1; z.maxAddr = 8; z.resSpan = 8;
+  IntraSizes worst;
+  memset(&worst, 0, sizeof(worst));
+  worst.jobs = -1;
+  if (!rec || !range) { z.jobs = -1; return z; }
+  const uint32_t ctusW = (h.width + (1u << h.log2_ctu) - 1) >> h.log2_ctu;
+  const bool maskFits = ctusW > 0 && 3 * ((h.n_ctu + ctusW - 1) / ctusW) <= 32 * HMR_INTRA_JOB_WORDS;
   for (uint32_t ctu = 0; ctu < h.n_ctu; ctu++)
     for (int c = 0; c < 3; c++)
     {
       const uint32_t first = range[ctu].first[c], count = range[ctu].count[c];
       if (!count) continue;
-      if (first > h.n_intra || count > h.n_intra - first) { const IntraSizes worst = { 0, 0, 0 }; return worst; }   // inconsistent ranges: worst-case capacities
+      if (maskFits) { const uint32_t jb = 3 * (ctu / ctusW) + c; z.jobMask[jb >> 5] |= 1u << (jb & 31); }
+      if (first > h.n_intra || count > h.n_intra - first) return worst;   // inconsistent ranges: worst-case capacities
       unsigned tab = 0, mn = 0xffffffffu, mx = 0;
       for (uint32_t k = 0; k < count; k++)
       {
         const hmr_intra& r = rec[first + k];
-        if (r.log2_size < 2 || r.log2_size > 5) { const IntraSizes worst = { 0, 0, 0 }; return worst; }
+        if (r.log2_size < 2 || r.log2_size > 5) return worst;
         tab += (4u << r.log2_size) + 1;
         if (r.resid_off != HMR_NO_OFFSET) { mn = r.resid_off < mn ? r.resid_off : mn; const unsigned e = r.resid_off + (1u << (2 * r.log2_size)); mx = e > mx ? e : mx; }
       }
@@ -874,6 +887,8 @@ IntraSizes intra_sizes_host(const hmr_frame_hdr& h, const hmr_intra* rec, const 
       if ((int)tab > z.maxAddr) z.maxAddr = (int)tab;
       if (mx > mn && (int)(mx - mn) > z.resSpan) z.resSpan = (int)(mx - mn);
     }
+  if (maskFits) for (int w = 0; w < HMR_INTRA_JOB_WORDS; w++) z.jobs += __builtin_popcount(z.jobMask[w]);
+  else z.jobs = -1;
   return z;
 }
 
@@ -921,15 +936,13 @@ cudaError_t launch_intra(const FrameParams& P, cudaStream_t s)
   int maxRec = P.intra_max_rec > 0 ? min(IN_MAXREC, P.intra_max_rec) : IN_MAXREC;
   int maxAddr = P.intra_max_addr > 0 ? min(IN_ADDR, (P.intra_max_addr + 7) & ~7) : IN_ADDR;
   intra_prep_kernel<<<(3 * P.ctus_w * P.ctus_h + PREP_WARPS - 1) / PREP_WARPS, PREP_WARPS * 32, 0, s>>>(P);
-  void* args[] = { (void*)&P, (void*)&resSamples, (void*)&maxRec, (void*)&maxAddr };
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const int limit = g_coopLimit[dev & 15] > 0 ? g_coopLimit[dev & 15] : 3 * P.ctus_h;
-#ifdef IN_EXP_FULLGRID
-  const int grid = min(3 * P.ctus_h, limit);
-#else
   static const int maxCtas = getenv("HMR_INTRA_CTAS") ? max(1, atoi(getenv("HMR_INTRA_CTAS"))) : IN_MAX_CTAS;   // (tuning knob)
-  const int grid = min(min(3 * P.ctus_h, limit), maxCtas);      // the CTAs take the jobs from a queue, in ascending order
-#endif
-  return cudaLaunchCooperativeKernel((const void*)intra_kernel, dim3(grid), dim3(IN_THREADS), args, intra_dyn_smem(resSamples, maxRec, maxAddr, P.ctus_w), s);
+  const int jobs = P.intra_jobs >= 0 ? P.intra_jobs : 3 * P.ctus_h;
+  if (jobs == 0) return cudaSuccess;
+  // An ordinary launch: a job only waits for a job that was handed out before it, i.e. to a CTA that is running — no CTA ever
+  // waits for one that has not started, so the grid need not be co-resident (a cooperative launch would also have to wait until
+  // the whole grid fits next to the other bitstreams' kernels).
+  const int grid = min(jobs, maxCtas);
+  intra_kernel<<<grid, IN_THREADS, intra_dyn_smem(resSamples, maxRec, maxAddr, P.ctus_w), s>>>(P, resSamples, maxRec, maxAddr);
+  return cudaGetLastError();
 }
