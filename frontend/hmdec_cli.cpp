@@ -58,6 +58,8 @@ int main(int argc, char** argv)
   FILE* fo = out ? fopen(out, "wb") : NULL;
   int pictures = 0; bool mismatch = false; const char* unsupported = NULL;
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  const bool picTimes = getenv("HMDEC_CLI_PICTURE_TIMES") != NULL;     // host time between picture boundaries (profiling aid)
+  double tLast = 0;
   for (int rep = 0; rep < repeat; rep++)
   {
     libHMDec_context* dec = dump ? libHMDecB200_new_decoder_ex(1, dump) : libHMDec_new_decoder();
@@ -90,6 +92,7 @@ int main(int argc, char** argv)
           else if (touch) for (int c = 0; c < 3; c++) (void)libHMDEC_get_image_plane(pic, (libHMDec_ColorComponent)c);
         }
       }
+      if (newPicture && picTimes) { const double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); fprintf(stderr, "picture boundary at NAL %zu: +%.2f ms\n", k, 1e3 * (t - tLast)); tLast = t; }
       if (!newPicture) k++;      // otherwise the same NAL must be pushed again
     }
     mismatch = mismatch || libHMDecB200_hash_mismatch(dec);
