@@ -110,7 +110,7 @@ HmFrameSink* hm_new_dump_sink(const char* path) { return new DumpSink(path); }
 class NullSink : public HmFrameSink
 {
 public:
-  virtual bool frameReady(const hmr_frame_desc&, TComPic*) { return true; }
+  virtual bool frameReady(const hmr_frame_desc&, TComPic* pic) { pic->getPicYuvRec()->setBorderExtension(true); return true; }   // like the GPU sink: no border padding
   virtual void fetchPicture(TComPic*) {}
   virtual bool wantHmRecon() const { return false; }
 };

@@ -640,6 +640,13 @@ static unsigned bsOfUnit(TComDataCU* cuP, unsigned partP, TComDataCU* cuQ, unsig
   TComSlice* sliceP = cuP->getSlice();
   TComCUMvField* fP0 = cuP->getCUMvField(REF_PIC_LIST_0);
   TComCUMvField* fQ0 = cuQ->getCUMvField(REF_PIC_LIST_0);
+  // identical motion data under the same reference lists: every branch of the rule below ends in 0 (the common case by far)
+  if (sliceP == sliceQ && fP0->getRefIdx(partP) == fQ0->getRefIdx(partQ) && fP0->getMv(partP) == fQ0->getMv(partQ))
+  {
+    TComCUMvField* gP1 = cuP->getCUMvField(REF_PIC_LIST_1);
+    TComCUMvField* gQ1 = cuQ->getCUMvField(REF_PIC_LIST_1);
+    if (gP1->getRefIdx(partP) == gQ1->getRefIdx(partQ) && gP1->getMv(partP) == gQ1->getMv(partQ)) return 0;
+  }
   int r = fP0->getRefIdx(partP);
   const TComPic* refP0 = r < 0 ? NULL : sliceP->getRefPic(REF_PIC_LIST_0, r);
   r = fQ0->getRefIdx(partQ);
@@ -754,27 +761,137 @@ void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, T
     }
 }
 
+// The same side info without HM's flag arrays: the edges of a leaf CU are enumerated from its geometry.  Per 4x4 unit on the
+// 8x8 grid (TComLoopFilter.cpp:199-206) an edge exists and counts as a transform edge exactly where xSetLoopfilterParam +
+// xSetEdgefilterTU + xSetEdgefilterPU (TComLoopFilter.cpp:270-409) leave their marks:
+//   CU border (unit column / row 0)   filter = TU marker = "the neighbour exists for deblocking" (slice / tile crossing rules of
+//                                     getPULeft / getPUAbove; a neighbour inside the same CTU always exists)
+//   inside the CU                     TU marker = the unit starts a transform block (size = CU size >> stored transform index);
+//                                     filter = TU marker, or the unit lies on the CU's prediction-partition boundary
+// each under "deblocking not disabled in this slice".  The flag-array version (bsWalk) stays as the A/B reference:
+// HMDEC_B200_BS_FLAGS=1 selects it, tests/test_frontend_fast_path.py requires byte-identical BS maps from both.
+void HmEmitter::bsDirect(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, bool lfCrossTiles)
+{
+  if (ctu->getPic() == 0 || ctu->getPartitionSize(absZorderIdx) == NUMBER_OF_PART_SIZES) return;
+  TComPic* pic = ctu->getPic();
+  const unsigned curNumParts = pic->getNumPartInCU() >> (depth << 1);
+  const unsigned qNumParts = curNumParts >> 2;
+  TComSlice* slice = ctu->getSlice();
+  const unsigned picW = slice->getSPS()->getPicWidthInLumaSamples();
+  const unsigned picH = slice->getSPS()->getPicHeightInLumaSamples();
+  if (ctu->getDepth(absZorderIdx) > depth)
+  {
+    for (unsigned p = 0; p < 4; p++, absZorderIdx += qNumParts)
+    {
+      unsigned lx = ctu->getCUPelX() + g_auiRasterToPelX[g_auiZscanToRaster[absZorderIdx]];
+      unsigned ty = ctu->getCUPelY() + g_auiRasterToPelY[g_auiZscanToRaster[absZorderIdx]];
+      if (lx < picW && ty < picH) bsDirect(ctu, absZorderIdx, depth + 1, lfCrossTiles);
+    }
+    return;
+  }
+  const unsigned raster0 = g_auiZscanToRaster[absZorderIdx];
+  const unsigned stride = pic->getNumPartInWidth();
+  const int ux0 = g_auiRasterToPelX[raster0] >> 2, uy0 = g_auiRasterToPelY[raster0] >> 2;
+  const int cuX = ctu->getCUPelX() + 4 * ux0, cuY = ctu->getCUPelY() + 4 * uy0;
+  const int cuSize = g_uiMaxCUWidth >> depth;
+  const int n = cuSize >> 2;
+  const bool internal = !slice->getDeblockingFilterDisable();
+  if (internal)
+  {
+    UInt tmp;
+    const bool sliceRestr = !slice->getLFCrossSliceBoundaryFlag();
+    const bool border[2] = {
+      cuX > 0 && (ux0 > 0 || ctu->getPULeft(tmp, absZorderIdx, sliceRestr, !lfCrossTiles) != NULL),
+      cuY > 0 && (uy0 > 0 || ctu->getPUAbove(tmp, absZorderIdx, sliceRestr, false, !lfCrossTiles) != NULL) };
+    int puEdge[2] = { -1, -1 };                              // unit column (EDGE_VER) / row (EDGE_HOR) of the partition boundary inside the CU
+    switch (ctu->getPartitionSize(absZorderIdx))
+    {
+      case SIZE_2NxN:  puEdge[EDGE_HOR] = n >> 1; break;
+      case SIZE_Nx2N:  puEdge[EDGE_VER] = n >> 1; break;
+      case SIZE_NxN:   puEdge[EDGE_VER] = puEdge[EDGE_HOR] = n >> 1; break;
+      case SIZE_2NxnU: puEdge[EDGE_HOR] = n >> 2; break;
+      case SIZE_2NxnD: puEdge[EDGE_HOR] = n - (n >> 2); break;
+      case SIZE_nLx2N: puEdge[EDGE_VER] = n >> 2; break;
+      case SIZE_nRx2N: puEdge[EDGE_VER] = n - (n >> 2); break;
+      default: break;
+    }
+    const bool oneTU = ctu->getTransformIdx(absZorderIdx) == 0;          // the CU is a single transform block: no transform edge inside
+    const unsigned numPartInCtu = pic->getNumPartInCU();
+    for (int dir = 0; dir < 2; dir++)
+      for (int e = 0; e < n; e += 2)                          // CU origins are multiples of 8 samples: e even = on the 8x8 grid
+      {
+        if (e == 0 ? !border[dir] : (oneTU && e != puEdge[dir])) continue;
+        for (int k = 0; k < n; k++)
+        {
+          const int x = dir == EDGE_VER ? e : k, y = dir == EDGE_VER ? k : e;
+          const unsigned raster = raster0 + y * stride + x;
+          const unsigned part = g_auiRasterToZscan[raster];
+          bool tuEdge = true;
+          if (e > 0)
+          {
+            tuEdge = !oneTU && ((4 * e) & ((cuSize >> ctu->getTransformIdx(part)) - 1)) == 0;
+            if (!tuEdge && e != puEdge[dir]) continue;
+          }
+          TComDataCU* cuP = ctu;
+          unsigned partP;
+          if (dir == EDGE_VER)
+          {
+            if (ux0 + x > 0) partP = g_auiRasterToZscan[raster - 1];
+            else { cuP = ctu->getCULeft(); partP = g_auiRasterToZscan[raster + stride - 1]; }
+          }
+          else
+          {
+            if (uy0 + y > 0) partP = g_auiRasterToZscan[raster - stride];
+            else { cuP = ctu->getCUAbove(); partP = g_auiRasterToZscan[raster + numPartInCtu - stride]; }
+          }
+          const unsigned bs = bsOfUnit(cuP, partP, ctu, part, tuEdge);
+          if (bs)
+          {
+            const int gx = (cuX >> 2) + x, gy = (cuY >> 2) + y;
+            m_bs[(size_t)gy * m_bsStride + gx] |= (uint8_t)(bs << (dir == EDGE_VER ? 0 : 2));
+          }
+        }
+      }
+  }
+  // QP / no-filter maps per 8x8 (TComLoopFilter.cpp:587-600,607-617)
+  const int qp = ctu->getQP(absZorderIdx);
+  const bool pcmFilterOff = slice->getSPS()->getUsePCM() && slice->getSPS()->getPCMFilterDisableFlag();
+  const bool nofilter = (pcmFilterOff && ctu->getIPCMFlag(absZorderIdx)) || ctu->isLosslessCoded(absZorderIdx);
+  if (nofilter) m_hdr.flags |= HMR_FRM_HAS_NOFILTER;
+  for (int y = cuY >> 3; y < ((cuY + cuSize) >> 3) && y < ((m_hdr.height + 7) >> 3); y++)
+    for (int x = cuX >> 3; x < ((cuX + cuSize) >> 3) && x < m_qpStride; x++)
+    {
+      m_qp[(size_t)y * m_qpStride + x] = (int8_t)qp;
+      m_cuFlags[(size_t)y * m_qpStride + x] = nofilter ? HMR_CU_NOFILTER : 0;
+    }
+}
+
 // Deblocking side info of one CTU, right after it was parsed (HM derives it for the whole picture at the end, TComLoopFilter.cpp:
 // 130-155, when every CTU's arrays have long left the caches): edge flags with HM's own xSetLoopfilterParam / xSetEdgefilterTU /
 // xSetEdgefilterPU on an emitter-owned TComLoopFilter, strengths with bsOfUnit.  Only the left and the above CTU are consulted and
 // both precede this one in decoding order (also across tiles: the tile to the left / above is decoded first).
 void HmEmitter::deblockCtu(TComDataCU* ctu)
 {
-  if (!m_lf || m_lfDepth != g_uiMaxCUDepth)
-  {
-    if (m_lf) { m_lf->destroy(); delete m_lf; }
-    m_lf = new TComLoopFilter;
-    m_lf->create(g_uiMaxCUDepth);
-    m_lfDepth = g_uiMaxCUDepth;
-  }
-  TComLoopFilter* lf = m_lf;
   TComSlice* s = ctu->getSlice();
-  lf->setCfg(s->getPPS()->getLoopFilterAcrossTilesEnabledFlag());
-  ::memset(lf->m_aapucBS[EDGE_VER], 0, sizeof(UChar) * lf->m_uiNumPartitions);
-  ::memset(lf->m_aapbEdgeFilter[EDGE_VER], 0, sizeof(Bool) * lf->m_uiNumPartitions);
-  ::memset(lf->m_aapucBS[EDGE_HOR], 0, sizeof(UChar) * lf->m_uiNumPartitions);
-  ::memset(lf->m_aapbEdgeFilter[EDGE_HOR], 0, sizeof(Bool) * lf->m_uiNumPartitions);
-  bsWalk(ctu, 0, 0, lf);
+  static const bool flagArrays = getenv("HMDEC_B200_BS_FLAGS") != NULL || getenv("HMDEC_B200_HM_BS") != NULL;   // A/B: HM's edge-flag machinery
+  if (!flagArrays) bsDirect(ctu, 0, 0, s->getPPS()->getLoopFilterAcrossTilesEnabledFlag());
+  else
+  {
+    if (!m_lf || m_lfDepth != g_uiMaxCUDepth)
+    {
+      if (m_lf) { m_lf->destroy(); delete m_lf; }
+      m_lf = new TComLoopFilter;
+      m_lf->create(g_uiMaxCUDepth);
+      m_lfDepth = g_uiMaxCUDepth;
+    }
+    TComLoopFilter* lf = m_lf;
+    lf->setCfg(s->getPPS()->getLoopFilterAcrossTilesEnabledFlag());
+    ::memset(lf->m_aapucBS[EDGE_VER], 0, sizeof(UChar) * lf->m_uiNumPartitions);
+    ::memset(lf->m_aapbEdgeFilter[EDGE_VER], 0, sizeof(Bool) * lf->m_uiNumPartitions);
+    ::memset(lf->m_aapucBS[EDGE_HOR], 0, sizeof(UChar) * lf->m_uiNumPartitions);
+    ::memset(lf->m_aapbEdgeFilter[EDGE_HOR], 0, sizeof(Bool) * lf->m_uiNumPartitions);
+    bsWalk(ctu, 0, 0, lf);
+  }
   const UInt a = ctu->getAddr();
   m_ctu[a].beta_offset_div2 = (int8_t)s->getDeblockingFilterBetaOffsetDiv2();
   m_ctu[a].tc_offset_div2   = (int8_t)s->getDeblockingFilterTcOffsetDiv2();

@@ -84,6 +84,7 @@ private:
   uint32_t emitResidualTU(CuCtx& c, int compID, void* rTu, bool intra, bool coded, int alpha);
   void deblockCtu(TComDataCU* ctu);
   void bsWalk(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, TComLoopFilter* lf);
+  void bsDirect(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, bool lfCrossTiles);   // edges enumerated from the CU / PU / TU geometry, no flag arrays
   void saoInfo(TComPic* pic, TComSampleAdaptiveOffset* sao);
   void fail(const char* what);
 
