@@ -423,3 +423,86 @@ void hm_fast_prefetch_begin(HmPrefetchCursor& pf, TComPic* pic, unsigned ctuAddr
     pfAdd(pf, f.m_pcMv, n * sizeof(TComMv)); pfAdd(pf, f.m_pcMvd, n * sizeof(TComMv)); pfAdd(pf, f.m_piRefIdx, n);
   }
 }
+
+// ---- per-CTU initialisation -----------------------------------------------------------------------------------------
+// TComDataCU::initCU (TComDataCU.cpp:329-520, its definition is renamed initCU_hm at build time) runs before every CTU is
+// parsed.  Two of its loops evaluate "does partition i lie behind the slice start" with half a dozen dependent loads per
+// partition (the stores into the UInt arrays keep the compiler from hoisting them: ~5000 loads per CTU), and a CTU that starts
+// inside the current slice segment — every CTU except the first of a segment that begins in mid-CTU, which no HEVC stream has —
+// is initialised purely by fills.  That case is restated here with the bounds computed once; anything else takes HM's routine.
+Void TComDataCU::initCU(TComPic* pcPic, UInt ctuAddr)
+{
+  TComSlice* slice = pcPic->getSlice(pcPic->getCurrSliceIdx());
+  const UInt n = pcPic->getNumPartInCU();
+  const UInt firstPart = pcPic->getPicSym()->getInverseCUOrderMap(ctuAddr) * n;        // this CTU's first partition in coding order
+  if (slice->getSliceSegmentCurStartCUAddr() > firstPart || slice->getSliceCurStartCUAddr() > firstPart)
+  {
+    initCU_hm(pcPic, ctuAddr);
+    return;
+  }
+  m_pcPic = pcPic;
+  m_pcSlice = slice;
+  m_uiCUAddr = ctuAddr;
+  m_uiCUPelX = (ctuAddr % pcPic->getFrameWidthInCU()) * g_uiMaxCUWidth;
+  m_uiCUPelY = (ctuAddr / pcPic->getFrameWidthInCU()) * g_uiMaxCUHeight;
+  m_uiAbsIdxInLCU = 0;
+  m_dTotalCost = MAX_DOUBLE;
+  m_uiTotalDistortion = 0;
+  m_uiTotalBits = 0;
+  m_uiTotalBins = 0;
+  m_uiNumPartition = n;
+  std::fill_n(m_sliceStartCU, n, slice->getSliceCurStartCUAddr());
+  std::fill_n(m_sliceSegmentStartCU, n, slice->getSliceSegmentCurStartCUAddr());
+
+  struct Fill { void* p; int v; size_t elem; };
+  const Fill fills[] = {
+    { m_skipFlag, 0, sizeof(*m_skipFlag) },                         { m_pePartSize, NUMBER_OF_PART_SIZES, sizeof(*m_pePartSize) },
+    { m_pePredMode, NUMBER_OF_PREDICTION_MODES, sizeof(*m_pePredMode) }, { m_CUTransquantBypass, 0, sizeof(*m_CUTransquantBypass) },
+    { m_puhDepth, 0, sizeof(*m_puhDepth) },                         { m_puhTrIdx, 0, sizeof(*m_puhTrIdx) },
+    { m_puhWidth, (int)g_uiMaxCUWidth, sizeof(*m_puhWidth) },       { m_puhHeight, (int)g_uiMaxCUHeight, sizeof(*m_puhHeight) },
+    { m_apiMVPIdx[0], -1, sizeof(*m_apiMVPIdx[0]) },                { m_apiMVPNum[0], -1, sizeof(*m_apiMVPNum[0]) },
+    { m_apiMVPIdx[1], -1, sizeof(*m_apiMVPIdx[1]) },                { m_apiMVPNum[1], -1, sizeof(*m_apiMVPNum[1]) },
+    { m_phQP, slice->getSliceQp(), sizeof(*m_phQP) },               { m_ChromaQpAdj, 0, sizeof(*m_ChromaQpAdj) },
+    { m_pbMergeFlag, 0, sizeof(*m_pbMergeFlag) },                   { m_puhMergeIndex, 0, sizeof(*m_puhMergeIndex) },
+    { m_puhIntraDir[0], DC_IDX, sizeof(*m_puhIntraDir[0]) },        { m_puhIntraDir[1], 0, sizeof(*m_puhIntraDir[1]) },
+    { m_puhInterDir, 0, sizeof(*m_puhInterDir) },                   { m_pbIPCMFlag, 0, sizeof(*m_pbIPCMFlag) } };
+  for (size_t i = 0; i < sizeof(fills) / sizeof(fills[0]); i++) ::memset(fills[i].p, fills[i].v, n * fills[i].elem);
+  for (UInt c = 0; c < MAX_NUM_COMPONENT; c++)
+  {
+    ::memset(m_crossComponentPredictionAlpha[c], 0, n * sizeof(*m_crossComponentPredictionAlpha[c]));
+    ::memset(m_puhTransformSkip[c], 0, n * sizeof(*m_puhTransformSkip[c]));
+    ::memset(m_puhCbf[c], 0, n * sizeof(*m_puhCbf[c]));
+    ::memset(m_explicitRdpcmMode[c], NUMBER_OF_RDPCM_MODES, n * sizeof(*m_explicitRdpcmMode[c]));
+  }
+  // coefficient storage: HM zeroes all of it here (TComDataCU.cpp:453); same rule as hm_fast_memset
+  {
+    const UInt numCoeffY = g_uiMaxCUWidth * g_uiMaxCUHeight;
+    for (UInt c = 0; c < MAX_NUM_COMPONENT; c++)
+    {
+      const UInt shift = m_pcPic->getComponentScaleX(ComponentID(c)) + m_pcPic->getComponentScaleY(ComponentID(c));
+      hm_fast_memset(m_pcTrCoeff[c], 0, sizeof(TCoeff) * numCoeffY >> shift);
+#if ADAPTIVE_QP_SELECTION
+      hm_fast_memset(m_pcArlCoeff[c], 0, sizeof(TCoeff) * numCoeffY >> shift);
+#endif
+    }
+  }
+  for (UInt l = 0; l < NUM_REF_PIC_LIST_01; l++)
+  {
+    TComCUMvField& f = m_acCUMvField[l];                      // clearMvField (TComMotionInfo.cpp:88-97): zero vectors, refIdx NOT_VALID
+    ::memset(f.m_pcMv, 0, sizeof(TComMv) * f.m_uiNumPartition);
+    ::memset(f.m_pcMvd, 0, sizeof(TComMv) * f.m_uiNumPartition);
+    ::memset(f.m_piRefIdx, NOT_VALID, sizeof(*f.m_piRefIdx) * f.m_uiNumPartition);
+  }
+  // neighbours (TComDataCU.cpp:497-540)
+  const UInt widthInCtus = pcPic->getFrameWidthInCU();
+  const UInt col = ctuAddr % widthInCtus;
+  m_pcCULeft = col ? pcPic->getCU(ctuAddr - 1) : NULL;
+  m_pcCUAbove = ctuAddr >= widthInCtus ? pcPic->getCU(ctuAddr - widthInCtus) : NULL;
+  m_pcCUAboveLeft = (m_pcCULeft && m_pcCUAbove) ? pcPic->getCU(ctuAddr - widthInCtus - 1) : NULL;
+  m_pcCUAboveRight = (m_pcCUAbove && col < widthInCtus - 1) ? pcPic->getCU(ctuAddr - widthInCtus + 1) : NULL;
+  for (UInt l = 0; l < NUM_REF_PIC_LIST_01; l++)
+  {
+    const RefPicList rpl = RefPicList(l);
+    m_apcCUColocated[rpl] = slice->getNumRefIdx(rpl) > 0 ? slice->getRefPic(rpl, 0)->getCU(ctuAddr) : NULL;
+  }
+}
