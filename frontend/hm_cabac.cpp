@@ -115,8 +115,8 @@ struct Engine
 // ---- tables derived from HM's own functions, per (channel type, log2 size, scan) ----
 struct ScanTables
 {
-  const UInt* scan;               // HM's grouped 4x4 scan: scan position -> raster position
-  const UInt* scanCG;             // scan order of the coefficient groups
+  std::vector<UInt> scan;         // HM's grouped 4x4 scan: scan position -> raster position (a COPY: HM's ROM arrays are freed
+  std::vector<UInt> scanCG;       // scan order of the coefficient groups                  when the last decoder of the process goes)
   std::vector<uint16_t> inverse;  // raster position -> scan position
   std::vector<uint8_t>  sigCtx;   // [pattern 0..3][scan position] -> context increment (TComTrQuant::getSigCtxInc)
 };
@@ -147,7 +147,7 @@ static void buildTables()
         if (lg == 2) cp.firstSignificanceMapContext = significanceMapContextSetStart[ch][CONTEXT_TYPE_4x4];
         else if (lg == 3) cp.firstSignificanceMapContext = significanceMapContextSetStart[ch][CONTEXT_TYPE_8x8] + (st != SCAN_DIAG ? nonDiagonalScan8x8ContextOffset[ch] : 0);
         else cp.firstSignificanceMapContext = significanceMapContextSetStart[ch][CONTEXT_TYPE_NxN];
-        t.scan = cp.scan; t.scanCG = cp.scanCG;
+        t.scan.assign(cp.scan, cp.scan + n); t.scanCG.assign(cp.scanCG, cp.scanCG + (n >> 4));
         t.inverse.resize(n);
         for (int s = 0; s < n; s++) t.inverse[cp.scan[s]] = (uint16_t)s;
         t.sigCtx.resize((size_t)4 * n);

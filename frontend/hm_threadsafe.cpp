@@ -5,7 +5,7 @@
 //     reference-counted versions below.
 //   * TComSlice::m_prevTid0POC, TComDataCU::m_pcGlbArlCoeff and g_md5_mismatch are made thread_local at build time
 //     (frontend/Makefile); hmdec_b200.cpp saves and restores the first and the last per decoder around every HM call.
-//   * The SPS-dependent globals — g_bitDepth, g_maxTrDynamicRange, g_uiMaxCUWidth/Height/Depth, g_uiAddCUDepth
+//   * The SPS-dependent globals — g_bitDepth, g_maxTrDynamicRange, g_saoMaxOffsetQVal, g_uiMaxCUWidth/Height/Depth, g_uiAddCUDepth
 //     (TComRom.cpp:245-252,319,542; written by TDecTop::xActivateParameterSets, TDecTop.cpp:323-333) and the z-scan /
 //     raster / pel tables (written by TDecCu::create for every picture, TDecCu.cpp:95-100) — stay process-global (they are
 //     read on every parser path; TLS in a dlopen'ed library would cost a call per access).  Instead every entry of the
@@ -20,6 +20,7 @@
 #include "TLibCommon/TComRom.h"
 #include "TLibCommon/TComSlice.h"
 #include "TLibCommon/TComChromaFormat.h"
+#include "TLibCommon/TComSampleAdaptiveOffset.h"
 #include "hm_threadsafe.h"
 
 static std::mutex g_romLock;
@@ -60,11 +61,15 @@ std::condition_variable g_gateCv;
 HmGeomKey g_bound;            // the key the globals hold now (invalid: unknown)
 int  g_users = 0;             // calls inside HM under g_bound
 bool g_exclusive = false;     // a call with an unknown key is inside, alone
+int  g_exclusiveWaiting = 0;  // calls with an unknown key that wait for the others to leave (newcomers queue behind them)
 unsigned long g_rebinds = 0;
 
 void bind(const HmGeomKey& k)
 {
   for (UInt ch = 0; ch < MAX_NUM_CHANNEL_TYPE; ch++) { g_bitDepth[ch] = k.bitDepth[ch]; g_maxTrDynamicRange[ch] = k.maxTrDynamicRange[ch]; }
+  // the truncation limit of sao_offset_abs, a global written by TComSampleAdaptiveOffset::create (TComSampleAdaptiveOffset.cpp:157)
+  // and read by the PARSER (TDecSbac.cpp:1796): a 10-bit stream parsed under an 8-bit neighbour's limit loses CABAC sync
+  for (UInt c = 0; c < MAX_NUM_COMPONENT; c++) g_saoMaxOffsetQVal[c] = (1u << (std::min<Int>(k.bitDepth[toChannelType(ComponentID(c))], MAX_SAO_TRUNCATED_BITDEPTH) - 5)) - 1;
   g_uiMaxCUWidth = k.maxCUWidth; g_uiMaxCUHeight = k.maxCUHeight; g_uiMaxCUDepth = k.maxCUDepth; g_uiAddCUDepth = k.addCUDepth;
   UInt* p = &g_auiZscanToRaster[0];
   initZscanToRaster(k.maxCUDepth, 1, 0, p);
@@ -82,12 +87,14 @@ void hm_geom_enter(const HmGeomKey& key)
   std::unique_lock<std::mutex> l(g_gateLock);
   if (!key.valid)
   {
+    g_exclusiveWaiting++;
     g_gateCv.wait(l, [] { return g_users == 0; });
+    g_exclusiveWaiting--;
     g_exclusive = true;
     g_users = 1;
     return;
   }
-  g_gateCv.wait(l, [&] { return !g_exclusive && (g_users == 0 || g_bound == key); });
+  g_gateCv.wait(l, [&] { return !g_exclusive && !g_exclusiveWaiting && (g_users == 0 || g_bound == key); });
   if (!(g_bound == key))
   {
     if (g_bound.valid) g_rebinds++;

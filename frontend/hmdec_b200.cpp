@@ -281,7 +281,9 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
   // Parameter sets are activated by the first slice of a picture only (TDecTop.cpp:505); a slice that arrives while a picture is
   // open either belongs to it or merely ends it (bNewPicture, nothing activated, the finished picture is filtered under ITS key).
   const bool activates = vcl && d->top.m_bFirstSliceInPicture;
-  GeomScope gate(d, activates ? peekSliceGeometry(d, nalu, bytes) : d->geom, vcl || (completes && d->geom.valid));
+  // parseSPS writes g_bitDepthInStream and reads it back a few lines later (TDecCAVLC.cpp:617-643): SPS NALs run alone.
+  const bool spsNal = nalu.m_nalUnitType == NAL_UNIT_SPS;
+  GeomScope gate(d, spsNal ? HmGeomKey() : (activates ? peekSliceGeometry(d, nalu, bytes) : d->geom), vcl || spsNal || (completes && d->geom.valid));
 
   hm_emit_set_current(d->emitter);
   hm_fast_set_skip_coeff_fill(d->emitter->cleanCoeffs());
