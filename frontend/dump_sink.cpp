@@ -76,10 +76,11 @@ public:
     TComPicYuv& rec = *pic->getPicYuvRec();
     TComDigest digest;
     calcMD5(rec, digest);                       // TComPicYuvMD5.cpp:183-205: 3 x 16 bytes
-    memcpy(m_gold[stage], digest.hash.data(), 48);
+    memset(m_gold[stage], 0, 48);               // absent components (4:0:0 chroma): all-zero digests
+    memcpy(m_gold[stage], digest.hash.data(), 16 * rec.getNumberValidComponents());
     if (m_planes)
     {
-      for (int c = 0; c < 3; c++)
+      for (int c = 0; c < (int)rec.getNumberValidComponents(); c++)
       {
         const ComponentID id = ComponentID(c);
         const int w = rec.getWidth(id), h = rec.getHeight(id), s = rec.getStride(id);

@@ -95,7 +95,7 @@ public:
     {
       TComPicYuv* rec = pic->getPicYuvRec();
       bool ok = true;
-      for (int c = 0; c < 3 && ok; c++)
+      for (int c = 0; c < (int)rec->getNumberValidComponents() && ok; c++)      // 4:0:0: the luma plane only
       {
         const ComponentID id = ComponentID(c);
         ok = hm_fast_plane_is_pinned(rec->getBuf(id)) &&
@@ -121,7 +121,7 @@ public:
     }
     TComPicYuv* rec = pic->getPicYuvRec();
     std::vector<Pel> keep;
-    for (int c = 0; c < 3; c++)
+    for (int c = 0; c < (int)rec->getNumberValidComponents(); c++)
     {
       const ComponentID id = ComponentID(c);
       const int w = rec->getWidth(id), h = rec->getHeight(id), st = rec->getStride(id);

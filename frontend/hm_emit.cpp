@@ -156,7 +156,7 @@ void HmEmitter::beginFrame(TComPic* pic, TComDataCU* ctu)
   }
   if (g_uiMaxCUWidth != g_uiMaxCUHeight)     fail("non-square CTU");
   if ((g_uiMaxCUWidth >> g_uiMaxCUDepth) != 4) fail("minimum partition size != 4");
-  if (pic->getChromaFormat() == CHROMA_400)  fail("4:0:0");
+  // 4:0:0: luma records only (HM walks getNumberValidComponents() components everywhere)
 
   m_tu.clear(); m_coef.clear(); m_intra.clear(); m_pu.clear(); m_puPrefix.clear(); m_puRefIdx.clear();
   m_puPrefix.push_back(0);

@@ -216,7 +216,7 @@ static int validate(hmr_engine* e, const hmr_frame_desc* f)
   const hmr_frame_hdr& h = *f->hdr;
   if (h.magic != HMR_MAGIC || h.version != HMR_VERSION) return fail(e, HMR_ERR_FORMAT, "bad magic/version in frame header");
   if (h.width <= 0 || h.height <= 0 || (h.width & 7) || (h.height & 7)) return fail(e, HMR_ERR_FORMAT, "picture size must be a positive multiple of 8");
-  if (h.chroma_format < HMR_CHROMA_420 || h.chroma_format > HMR_CHROMA_444) return fail(e, HMR_ERR_FORMAT, "unsupported chroma format");
+  if (h.chroma_format > HMR_CHROMA_444) return fail(e, HMR_ERR_FORMAT, "unsupported chroma format");      // 4:0:0 .. 4:4:4 (TypeDef.h ChromaFormat)
   if (h.log2_ctu < 4 || h.log2_ctu > 6) return fail(e, HMR_ERR_FORMAT, "unsupported CTU size");
   if (h.bit_depth_luma < 8 || h.bit_depth_luma > 12 || h.bit_depth_chroma < 8 || h.bit_depth_chroma > 12) return fail(e, HMR_ERR_FORMAT, "bit depth outside 8..12");
   if (h.out_slot >= HMR_MAX_SLOTS) return fail(e, HMR_ERR_FORMAT, "out_slot out of range");
@@ -243,7 +243,7 @@ static int validate(hmr_engine* e, const hmr_frame_desc* f)
     const int csx = (h.chroma_format == HMR_CHROMA_420 || h.chroma_format == HMR_CHROMA_422) ? 1 : 0, csy = h.chroma_format == HMR_CHROMA_420 ? 1 : 0;
     auto inside = [&](int comp, unsigned x, unsigned y, unsigned n) {
       const unsigned w = comp ? h.width >> csx : h.width, hh = comp ? h.height >> csy : h.height;
-      return comp <= 2 && x + n <= w && y + n <= hh;
+      return comp <= (h.chroma_format == HMR_CHROMA_400 ? 0 : 2) && x + n <= w && y + n <= hh;
     };
     for (uint32_t i = 0; i < h.n_tu; i++)
     {
@@ -312,9 +312,10 @@ static int ensure_geometry(hmr_engine* e, const hmr_frame_hdr& h)
     e->fmt = h.chroma_format; e->csx = csx; e->csy = csy; e->log2ctu = h.log2_ctu;
     for (int c = 0; c < 3; c++)
     {
-      e->w[c] = c ? h.width >> csx : h.width;
-      e->h[c] = c ? h.height >> csy : h.height;
-      e->pitch[c] = (int)ALIGN_UP((size_t)e->w[c], 64);      // 128-byte rows
+      const bool absent = c && h.chroma_format == HMR_CHROMA_400;      // 4:0:0: the chroma planes are empty (TComPicYuv allocates none)
+      e->w[c] = absent ? 0 : (c ? h.width >> csx : h.width);
+      e->h[c] = absent ? 0 : (c ? h.height >> csy : h.height);
+      e->pitch[c] = (int)ALIGN_UP((size_t)std::max(e->w[c], 1), 64);      // 128-byte rows
     }
     e->ctusW = (h.width + (1 << h.log2_ctu) - 1) >> h.log2_ctu;
     e->ctusH = (h.height + (1 << h.log2_ctu) - 1) >> h.log2_ctu;
@@ -608,7 +609,9 @@ int hmr_sync(hmr_engine* e)
 
 static int read_planeset(hmr_engine* e, const PlaneSet& ps, int comp, int16_t* dst, size_t dstStride, bool async)
 {
-  if (!e->haveGeom || comp < 0 || comp > 2 || !dst) return fail(e, HMR_ERR_ARG, "read_plane: bad argument");
+  if (!e->haveGeom || comp < 0 || comp > 2) return fail(e, HMR_ERR_ARG, "read_plane: bad argument");
+  if (e->w[comp] == 0 || e->h[comp] == 0) return HMR_OK;   // an absent component (4:0:0 chroma): nothing to copy
+  if (!dst) return fail(e, HMR_ERR_ARG, "read_plane: bad argument");
   CK(cudaSetDevice(e->device));
   CK(cudaMemcpy2DAsync(dst, dstStride * sizeof(int16_t), ps.p[comp], (size_t)ps.pitch[comp] * sizeof(int16_t),
                        (size_t)e->w[comp] * sizeof(int16_t), e->h[comp], cudaMemcpyDeviceToHost, e->stream));
@@ -669,6 +672,7 @@ int hmr_picture_hash(hmr_engine* e, int slot, int type, uint32_t out[3])
   CK(cudaSetDevice(e->device));
   if (!e->dHash) CK(cudaMalloc(&e->dHash, 3 * sizeof(uint32_t)));
   const size_t rows = (size_t)e->h[0] + e->h[1] + e->h[2];
+  out[0] = out[1] = out[2] = 0;                             // absent components (4:0:0 chroma) report 0
   if (rows > e->hashRowsCap)
   {
     if (e->dHashRows) cudaFree(e->dHashRows);
@@ -690,6 +694,7 @@ int hmr_picture_hash(hmr_engine* e, int slot, int type, uint32_t out[3])
   size_t base = 0;
   for (int c = 0; c < 3; c++)
   {
+    if (e->h[c] == 0) continue;
     const uint64_t rowBits = (uint64_t)e->w[c] * (bd[c] > 8 ? 16 : 8);
     const uint32_t shiftRow = gf_xpow(rowBits);
     uint32_t crc = 0xffff;

@@ -54,13 +54,14 @@ void launch_hash(const PlaneSet& pic, const int w[3], const int h[3], const int 
   if (type == 3)
   {
     cudaMemsetAsync(d_out, 0, 3 * sizeof(uint32_t), s);
-    for (int c = 0; c < 3; c++) checksum_kernel<<<296, 256, 0, s>>>(pic.p[c], w[c], h[c], pic.pitch[c], bd[c], d_out + c);
+    for (int c = 0; c < 3; c++) if (w[c] && h[c]) checksum_kernel<<<296, 256, 0, s>>>(pic.p[c], w[c], h[c], pic.pitch[c], bd[c], d_out + c);
   }
   else
   {
     uint32_t* rows = d_scratch;
     for (int c = 0; c < 3; c++)
     {
+      if (h[c] == 0) continue;                               // 4:0:0: no chroma planes
       crc_rows_kernel<<<(h[c] + 127) / 128, 128, 0, s>>>(pic.p[c], w[c], h[c], pic.pitch[c], bd[c], rows);
       rows += h[c];
     }

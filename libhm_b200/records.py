@@ -59,6 +59,8 @@ class Frame:
 
     def comp_size(self, c):
         fmt = int(self.h["chroma_format"])
+        if c and fmt == 0:
+            return 0, 0          # 4:0:0: no chroma planes (TComPicYuv allocates none)
         sx = 1 if (c and fmt in (1, 2)) else 0
         sy = 1 if (c and fmt == 1) else 0
         return int(self.h["width"]) >> sx, int(self.h["height"]) >> sy
@@ -125,6 +127,8 @@ def picture_md5(planes, bit_depths):
     import hashlib
     out = np.zeros((3, 16), np.uint8)
     for c, (p, bd) in enumerate(zip(planes, bit_depths)):
+        if p.size == 0:          # an absent component (4:0:0 chroma): all-zero digest, the convention of the dump's GOLD section
+            continue
         raw = p.astype(np.uint8).tobytes() if bd <= 8 else p.astype("<u2").tobytes()
         out[c] = np.frombuffer(hashlib.md5(raw).digest(), np.uint8)
     return out

@@ -228,7 +228,7 @@ void orc_predict_pu(const hmr_frame_hdr* h, const hmr_pu* p, const hmr_wp* wp, i
 {
   int16_t a[64 * 64], b[64 * 64];
   const int fmt = h->chroma_format;
-  for (int c = 0; c < 3; c++)
+  for (int c = 0; c < (fmt == HMR_CHROMA_400 ? 1 : 3); c++)   /* getNumberValidComponents (TComPrediction.cpp:520) */
   {
     const int cx = csx_of(fmt, c), cy = csy_of(fmt, c);
     const int bd = c ? h->bit_depth_chroma : h->bit_depth_luma;
@@ -513,7 +513,7 @@ void orc_sao(const hmr_frame_desc* f, const orc_pic* src, orc_pic* dst)
     const int av = cp->avail;
     const int L = av & HMR_AV_L, R = av & HMR_AV_R, A = av & HMR_AV_A, B = av & HMR_AV_B;
     const int AL = av & HMR_AV_AL, AR = av & HMR_AV_AR, BL = av & HMR_AV_BL, BR = av & HMR_AV_BR;
-    for (int c = 0; c < 3; c++)
+    for (int c = 0; c < (fmt == HMR_CHROMA_400 ? 1 : 3); c++)
     {
       const hmr_sao* s = &cp->sao[c];
       if (s->type == HMR_SAO_OFF) continue;

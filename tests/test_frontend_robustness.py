@@ -124,15 +124,15 @@ def test_decoders_of_different_geometry_run_concurrently_as_threads(tmp_path):
 
 
 def test_unsupported_feature_is_reported_through_the_reference_abi(tmp_path):
-    """4:0:0 is not on the GPU reconstruction path: the decoder must stop with LIBHMDEC_ERROR from libHMDec_push_nal_unit (sticky),
+    """A stream whose smallest partition is 8x8 (min TU 8, min CU 16) is not on the GPU reconstruction path: the decoder must stop with LIBHMDEC_ERROR from libHMDec_push_nal_unit (sticky),
     name the feature through libHMDecB200_unsupported, and leave the process alive."""
     lib = _lib()
     dec = lib.libHMDecB200_new_decoder_ex(1, str(tmp_path / "g.hmr").encode())
     assert dec
-    nals = _nals(os.path.join(GOLDEN, "s_gray400_240p.bin"))
+    nals = _nals(os.path.join(GOLDEN, "s_mintu8_240p.bin"))
     pics, rc = _decode(lib, dec, nals)
     assert rc == ERROR
-    assert b"4:0:0" in lib.libHMDecB200_unsupported(dec)
+    assert b"minimum partition size" in lib.libHMDecB200_unsupported(dec)
     newpic, check = C.c_bool(False), C.c_bool(False)
     buf = C.create_string_buffer(nals[-1], len(nals[-1]))
     assert lib.libHMDec_push_nal_unit(dec, buf, len(nals[-1]), True, C.byref(newpic), C.byref(check)) == ERROR

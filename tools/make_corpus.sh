@@ -58,6 +58,7 @@ JOBS=(
  "s_slseg_240p       encoder_randomaccess_main.cfg         416  240  9  8  420 43 --SliceSegmentMode=1 --SliceSegmentArgument=7 -q 30"
  "s_gray400_240p     encoder_randomaccess_main_rext.cfg    416  240  5  8  400 44 --InternalBitDepth=8 -q 30"
  "s_cksum_240p       encoder_randomaccess_main10.cfg       416  240  9  10 420 42 --SEIDecodedPictureHash=3 -q 30"
+ "s_mintu8_240p      encoder_intra_main.cfg                416  240  2  8  420 45 --QuadtreeTULog2MinSize=3 --MaxPartitionDepth=3 -q 32"
 )
 WANT=$1
 # s_switch_240p: five coded video sequences back to back, every one starting with an IDR and four of the five activating an SPS of
