@@ -108,7 +108,7 @@ def algorithmic_bytes(fr):
     import numpy as np
     h = fr.h
     fmt = int(h["chroma_format"])
-    cf = {1: 0.5, 2: 1.0, 3: 2.0}[fmt]                      # chroma samples per luma sample (both planes)
+    cf = {0: 0.0, 1: 0.5, 2: 1.0, 3: 2.0}[fmt]                      # chroma samples per luma sample (both planes)
     S_b = 2.0 * int(h["width"]) * int(h["height"]) * (1 + cf)
     w4, h4 = (int(h["width"]) + 3) // 4, (int(h["height"]) + 3) // 4
     w8, h8 = (int(h["width"]) + 7) // 8, (int(h["height"]) + 7) // 8

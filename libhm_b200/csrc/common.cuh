@@ -6,6 +6,32 @@
 
 #define HMR_INTRA_JOB_WORDS 16      // 512 (row, component) jobs: 170 CTU rows
 
+// Order in which intra_kernel's CTAs claim the (CTU row, component) jobs of a picture = bit order of intra_job_mask.  Per component the
+// rows ascend (a job only ever waits for the row above of its own component, which must have been handed out before it).  Between the
+// components luma goes first: a luma row takes about twice as long as a chroma row and its wavefront is the critical path of the picture,
+// so a chroma pair follows every SECOND luma row (Y0 Cb0 Cr0 Y1 | Y2 Cb1 Cr1 Y3 | ...) and the second half of the chroma rows comes
+// after the last luma row — with the launcher's CTA limit, row-major order (Y Cb Cr per row) left late luma rows waiting for a CTA
+// while chroma rows far ahead of their turn held them (2160p I picture: row 32 started 340 us late).
+__host__ __device__ inline int intra_job_index(int row, int comp, int rows)
+{
+  const int H = (rows + 1) >> 1;
+  if (comp == 0) return row + 2 * ((row + 1) >> 1);
+  if (row < H) return 4 * row + comp;
+  return rows + 2 * H + 2 * (row - H) + (comp - 1);
+}
+__host__ __device__ inline void intra_job_decode(int job, int rows, int& row, int& comp)
+{
+  const int H = (rows + 1) >> 1, head = rows + 2 * H;
+  if (job < head)
+  {
+    const int q = job >> 2, m = job & 3;
+    if (m == 0) { row = 2 * q; comp = 0; }
+    else if (m == 3) { row = 2 * q + 1; comp = 0; }
+    else { row = q; comp = m; }
+  }
+  else { const int t = job - head; row = H + (t >> 1); comp = 1 + (t & 1); }
+}
+
 struct PlaneSet
 {
   int16_t* p[3];
@@ -46,7 +72,7 @@ struct FrameParams
   int                        intra_max_addr;  // largest reference-address table of one (component, CTU), entries           } capacities of
   int                        intra_res_span;  // largest residual span of one (component, CTU), samples                      } intra_kernel
   unsigned long long*        intra_progress;  // [3][ctus_h], (epoch << 32) | CTUs finished in that row; [3 * ctus_h] = the job counter (zeroed by the pre-pass)
-  uint32_t                   intra_job_mask[HMR_INTRA_JOB_WORDS];   // bit 3 * row + comp: that CTU row of that component has intra TUs (a "job" of intra_kernel)
+  uint32_t                   intra_job_mask[HMR_INTRA_JOB_WORDS];   // bit intra_job_index(row, comp, ctus_h): that CTU row of that component has intra TUs (a "job" of intra_kernel)
   int                        intra_jobs;      // number of set bits; -1 = every (row, component) is a job (mask not filled in: more rows than it has bits, or records not inspected)
   unsigned long long         epoch;
 };

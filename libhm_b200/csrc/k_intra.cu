@@ -405,6 +405,7 @@ __device__ __forceinline__ void line_phase(const IntraOp op, const uint16_t* __r
 __global__ void __launch_bounds__(PREP_WARPS * 32) intra_prep_kernel(const __grid_constant__ FrameParams P)
 {
   __shared__ int s_offAll[PREP_WARPS][IN_MAXREC + 1];
+  __shared__ uint4 s_recAll[PREP_WARPS][IN_MAXREC];                // the CTU's records (16 bytes each), read from global memory ONCE
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nctu = P.ctus_w * P.ctus_h;
   const int job = blockIdx.x * PREP_WARPS + warp;
@@ -416,6 +417,15 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) intra_prep_kernel(const __gri
   const int count = (int)min(__ldg(&P.irange[ctu].count[comp]), (uint32_t)IN_MAXREC);
   if (count == 0) { if (lane == 0) P.intra_prep[job] = make_uint4(0, 0, 0, 0); return; }
   int* s_off = s_offAll[warp];
+  uint4* s_rec = s_recAll[warp];
+  // all record loads of the CTU in flight together (independent, coalesced); everything below reads shared memory — a warp that
+  // fetched record k from global memory inside its TU loop paid one L2 round trip per TU (74 us for a 2160p I picture)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P.intra + first);
+#pragma unroll 4
+    for (int k = lane; k < count; k += 32) s_rec[k] = __ldg(src + k);
+  }
+  __syncwarp();
   const int csx = comp ? P.csx : 0, csy = comp ? P.csy : 0;
   IntraGeom g;
   g.CTW = (1 << P.hdr.log2_ctu) >> csx; g.CTH = (1 << P.hdr.log2_ctu) >> csy;
@@ -430,7 +440,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) intra_prep_kernel(const __gri
     int len = 0;
     if (k < count)
     {
-      const hmr_intra r = P.intra[first + k];
+      const hmr_intra r = *reinterpret_cast<const hmr_intra*>(&s_rec[k]);
       len = (4 << r.log2_size) + 1;
       if (r.resid_off != HMR_NO_OFFSET) { mn = min(mn, r.resid_off); mx = max(mx, r.resid_off + (1u << (2 * r.log2_size))); }
     }
@@ -445,12 +455,17 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) intra_prep_kernel(const __gri
   __syncwarp();
   const bool strongAllowed = P.hdr.flags & HMR_FRM_STRONG_INTRA_SMOOTHING;
   uint16_t* tab = P.intra_tab + (size_t)job * IN_ADDR;
+  // micro-ops: one lane per TU (16-byte stores, coalesced)
+  for (int k = lane; k < count; k += 32)
+  {
+    const hmr_intra r = *reinterpret_cast<const hmr_intra*>(&s_rec[k]);
+    P.intra_ops[first + k] = intra_make_op(r, g, mn, strongAllowed, s_off[k]);
+  }
+  // address tables: the warp walks the TUs, lanes = table entries
   for (int k = 0; k < count; k++)
   {
-    const hmr_intra r = P.intra[first + k];
-    const int off = s_off[k];
-    intra_addr_table(r, tab + off, g, lane);
-    if (lane == 0) P.intra_ops[first + k] = intra_make_op(r, g, mn, strongAllowed, off);
+    const hmr_intra r = *reinterpret_cast<const hmr_intra*>(&s_rec[k]);
+    intra_addr_table(r, tab + s_off[k], g, lane);
   }
   if (lane == 0) P.intra_prep[job] = make_uint4(mn, mx > mn ? mx - mn : 0u, (unsigned)running, 0u);
 }
@@ -549,7 +564,7 @@ __device__ __forceinline__ void chain_tu(const IntraOp op, const int k, const in
   }
 }
 
-// Persistent CTAs take (CTU row, component) jobs from a queue, in ascending order (row-major: Y, Cb, Cr of row 0, then row 1, ...).
+// Persistent CTAs take (CTU row, component) jobs from a queue, in the order of intra_job_index (common.cuh: rows ascending per component, luma ahead of chroma).
 // A job only waits for the job of the same component one row up, which was handed out earlier to a CTA that is resident (cooperative
 // launch): no deadlock however few CTAs there are.  A row lags the one above by two CTUs, so only ~a third of the rows of a 2160p
 // picture are ever active at once: the launcher starts IN_MAX_CTAS CTAs, not one per job — what a CTA holds (registers, shared memory)
@@ -605,11 +620,13 @@ __global__ void __launch_bounds__(IN_THREADS, 3) intra_kernel(const __grid_const
   __syncthreads();
   const int job = s_job;
   if (job >= 3 * P.ctus_h) break;
-  const int row = job / 3, comp = job - 3 * row;
+  int row, comp;
+  intra_job_decode(job, P.ctus_h, row, comp);
   if (comp > 0 && P.hdr.chroma_format == HMR_CHROMA_400) continue;
   unsigned long long* myProg = P.intra_progress + comp * P.ctus_h + row;
   // the row above only has to be waited for if it is a job itself (without intra TUs its samples were final before the launch)
-  const bool upIsJob = row > 0 && (P.intra_jobs < 0 || ((P.intra_job_mask[(job - 3) >> 5] >> ((job - 3) & 31)) & 1));
+  const int upJob = row > 0 ? intra_job_index(row - 1, comp, P.ctus_h) : 0;
+  const bool upIsJob = row > 0 && (P.intra_jobs < 0 || ((P.intra_job_mask[upJob >> 5] >> (upJob & 31)) & 1));
   const volatile unsigned long long* upProg = upIsJob ? P.intra_progress + comp * P.ctus_h + row - 1 : nullptr;
   const unsigned long long base = P.epoch << 32;
 
@@ -812,10 +829,26 @@ __global__ void __launch_bounds__(IN_THREADS, 3) intra_kernel(const __grid_const
     bar_sync(BAR_DONE + b, 64);                              // the chain has predicted CTU c
     const int16_t* ptile = s_tileB + b * TILE_PAD;
     const int pox = c * CTW, pcw = min(CTW, W - pox);
+    // The row below reads nothing of this CTU but its BOTTOM row (reference samples above / above-right): that row goes out first and the
+    // progress is published right behind it — the fence then waits for one 128-byte store instead of the whole tile, which takes about a
+    // microsecond out of every row-to-row hand-over (33 of them on the critical path of a 2160p I picture).  Everything else only has to be
+    // in memory when the kernel ends (deblocking is stream-ordered behind it).
+    {
+      const int y = ch - 1;
+      int16_t* grow = plane + (size_t)(oy + y) * pitch + pox;
+      if ((pcw & 7) == 0) { if (lane < (pcw >> 3)) *((uint4*)grow + lane) = *(const uint4*)&ptile[TIDX(y, 8 * lane)]; }
+      else                { if (lane < (pcw >> 2)) *((uint2*)grow + lane) = *(const uint2*)&ptile[TIDX(y, 4 * lane)]; }
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+      __threadfence();
+      *(volatile unsigned long long*)myProg = base + (unsigned long long)cn;    // every CTU before cn (the next intra CTU, or the end of the row) is final for the row below
+    }
     if ((pcw & 7) == 0)
     {
       const int vecPerRow = pcw >> 3;
-      for (int i = lane; i < ch * vecPerRow; i += 32)
+      for (int i = lane; i < (ch - 1) * vecPerRow; i += 32)
       {
         const int y = i / vecPerRow, v = i - y * vecPerRow;
         *((uint4*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint4*)&ptile[TIDX(y, 8 * v)];
@@ -824,18 +857,13 @@ __global__ void __launch_bounds__(IN_THREADS, 3) intra_kernel(const __grid_const
     else
     {
       const int vecPerRow = pcw >> 2;
-      for (int i = lane; i < ch * vecPerRow; i += 32)
+      for (int i = lane; i < (ch - 1) * vecPerRow; i += 32)
       {
         const int y = i / vecPerRow, v = i - y * vecPerRow;
         *((uint2*)(plane + (size_t)(oy + y) * pitch + pox) + v) = *(const uint2*)&ptile[TIDX(y, 4 * v)];
       }
     }
     __syncwarp();
-    if (lane == 0)
-    {
-      __threadfence();
-      *(volatile unsigned long long*)myProg = base + (unsigned long long)cn;    // every CTU before cn (the next intra CTU, or the end of the row) is final
-    }
     __threadfence_block();
     bar_arrive(BAR_FREE + b, 64);                            // the fetcher may reuse the buffer (CTU n + 2)
     c = cn;
@@ -867,13 +895,14 @@ IntraSizes intra_sizes_host(const hmr_frame_hdr& h, const hmr_intra* rec, const 
   worst.jobs = -1;
   if (!rec || !range) { z.jobs = -1; return z; }
   const uint32_t ctusW = (h.width + (1u << h.log2_ctu) - 1) >> h.log2_ctu;
-  const bool maskFits = ctusW > 0 && 3 * ((h.n_ctu + ctusW - 1) / ctusW) <= 32 * HMR_INTRA_JOB_WORDS;
+  const uint32_t rows = ctusW ? (h.n_ctu + ctusW - 1) / ctusW : 0;
+  const bool maskFits = ctusW > 0 && 3 * rows + 1 <= 32 * HMR_INTRA_JOB_WORDS;
   for (uint32_t ctu = 0; ctu < h.n_ctu; ctu++)
     for (int c = 0; c < 3; c++)
     {
       const uint32_t first = range[ctu].first[c], count = range[ctu].count[c];
       if (!count) continue;
-      if (maskFits) { const uint32_t jb = 3 * (ctu / ctusW) + c; z.jobMask[jb >> 5] |= 1u << (jb & 31); }
+      if (maskFits) { const uint32_t jb = (uint32_t)intra_job_index((int)(ctu / ctusW), c, (int)rows); z.jobMask[jb >> 5] |= 1u << (jb & 31); }
       if (first > h.n_intra || count > h.n_intra - first) return worst;   // inconsistent ranges: worst-case capacities
       unsigned tab = 0, mn = 0xffffffffu, mx = 0;
       for (uint32_t k = 0; k < count; k++)
