@@ -385,7 +385,10 @@ def main():
         pics = sum(count_pictures(bins[i % len(bins)]) for i in range(ncores))
         return {"value": round(pics / wall, 3), "unit": "frames/s", "cores": ncores, "kind": "reference", "sample": "one pass per core, TAppDecoderStatic -d 0 (SEI MD5 check on)"}
 
-    thr = cores_rank + cores_rank // 2      # 1.5 decoder threads per host core: the surplus fills the ~0.13 s a finishing decoder waits for its last MD5 chains
+    # 2 decoder threads per host core: a decoder that has pushed its last NAL waits ~0.14 s for the MD5 chains of its last pictures (a serial
+    # chain per plane, on the device); the surplus threads parse meanwhile (tools/gpu_e2e_waits.sh: 16 / 24 / 32 threads on 16 cores give
+    # 569 / 742 / 808 frames/s, 820 without the hash check)
+    thr = 2 * cores_rank
     have_cli = os.path.exists(CLI)
 
     # ---- headline: `value` = 8 copies of the stream per GPU, records resident in HBM

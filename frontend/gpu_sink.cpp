@@ -14,6 +14,7 @@
 #include <mutex>
 #include "hm_emit.h"
 #include "hm_fast.h"
+#include "hm_waitstats.h"
 #include "hmrecon.h"
 
 // Process-wide pool of page-locked plane buffers (cudaMallocHost through the engine's C ABI).  Allocation is slow
@@ -84,7 +85,7 @@ public:
   virtual bool frameReady(const hmr_frame_desc& d, TComPic* pic)
   {
     if (!m_error.empty()) return false;
-    if (hmr_submit_frame(m_eng, &d) != HMR_OK) return engineFailed("hmr_submit_frame");
+    { HmWaitScope ws(HMW_SUBMIT); if (hmr_submit_frame(m_eng, &d) != HMR_OK) return engineFailed("hmr_submit_frame"); }
     State& s = m_state[pic];
     s.slot = d.hdr->out_slot;
     s.hostStale = true;
@@ -158,7 +159,7 @@ public:
   {
     std::map<TComPic*, State>::iterator it = m_state.find(pic);
     if (it == m_state.end() || m_verify || !m_gpuMd5) return false;
-    while (m_jobs >= 7) deliverFront(true);                  // the engine keeps at most 8 digests in flight
+    if (m_jobs >= HMR_MD5_MAX_JOBS - 1) { HmWaitScope ws(HMW_HASH_RING); while (m_jobs >= HMR_MD5_MAX_JOBS - 1) deliverFront(true); }   // the engine's ring is full: the parser waits for the oldest digest
     Pending p;
     p.isJob = true; p.quiet = quiet; p.ncomp = ncomp; p.line = line;
     p.expected.assign(expected, expected + 16 * ncomp);

@@ -22,6 +22,28 @@
 #include "TLibCommon/TComChromaFormat.h"
 #include "TLibCommon/TComSampleAdaptiveOffset.h"
 #include "hm_threadsafe.h"
+#include "hm_waitstats.h"
+#include <cstdio>
+
+thread_local bool t_hmwActive = true;
+
+HmWaitStats& hm_wait_stats()
+{
+  static HmWaitStats s;
+  static const bool init = [] {
+    for (int i = 0; i < HMW_COUNT; i++) { s.ns[i] = 0; s.calls[i] = 0; }
+    s.on = getenv("HMDEC_B200_STATS") != NULL;
+    s.decoders = 0;
+    s.skip = s.on ? atoi(getenv("HMDEC_B200_STATS")) : 0;
+    if (s.on) atexit([] {
+      static const char* name[HMW_COUNT] = { "new_decoder", "free_decoder", "sink submit (validate + pack + enqueue)", "wait for a picture's planes", "wait for hash verdicts", "geometry gate", "hash ring full (inside push)", "push_nal_unit (total)" };
+      fprintf(stderr, "hmdec_b200 wait stats (wall clock, all threads; decoders %d.. of %d):\n", s.skip + 1, s.decoders.load());
+      for (int i = 0; i < HMW_COUNT; i++) fprintf(stderr, "  %-42s %9.3f s in %8lld calls\n", name[i], 1e-9 * (double)s.ns[i].load(), s.calls[i].load());
+    });
+    return true; }();
+  (void)init;
+  return s;
+}
 
 static std::mutex g_romLock;
 static int g_romUsers = 0;
@@ -84,6 +106,7 @@ static bool gateOff() { static const bool off = getenv("HMDEC_B200_NO_GEOM_GATE"
 void hm_geom_enter(const HmGeomKey& key)
 {
   if (gateOff()) return;
+  HmWaitScope ws(HMW_GEOM_GATE);
   std::unique_lock<std::mutex> l(g_gateLock);
   if (!key.valid)
   {

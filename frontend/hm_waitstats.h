@@ -1,0 +1,34 @@
+// hm_waitstats.h — HMDEC_B200_STATS: wall-clock time the decoder threads of the process spend in the places where they can BLOCK
+// (waiting for the device or for each other), summed over all threads and printed once at exit.  The end-to-end rate is bounded by the
+// host; this tells CPU work from waiting.
+#ifndef HM_WAITSTATS_H
+#define HM_WAITSTATS_H
+#include <atomic>
+#include <chrono>
+
+enum HmWaitKind { HMW_NEW_DECODER = 0, HMW_FREE_DECODER, HMW_SUBMIT, HMW_PLANE_WAIT, HMW_HASH_WAIT, HMW_GEOM_GATE, HMW_HASH_RING, HMW_PUSH_TOTAL, HMW_COUNT };
+
+struct HmWaitStats
+{
+  std::atomic<long long> ns[HMW_COUNT];
+  std::atomic<long long> calls[HMW_COUNT];
+  std::atomic<int> decoders;     // decoders created so far
+  int skip;                      // HMDEC_B200_STATS=<n>: the first n decoders of the process (a harness's warm-up pass) are not counted
+  bool on;
+};
+HmWaitStats& hm_wait_stats();
+extern thread_local bool t_hmwActive;     // the decoder this thread is driving is being counted
+
+struct HmWaitScope
+{
+  HmWaitKind k; std::chrono::steady_clock::time_point t0; bool on;
+  explicit HmWaitScope(HmWaitKind kind) : k(kind), on(hm_wait_stats().on && t_hmwActive) { if (on) t0 = std::chrono::steady_clock::now(); }
+  ~HmWaitScope()
+  {
+    if (!on) return;
+    HmWaitStats& s = hm_wait_stats();
+    s.ns[k] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    s.calls[k] += 1;
+  }
+};
+#endif

@@ -34,6 +34,7 @@
 #include "hm_emit.h"
 #include "hm_fast.h"
 #include "hm_threadsafe.h"
+#include "hm_waitstats.h"
 
 // HM keeps the "hash mismatch seen" flag in a global that the application must define (TDecGop.cpp:48); thread_local in this
 // build (frontend/Makefile patches the declaration), saved and restored per decoder around every HM call.
@@ -72,6 +73,7 @@ struct Decoder
   bool  failed;              // sticky: an unsupported feature or an engine error was reported through LIBHMDEC_ERROR
   Int   prevTid0POC;         // per-decoder copy of TComSlice::m_prevTid0POC (thread_local in this build)
   HmGeomKey geom;            // SPS-dependent HM globals this decoder runs under (hm_threadsafe.cpp); invalid before the first activation
+  bool  statsActive;         // HMDEC_B200_STATS counts this decoder (hm_waitstats.h)
   std::vector<libHMDec_BlockValue> internals;
 
   Decoder(HmFrameSink* s)
@@ -198,12 +200,17 @@ static void tuneMallocOnce()
 libHMDec_context* libHMDecB200_new_decoder_ex(int backend, const char* arg)
 {
   tuneMallocOnce();
+  const bool counted = hm_wait_stats().on && ++hm_wait_stats().decoders > hm_wait_stats().skip;
+  t_hmwActive = counted;
+  HmWaitScope ws(HMW_NEW_DECODER);
   HmFrameSink* sink = NULL;
   if (backend == 0) sink = hm_new_gpu_sink();
   else if (backend == 1 && arg && !strcmp(arg, "null")) sink = hm_new_null_sink();
   else if (backend == 1 && arg) sink = hm_new_dump_sink(arg);
   if (!sink) return NULL;
-  return (libHMDec_context*)new Decoder(sink);
+  Decoder* d = new Decoder(sink);
+  d->statsActive = counted;
+  return (libHMDec_context*)d;
 }
 
 libHMDec_context* libHMDec_new_decoder(void)
@@ -216,6 +223,8 @@ libHMDec_context* libHMDec_new_decoder(void)
 libHMDec_error libHMDec_free_decoder(libHMDec_context* decCtx)
 {
   if (!decCtx) return LIBHMDEC_ERROR;
+  t_hmwActive = D(decCtx)->statsActive;
+  HmWaitScope ws(HMW_FREE_DECODER);
   delete D(decCtx);
   return LIBHMDEC_OK;
 }
@@ -234,7 +243,8 @@ bool libHMDecB200_hash_mismatch(libHMDec_context* decCtx)
 {
   if (!decCtx) return false;
   Decoder* d = D(decCtx);
-  d->sink->drainHashes(true);            // digests still in flight on the device
+  t_hmwActive = d->statsActive;
+  { HmWaitScope ws(HMW_HASH_WAIT); d->sink->drainHashes(true); }            // digests still in flight on the device
   if (d->sink->hashMismatchSeen()) d->hashMismatch = true;
   return d->hashMismatch;
 }
@@ -258,6 +268,8 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
 {
   Decoder* d = D(decCtx);
   if (!d) return LIBHMDEC_ERROR;
+  t_hmwActive = d->statsActive;
+  HmWaitScope wsTotal(HMW_PUSH_TOTAL);
   if (length <= 0) return LIBHMDEC_ERROR_READ_ERROR;
   if (length < 4 && !eof) return LIBHMDEC_ERROR_READ_ERROR;
 
@@ -281,9 +293,13 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
   // Parameter sets are activated by the first slice of a picture only (TDecTop.cpp:505); a slice that arrives while a picture is
   // open either belongs to it or merely ends it (bNewPicture, nothing activated, the finished picture is filtered under ITS key).
   const bool activates = vcl && d->top.m_bFirstSliceInPicture;
-  // parseSPS writes g_bitDepthInStream and reads it back a few lines later (TDecCAVLC.cpp:617-643): SPS NALs run alone.
-  const bool spsNal = nalu.m_nalUnitType == NAL_UNIT_SPS;
-  GeomScope gate(d, spsNal ? HmGeomKey() : (activates ? peekSliceGeometry(d, nalu, bytes) : d->geom), vcl || spsNal || (completes && d->geom.valid));
+  GeomScope gate(d, activates ? peekSliceGeometry(d, nalu, bytes) : d->geom, vcl || (completes && d->geom.valid));
+  // parseSPS writes the global g_bitDepthInStream and reads it back a few lines later (TDecCAVLC.cpp:617-643; nothing else on the product
+  // path reads it): SPS NALs of different decoders exclude EACH OTHER — not the slice parsing of the other decoders, which a pass through
+  // the geometry gate with an unknown key would stall for the length of a picture at the start of every bitstream.
+  static std::mutex spsParseLock;
+  std::unique_lock<std::mutex> spsGuard(spsParseLock, std::defer_lock);
+  if (nalu.m_nalUnitType == NAL_UNIT_SPS) spsGuard.lock();
 
   hm_emit_set_current(d->emitter);
   hm_fast_set_skip_coeff_fill(d->emitter->cleanCoeffs());
@@ -406,7 +422,8 @@ short* libHMDEC_get_image_plane(libHMDec_picture* pic, libHMDec_ColorComponent c
   }
   if (owner)
   {
-    owner->sink->fetchPicture((TComPic*)pic);            // device -> HM's padded host plane, once per picture
+    t_hmwActive = owner->statsActive;
+    { HmWaitScope ws(HMW_PLANE_WAIT); owner->sink->fetchPicture((TComPic*)pic); }            // device -> HM's padded host plane, once per picture
     if (owner->sink->error()) return NULL;               // the samples never arrived
   }
   return ((TComPic*)pic)->getPicYuvRec()->getAddr(id);

@@ -35,6 +35,7 @@ extern "C" {
 typedef struct hmr_engine hmr_engine;
 typedef struct hmr_resident_frame hmr_resident_frame;
 
+#define HMR_MD5_MAX_JOBS 24      /* digests one engine keeps in flight (each holds a private copy of its picture) */
 enum { HMR_OK = 0, HMR_PENDING = 1, HMR_ERR_CUDA = -1, HMR_ERR_ARG = -2, HMR_ERR_FORMAT = -3, HMR_ERR_NOMEM = -4, HMR_ERR_BUSY = -5 };
 
 /* stage bits for hmr_set_stage_mask (default: all).  Same numbering as the oracle's orc_reconstruct_frame. */
@@ -69,7 +70,8 @@ int  hmr_write_plane(hmr_engine* e, int slot, int comp, const int16_t* src, size
 int  hmr_picture_hash(hmr_engine* e, int slot, int type, uint32_t out[3]);
 
 /* Asynchronous SEI-MD5 of the picture in `slot` as it is after everything submitted so far.  The engine hashes a private
- * copy on a side stream; at most 8 jobs may be outstanding (HMR_ERR_BUSY: collect results first).
+ * copy on a side stream; at most HMR_MD5_MAX_JOBS jobs may be outstanding (HMR_ERR_BUSY: collect results first).  A 2160p picture's
+ * chain takes ~0.13 s whatever the load, and a parser delivers a group of B pictures in less than that: the ring has to hold a burst.
  * hmr_md5_result: out = 3 x 16 digest bytes (Y, Cb, Cr); wait = 0 polls (HMR_PENDING while running). */
 int  hmr_md5_submit(hmr_engine* e, int slot, uint64_t* job);
 int  hmr_md5_result(hmr_engine* e, uint64_t job, uint8_t out[48], int wait);

@@ -15,7 +15,7 @@
 
 #define RING 3
 #define MARKERS 64
-#define MD5_RING 8
+#define MD5_RING HMR_MD5_MAX_JOBS
 #define ALIGN_UP(v, a) (((v) + (a) - 1) / (a) * (a))
 
 struct Section { size_t off, bytes; };

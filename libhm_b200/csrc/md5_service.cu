@@ -44,7 +44,7 @@ void worker(Service* sv)
   cudaStream_t stream = nullptr;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);                   // lo = lowest priority
-  const int MAXJ = 512;
+  const int MAXJ = 1024;                                        // jobs one tick advances (32 decoder threads x HMR_MD5_MAX_JOBS fit; more wait in `pending`)
   Md5TickJob* table[2] = { nullptr, nullptr };
   cudaEvent_t ev[2];
   bool evMade[2] = { false, false };
