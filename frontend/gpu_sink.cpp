@@ -94,6 +94,7 @@ public:
     // libHMDEC_get_image_plane finds it there; pictures nobody will look at never leave the device.
     if (!m_verify && m_eager && pic->getSlice(0)->getPicOutputFlag())
     {
+      HmWaitScope wsDma(HMW_DMA_ISSUE);
       TComPicYuv* rec = pic->getPicYuvRec();
       bool ok = true;
       for (int c = 0; c < (int)rec->getNumberValidComponents() && ok; c++)      // 4:0:0: the luma plane only
@@ -163,7 +164,7 @@ public:
     Pending p;
     p.isJob = true; p.quiet = quiet; p.ncomp = ncomp; p.line = line;
     p.expected.assign(expected, expected + 16 * ncomp);
-    if (hmr_md5_submit(m_eng, it->second.slot, &p.job) != HMR_OK) return false;
+    { HmWaitScope ws(HMW_HASH_SUBMIT); if (hmr_md5_submit(m_eng, it->second.slot, &p.job) != HMR_OK) return false; }
     m_pending.push_back(p);
     m_jobs++;
     return true;

@@ -31,14 +31,14 @@ HmWaitStats& hm_wait_stats()
 {
   static HmWaitStats s;
   static const bool init = [] {
-    for (int i = 0; i < HMW_COUNT; i++) { s.ns[i] = 0; s.calls[i] = 0; }
+    for (int i = 0; i < HMW_COUNT; i++) { s.ns[i] = 0; s.cpuNs[i] = 0; s.calls[i] = 0; }
     s.on = getenv("HMDEC_B200_STATS") != NULL;
     s.decoders = 0;
     s.skip = s.on ? atoi(getenv("HMDEC_B200_STATS")) : 0;
     if (s.on) atexit([] {
-      static const char* name[HMW_COUNT] = { "new_decoder", "free_decoder", "sink submit (validate + pack + enqueue)", "wait for a picture's planes", "wait for hash verdicts", "geometry gate", "hash ring full (inside push)", "push_nal_unit (total)" };
+      static const char* name[HMW_COUNT] = { "new_decoder", "free_decoder", "sink submit (validate + pack + enqueue)", "wait for a picture's planes", "wait for hash verdicts", "geometry gate", "hash ring full (inside push)", "issue of the output DMA", "hash job submit", "picture completion (executeLoopFilters)", "push_nal_unit (total)" };
       fprintf(stderr, "hmdec_b200 wait stats (wall clock, all threads; decoders %d.. of %d):\n", s.skip + 1, s.decoders.load());
-      for (int i = 0; i < HMW_COUNT; i++) fprintf(stderr, "  %-42s %9.3f s in %8lld calls\n", name[i], 1e-9 * (double)s.ns[i].load(), s.calls[i].load());
+      for (int i = 0; i < HMW_COUNT; i++) fprintf(stderr, "  %-42s %9.3f s wall, %9.3f s on a CPU, %8lld calls\n", name[i], 1e-9 * (double)s.ns[i].load(), 1e-9 * (double)s.cpuNs[i].load(), s.calls[i].load());
     });
     return true; }();
   (void)init;

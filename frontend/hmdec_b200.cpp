@@ -320,7 +320,7 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
     {
       int poc;
       g_md5_mismatch = d->hashMismatch;
-      d->top.executeLoopFilters(poc, d->dpb);          // -> TDecGop::filterPicture hook -> engine
+      { HmWaitScope ws(HMW_PICTURE_DONE); d->top.executeLoopFilters(poc, d->dpb); }          // -> TDecGop::filterPicture hook -> engine
       d->hashMismatch = g_md5_mismatch;
       d->claimPictures();
     }
