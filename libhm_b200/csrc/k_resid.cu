@@ -19,6 +19,10 @@
 
 // 32-bit entries: an IMAD then takes the matrix element straight from the constant bank (c[bank][imm]); with int16 entries
 // every MAC paid a uniform load plus a sign-extending permute on top (3 instructions per MAC, 190 KB of code)
+#define RS_PARTS(lg) ((lg) == 5 ? 4 : ((lg) == 4 ? 2 : 1))   // threads per column of a TU (see resid_block)
+#ifndef RS_COMPACT_FROM
+#define RS_COMPACT_FROM 4            // log2 transform size from which stage 1 runs as a loop (6 = never)
+#endif
 __constant__ int c_T32[32][32];
 static const int16_t h_cosTab[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
                                       61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
@@ -46,10 +50,13 @@ static void upload_tables(int device)
 template <int LOG2N>
 __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all, const uint32_t first, const uint32_t count, const uint32_t block, const int phase)
 {
-  constexpr int N = 1 << LOG2N, NN = N * N, LD = N + 2, PER_BLOCK = RS_THREADS / N, STEP = 32 / N;
+  // PARTS threads share a column (stage 1) / row (stage 2) of a large TU, KP of its N outputs each: a 32x32 TU is four warps' work, not
+  // one warp's (a lone 32x32 TU in a B picture was a 20-30 us serial tail of the launch), and nobody holds more than 16 accumulators
+  constexpr int N = 1 << LOG2N, NN = N * N, LD = N + 2, PARTS = RS_PARTS(LOG2N), KP = N / PARTS, PER_BLOCK = RS_THREADS / (N * PARTS), STEP = 32 / N;
   int16_t (*s_buf)[N * LD] = (int16_t (*)[N * LD])s_all;
-  const int g = threadIdx.x / N;          // TU slot inside the CTA
-  const int j = threadIdx.x % N;          // my column (stage 1) / row (stage 2) / column again (store)
+  const int g = threadIdx.x / (N * PARTS);   // TU slot inside the CTA
+  const int j = threadIdx.x % N;             // my column (stage 1) / row (stage 2) / column again (store)
+  const int k0 = ((threadIdx.x / N) % PARTS) * KP;   // my outputs k0 .. k0 + KP - 1 (stage 1 / 2), my rows in the column-wise passes
   const uint32_t idx = block * PER_BLOCK + g;
   bool active = idx < count;
   hmr_tu t;
@@ -65,7 +72,7 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
   const bool coded = active && (t.flags & HMR_TU_CODED);
   const bool plainTransform = coded && !(t.flags & (HMR_TU_BYPASS | HMR_TU_TSKIP));
 
-  int acc[N];
+  int acc[KP];
   // ---------------- stage 1 (or the non-transform paths, written straight into residual layout [y][x]) ----------------
   if (plainTransform)
   {
@@ -77,7 +84,46 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
     const int inMin = -(1 << (inBits - 1)), inMax = (1 << (inBits - 1)) - 1;
     const bool dst = (LOG2N == 2) && (t.flags & HMR_TU_DST);
 #pragma unroll
-    for (int k = 0; k < N; k++) acc[k] = 0;
+    for (int k = 0; k < KP; k++) acc[k] = 0;
+    if (LOG2N >= RS_COMPACT_FROM)
+    {
+      // 16- and 32-point transforms: the row loop is a LOOP over chunks of 4 rows (matrix rows through a register-indexed constant load),
+      // not N x N multiply-adds of straight-line code — 16 KB for the 32-point stage alone, which every SM had to fetch cold: a B picture
+      // with a single 32x32 TU spent 30 of its 38 us there, and the I picture's launch (IPC 1.7) was short of instructions, not of ALUs.
+      // The levels of the next chunk are in flight while this one is multiplied.
+      constexpr int CH = 4;
+      int qa[CH], qb[CH];
+#pragma unroll
+      for (int i = 0; i < CH; i++) { qa[i] = __ldg(lev + i * N + j); qb[i] = 0; }
+#pragma unroll 1
+      for (int n0 = 0; n0 < N; n0 += CH)
+      {
+        if (n0 + CH < N)
+        {
+#pragma unroll
+          for (int i = 0; i < CH; i++) qb[i] = __ldg(lev + (n0 + CH + i) * N + j);
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++)
+        {
+          const int q = qa[i], n = n0 + i;
+          if (q != 0)
+          {
+            const int qc = clip3i(inMin, inMax, q);
+            const int sc = sl ? scale * (int)__ldg(sl + n * N + j) : scale;
+            int c = rshift > 0 ? (qc * sc + (1 << (rshift - 1))) >> rshift : (int)((unsigned)(qc * sc) << (-rshift));
+            c = clip3i(-32768, 32767, c);
+            const int* __restrict__ row = c_T32[n * STEP] + k0;
+#pragma unroll
+            for (int k = 0; k < KP; k++) acc[k] += row[k] * c;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++) qa[i] = qb[i];
+      }
+    }
+    else
+    {
     int lv[N];
 #pragma unroll
     for (int n = 0; n < N; n++) lv[n] = __ldg(lev + n * N + j);
@@ -97,24 +143,25 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
         acc[k] += m * c;
       }
     }
+    }
     // tmp[j][k] = clip16((acc + 64) >> 7)
 #pragma unroll
-    for (int k = 0; k < N; k++) sb[j * LD + k] = (int16_t)clip3i(-32768, 32767, (acc[k] + 64) >> 7);
+    for (int k = 0; k < KP; k++) sb[j * LD + k0 + k] = (int16_t)clip3i(-32768, 32767, (acc[k] + 64) >> 7);
   }
   __syncthreads();
   if (plainTransform)
   {
     const bool dst = (LOG2N == 2) && (t.flags & HMR_TU_DST);
 #pragma unroll
-    for (int k = 0; k < N; k++) acc[k] = 0;
+    for (int k = 0; k < KP; k++) acc[k] = 0;
     for (int n = 0; n < N; n++)
     {
       const int c = sb[n * LD + j];          // tmp[n][y = j]
       if (c == 0) continue;
 #pragma unroll
-      for (int k = 0; k < N; k++)
+      for (int k = 0; k < KP; k++)
       {
-        const int m = (LOG2N == 2 && dst) ? c_dst4[n][k] : c_T32[n * STEP][k];
+        const int m = (LOG2N == 2 && dst) ? c_dst4[n][k] : c_T32[n * STEP][k0 + k];
         acc[k] += m * c;
       }
     }
@@ -124,15 +171,15 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
   {
     const int shift2 = 20 - bd, rnd2 = 1 << (shift2 - 1);
 #pragma unroll
-    for (int k = 0; k < N; k++) sb[j * LD + k] = (int16_t)clip3i(-32768, 32767, (acc[k] + rnd2) >> shift2);   // row y = j
+    for (int k = 0; k < KP; k++) sb[j * LD + k0 + k] = (int16_t)clip3i(-32768, 32767, (acc[k] + rnd2) >> shift2);   // row y = j
   }
   else if (active)
   {
     // thread j fills column j of resi[y][x]
-    if (!coded) { for (int y = 0; y < N; y++) sb[y * LD + j] = 0; }
+    if (!coded) { for (int y = k0; y < k0 + KP; y++) sb[y * LD + j] = 0; }
     else if (t.flags & HMR_TU_BYPASS)
     {
-      for (int y = 0; y < N; y++)
+      for (int y = k0; y < k0 + KP; y++)
       {
         const int i = y * N + j;
         sb[y * LD + j] = lev[(t.flags & HMR_TU_ROTATE) ? NN - 1 - i : i];
@@ -147,7 +194,7 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
       const int rshift = 6 - (trShift + per) + (sl ? 4 : 0);
       const int inBits = min(16, 32 + rshift - (sl ? 15 : 7));
       const int inMin = -(1 << (inBits - 1)), inMax = (1 << (inBits - 1)) - 1;
-      for (int y = 0; y < N; y++)
+      for (int y = k0; y < k0 + KP; y++)
       {
         const int i = y * N + j;
         const int src = (t.flags & HMR_TU_ROTATE) ? NN - 1 - i : i;
@@ -162,9 +209,9 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
   }
   __syncthreads();
   // ---------------- RDPCM: running sums down columns / along rows, Pel (int16) wrap-around ----------------
-  if (active && (t.flags & HMR_TU_RDPCM_V))
+  if (active && k0 == 0 && (t.flags & HMR_TU_RDPCM_V))        // (serial along the column / row: the first of the PARTS threads)
     for (int y = 1; y < N; y++) sb[y * LD + j] = (int16_t)(sb[y * LD + j] + sb[(y - 1) * LD + j]);
-  if (active && (t.flags & HMR_TU_RDPCM_H))
+  if (active && k0 == 0 && (t.flags & HMR_TU_RDPCM_H))
     for (int x = 1; x < N; x++) sb[j * LD + x] = (int16_t)(sb[j * LD + x] + sb[j * LD + x - 1]);
   __syncthreads();
   if (!active) return;
@@ -179,9 +226,9 @@ __device__ __forceinline__ void resid_block(const FrameParams& P, int16_t* s_all
   int16_t* d0 = plane + (size_t)t.y * pitch + t.x + j;
   // loads of a batch of rows first (prediction samples, luma residuals for CCP): independent loads in flight instead of
   // one load -> store round trip per row
-  constexpr int BATCH = N < 8 ? N : 8;
+  constexpr int BATCH = KP < 8 ? KP : 8;
 #pragma unroll 1
-  for (int y0 = 0; y0 < N; y0 += BATCH)
+  for (int y0 = k0; y0 < k0 + KP; y0 += BATCH)
   {
     int cur[BATCH], lum[BATCH];
 #pragma unroll
@@ -229,7 +276,7 @@ int launch_resid(const FrameParams& P, cudaStream_t s)
   {
     G.first[k] = P.hdr.tu_first[k];
     G.count[k] = P.hdr.tu_first[k + 1] - P.hdr.tu_first[k];
-    const uint32_t perBlock = RS_THREADS >> (k + 2);
+    const uint32_t perBlock = RS_THREADS / ((4u << k) * RS_PARTS(k + 2));
     blocks += (G.count[k] + perBlock - 1) / perBlock;
     G.blockEnd[k] = blocks;
   }
