@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <string>
 #include <vector>
+#include <memory>
+#include <new>
 #include <map>
 #include "hmr_records.h"
 
@@ -56,6 +58,17 @@ struct HmFrameSink
 
 #include "hm_fast.h"
 
+// std::allocator whose construct() default-initialises: resize() of a vector of a trivial type then leaves the new tail untouched
+// instead of zeroing it (the level arena grows by a whole TU at a time and is overwritten at once: 24 MB per 2160p I picture).
+template <class T> struct HmDefaultInit : std::allocator<T>
+{
+  template <class U> struct rebind { typedef HmDefaultInit<U> other; };
+  HmDefaultInit() {}
+  template <class U> HmDefaultInit(const HmDefaultInit<U>&) {}
+  template <class U> void construct(U* p) { ::new ((void*)p) U; }
+  template <class U, class A1> void construct(U* p, const A1& a1) { ::new ((void*)p) U(a1); }
+};
+
 class HmEmitter
 {
 public:
@@ -101,7 +114,7 @@ private:
 
   hmr_frame_hdr                    m_hdr;
   std::vector<hmr_tu>              m_tu;
-  std::vector<int16_t>             m_coef;
+  std::vector<int16_t, HmDefaultInit<int16_t> > m_coef;   // grown by resize() WITHOUT the value-initialising fill: every entry is written right after
   std::vector<hmr_intra>           m_intra;
   std::vector<hmr_intra>           m_intraTmp[3];
   std::vector<hmr_ctu_intra_range> m_range;
