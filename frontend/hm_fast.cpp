@@ -113,34 +113,6 @@ static void releasePlanes(TComPicYuv* yuv)
   }
 }
 
-// ---- lazy motion compression ---------------------------------------------------------------------------------
-// TComPic::compressMotion (16x16 motion storage for TMVP) is pure overhead for a picture that is never a reference:
-// nothing will ever read its motion field again — except libHMDEC_get_internal_info, which then compresses on demand
-// so that the API reports exactly what the reference reports.
-static std::mutex g_motionLock;
-static std::set<TComPic*> g_motionPending;
-
-void hm_fast_defer_motion_compression(TComPic* pic)
-{
-  std::lock_guard<std::mutex> g(g_motionLock);
-  g_motionPending.insert(pic);
-}
-
-void hm_fast_ensure_motion_compressed(TComPic* pic)
-{
-  {
-    std::lock_guard<std::mutex> g(g_motionLock);
-    if (!g_motionPending.erase(pic)) return;
-  }
-  pic->compressMotion();
-}
-
-static void forgetMotion(TComPic* pic)
-{
-  std::lock_guard<std::mutex> g(g_motionLock);
-  g_motionPending.erase(pic);
-}
-
 // ---- process-wide pool of complete picture buffers ------------------------------------------------------------
 // A TComPic of a 2160p stream is ~70 000 allocations (2040 CTUs x ~35 arrays).  A decoder that ends parks its pictures here
 // (planes attached) and the next decoder of the same geometry adopts them: opening a new bitstream costs no allocation.
@@ -244,7 +216,6 @@ static TComPic* findOrphan(TDecTop* dec, TComList<TComPic*>& list, TComSPS* sps)
   for (size_t i = 0; i < stale.size(); i++)
   {
     TComPic* pic = stale[i];
-    forgetMotion(pic);
     hm_emit_release_slot(pic);
     if (pic->getPicYuvRec()) releasePlanes(pic->getPicYuvRec());
     pic->destroy();
@@ -266,7 +237,6 @@ void hm_fast_release_decoder(TDecTop* dec)
   for (size_t i = 0; i < mine.size(); i++)
   {
     TComPic* pic = mine[i];
-    forgetMotion(pic);
     if (poolEnabled() && pic->m_apcPicSym && pic->getPicYuvRec())
     {
       // park the complete buffer (planes stay attached); HM's teardown must not see it any more
@@ -306,7 +276,6 @@ static bool sameGeometry(TComPic* pic, TComSPS* sps)
 static void resetPicture(TComPic* pic, Window& conf, Window& disp, Int* reorder)
 {
   TComPicSym* sym = pic->m_apcPicSym;
-  forgetMotion(pic);
   sym->clearSliceBuffer();
   delete sym->getSlice(0);
   sym->setSlice(new TComSlice, 0);

@@ -13,9 +13,6 @@ void hm_fast_set_plane_allocator(HmPlaneAlloc a, HmPlaneFree f);
 bool hm_fast_plane_is_pinned(const void* planeBuffer);
 // Must run before TDecTop::destroy: hands allocator-owned planes back and frees picture buffers a flush dropped from the DPB list.
 void hm_fast_release_decoder(TDecTop* dec);
-// Motion-field compression of a picture nobody will reference, postponed until somebody asks for its motion data.
-void hm_fast_defer_motion_compression(TComPic* pic);
-void hm_fast_ensure_motion_compressed(TComPic* pic);
 // warm the per-partition arrays of a CTU ahead of TComDataCU::initCU, a few cache lines at a time (hm_fast.cpp)
 struct HmPrefetchCursor
 {

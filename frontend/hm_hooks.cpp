@@ -146,9 +146,8 @@ Void TDecGop::filterPicture(TComPic*& rpcPic)
   }
 #endif
 
-  // TMVP storage (TDecGop.cpp:176): never rewritten — xGetColMVP reads the uncompressed field at the 16x16 run start
-  // (hm_fast_memset.h: hm_fast_col_part); only libHMDEC_get_internal_info compresses, on demand
-  hm_fast_defer_motion_compression(rpcPic);
+  // TMVP storage (TDecGop.cpp:176, TComPic::compressMotion): never rewritten — xGetColMVP and libHMDEC_get_internal_info read
+  // the uncompressed field at the 16x16 run start (hm_fast_memset.h: hm_fast_col_part; internals.cpp)
   static const bool quiet = getenv("HMDEC_B200_QUIET") != NULL;   // the hash is still verified
   printStatusAndHash(rpcPic, slice, m_decodedPictureHashSEIEnabled, e, quiet);
   e->sink()->drainHashes(false);

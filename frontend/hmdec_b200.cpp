@@ -43,7 +43,12 @@ thread_local bool g_md5_mismatch = false;
 HmFrameSink* hm_new_dump_sink(const char* path);
 HmFrameSink* hm_new_null_sink();
 HmFrameSink* hm_new_gpu_sink();           // gpu_sink.cpp
-std::vector<libHMDec_BlockValue>* hm_collect_internals(std::vector<libHMDec_BlockValue>& out, TComPic* pic, libHMDec_info_type type); // internals.cpp
+// internals.cpp: flat block index of one picture, built by the first query and kept until the next push
+struct HmInternalsCache;
+HmInternalsCache* hm_internals_cache_new();
+void hm_internals_cache_free(HmInternalsCache* c);
+void hm_internals_cache_invalidate(HmInternalsCache* c);
+std::vector<libHMDec_BlockValue>* hm_collect_internals(HmInternalsCache* cache, std::vector<libHMDec_BlockValue>& out, TComPic* pic, libHMDec_info_type type);
 
 namespace {
 
@@ -75,11 +80,12 @@ struct Decoder
   HmGeomKey geom;            // SPS-dependent HM globals this decoder runs under (hm_threadsafe.cpp); invalid before the first activation
   bool  statsActive;         // HMDEC_B200_STATS counts this decoder (hm_waitstats.h)
   std::vector<libHMDec_BlockValue> internals;
+  HmInternalsCache* internalsIndex;
 
   Decoder(HmFrameSink* s)
     : sink(s), emitter(new HmEmitter(s)), maxTemporalLayer(-1), lastDisplayedPoc(-MAX_INT), skipFrames(0), dpb(NULL),
       cursor(0), pendingOutput(0), dpbFullness(0), reorderLimit(0), bufferingLimit(0), loopFilterDone(false),
-      flushing(false), flushAfterThisPass(false), hashMismatch(false), failed(false), prevTid0POC(0)
+      flushing(false), flushAfterThisPass(false), hashMismatch(false), failed(false), prevTid0POC(0), internalsIndex(hm_internals_cache_new())
   {
     top.create();
     top.init();
@@ -102,6 +108,7 @@ struct Decoder
     if (geom.valid) hm_geom_leave(geom);
     delete emitter;
     delete sink;
+    hm_internals_cache_free(internalsIndex);
   }
 
   void claimPictures()
@@ -272,6 +279,7 @@ libHMDec_error libHMDec_push_nal_unit(libHMDec_context* decCtx, const void* data
   HmWaitScope wsTotal(HMW_PUSH_TOTAL);
   if (length <= 0) return LIBHMDEC_ERROR_READ_ERROR;
   if (length < 4 && !eof) return LIBHMDEC_ERROR_READ_ERROR;
+  hm_internals_cache_invalidate(d->internalsIndex);      // picture buffers only change inside a push
 
   // tolerate a leading Annex-B start code (00 00 01 / 00 00 00 01); the payload starts at the 2-byte NAL header.
   // (The reference tests bytes 0,1,1 for the 3-byte form, libHMDecoder.cpp:128, which never matches a real start code.)
@@ -458,7 +466,7 @@ std::vector<libHMDec_BlockValue>* libHMDEC_get_internal_info(libHMDec_context* d
   d->internals.clear();
   if (!pic) return NULL;
   GeomScope gate(d, d->geom, d->geom.valid);           // the walk indexes the z-scan tables of this decoder's CTU geometry
-  return hm_collect_internals(d->internals, (TComPic*)pic, type);
+  return hm_collect_internals(d->internalsIndex, d->internals, (TComPic*)pic, type);
 }
 
 libHMDec_error libHMDEC_clear_internal_info(libHMDec_context* decCtx)

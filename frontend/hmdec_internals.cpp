@@ -66,7 +66,8 @@ int main(int argc, char** argv)
         {
           const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
           std::vector<libHMDec_BlockValue>* v = p_libHMDEC_get_internal_info(dec, pic, (libHMDec_info_type)type);
-          { const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); secInfo += dt; secType[type] += dt; }
+          { const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); secInfo += dt; secType[type] += dt;
+            if (timeOnly && type == 0 && getenv("HMDEC_INTERNALS_TIME")[0] == '2') printf("picture %ld: first query %.3f ms\n", pictures, 1e3 * dt); }
           if (v) blocks += (long)v->size();
           fprintf(out, " type %d n %ld\n", type, v ? (long)v->size() : -1L);
           if (v && !timeOnly) for (size_t i = 0; i < v->size(); i++)
