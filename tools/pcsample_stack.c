@@ -1,4 +1,4 @@
-// Like pcsample.c, but keeps the top 96 stack words of every sample so that the resolver can find the first return address
+// Like pcsample.c, but keeps the top 192 stack words of every sample so that the resolver can find the first return address
 // outside libc (who called malloc / free / memset when the PC is inside a static libc routine).  1 kHz SIGPROF, <= 64 K samples.
 #define _GNU_SOURCE
 #include <signal.h>
@@ -8,7 +8,7 @@
 #include <sys/time.h>
 #include <ucontext.h>
 #define MAXS (1<<16)
-#define NW 96
+#define NW 192
 static unsigned long *pcs, *stk; static volatile long n;
 static void h(int sig, siginfo_t* si, void* uc_) { ucontext_t* uc = (ucontext_t*)uc_; long i = __sync_fetch_and_add(&n, 1); if (i < MAXS) { pcs[i] = uc->uc_mcontext.gregs[REG_RIP]; memcpy(stk + i * NW, (void*)uc->uc_mcontext.gregs[REG_RSP], NW * 8); } }
 __attribute__((constructor)) static void init(void) {

@@ -1,5 +1,5 @@
-# Resolver for pcsample_stack.c: for every sample whose PC is inside libc, the first two stack words that point into another
-# text mapping name the callers.  usage: python tools/pcsample_stack_resolve.py /tmp/pcsample_stack.txt [rows]
+# Resolver for pcsample_stack.c: for every sample whose PC is inside libc or libcuda, the first two stack words that point into
+# one of OUR text mappings (not libc / libcuda / libstdc++) name the callers.  usage: python tools/pcsample_stack_resolve.py /tmp/pcsample_stack.txt [rows]
 import sys,subprocess,bisect,collections
 maps=[];S=[]
 for l in open(sys.argv[1]):
@@ -24,11 +24,11 @@ def sym_of(pc):
 tot=len(S); c1=collections.Counter(); nl=0
 for pc,st in S:
     m,n=sym_of(pc)
-    if not m or 'libc.so' not in m: continue
+    if not m or ('libc.so' not in m and 'libcuda' not in m): continue
     nl+=1; chain=[]
     for w in st:
         cm,cn=sym_of(w)
-        if cm and 'libc.so' not in cm and 'pcsample' not in cm:
+        if cm and 'libc.so' not in cm and 'pcs' not in cm and 'libcuda' not in cm and 'libpthread' not in cm and 'libstdc++' not in cm:
             if not chain or chain[-1]!=cn[:70]: chain.append(cn[:70])
             if len(chain)==2: break
     c1[(n[:28],' <- '.join(chain))]+=1
