@@ -107,3 +107,54 @@ def test_push_repush_drain_loop_delivers_all_pictures_in_output_order(lib, name,
     assert lib.libHMDec_free_decoder(dec) == OK
     assert len(pocs) == expected and pocs == sorted(pocs) and len(set(pocs)) == expected
     assert repushed >= expected - 1
+
+
+def _blocks(lib, dec, pic, t):
+    """libHMDEC_get_internal_info returns a std::vector<libHMDec_BlockValue>* (libHMDecoder.h:291): begin / end pointers, 16-byte entries."""
+    lib.libHMDEC_get_internal_info.restype = C.c_void_p
+    lib.libHMDEC_get_internal_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    v = lib.libHMDEC_get_internal_info(dec, pic, t)
+    assert v
+    begin, end = (C.c_void_p * 2).from_address(v)
+    n = ((end or 0) - (begin or 0))
+    assert n % 16 == 0
+    return C.string_at(begin, n) if n else b""
+
+
+def test_internal_info_index_is_order_independent_and_per_picture(lib):
+    """The block lists come from a per-picture index built by the first query (frontend/internals.cpp): whatever the order
+    of the queries, with libHMDEC_clear_internal_info in between, and with queries for two pictures interleaved, every
+    (picture, type) pair must answer the same bytes; the index must not survive into the next push."""
+    nals = _nals(os.path.join(GOLDEN, "s_ra8_240p.bin"))
+    dec = lib.libHMDecB200_new_decoder_ex(1, b"null")
+    lib.libHMDec_set_SEI_Check(dec, False)
+    order = [21, 3, 12, 0, 15, 22, 8, 1, 11, 14, 23, 5, 18, 7, 10, 2, 9, 16, 4, 13, 17, 6, 19, 20]
+    k, seen, interleaved = 0, 0, 0
+    while k < len(nals):
+        new, chk = C.c_bool(False), C.c_bool(False)
+        buf = (C.c_ubyte * len(nals[k])).from_buffer_copy(nals[k])
+        assert lib.libHMDec_push_nal_unit(dec, buf, len(nals[k]), k + 1 == len(nals), C.byref(new), C.byref(chk)) == OK
+        if chk.value:
+            pics = []
+            while True:
+                pic = lib.libHMDec_get_picture(dec)
+                if not pic:
+                    break
+                pics.append(pic)
+            first = {}
+            for p in pics:                                 # ascending types, one picture after the other
+                for t in range(24):
+                    first[(p, t)] = _blocks(lib, dec, p, t)
+            assert lib.libHMDEC_clear_internal_info(dec) == OK
+            for t in order:                                # scrambled types, pictures interleaved (the index is rebuilt on every switch)
+                for p in reversed(pics):
+                    assert _blocks(lib, dec, p, t) == first[(p, t)], (lib.libHMDEC_get_POC(p), t)
+            seen += len(pics)
+            interleaved += len(pics) > 1
+            if pics:
+                assert len(first[(pics[0], 0)]) // 16 == 28       # one entry per CTU: 7 x 4 CTUs of 64x64 at 416x240
+                assert len(first[(pics[0], 9)]) == 0              # QUIRK: PU_MERGE_INDEX reports nothing (libHMDecoder.cpp:663)
+        if not new.value:
+            k += 1
+    assert lib.libHMDec_free_decoder(dec) == OK
+    assert seen == 17 and interleaved >= 1
