@@ -355,7 +355,11 @@ def main():
         if world > 1:
             cmd = ["taskset", "-c", f"{my_cores[0]}-{my_cores[0] + cores_rank - 1}"] + cmd
         res, good = None, False
-        if bins:
+        for attempt in range(2 if world == 1 else 1):            # one more try on a single rank (no common start time to renegotiate)
+            if not bins or good:
+                break
+            if attempt:
+                cmd[cmd.index("--start-at") + 1] = f"{time.time() + 12.0 + 0.4 * thr:.3f}"
             pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
             try:
                 res = json.loads(pr.stdout.strip().splitlines()[-1])
@@ -363,7 +367,7 @@ def main():
             except Exception:
                 res, good = None, False
             if not good:
-                sys.stderr.write(f"bench: hmdec_mt failed (rc {pr.returncode}): {' '.join(cmd)}\n{pr.stdout[-500:]}\n{pr.stderr[-1500:]}\n")
+                sys.stderr.write(f"bench: hmdec_mt failed (rc {pr.returncode}, attempt {attempt + 1}): {' '.join(cmd)}\n{pr.stdout[-500:]}\n{pr.stderr[-1500:]}\n")
         tt = torch.tensor([-res["t_start"] if good else 0.0, res["t_end"] if good else 1e30, float(res["pictures"]) if good else 0.0], device="cuda", dtype=torch.float64)
         if world > 1:
             both = tt[:2].clone()

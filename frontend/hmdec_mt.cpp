@@ -166,5 +166,6 @@ int main(int argc, char** argv)
          "\"cpu_user_s\": %.3f, \"cpu_sys_s\": %.3f, \"minor_faults\": %ld, \"ctx_switches_invol\": %ld}\n",
          threads, repeat, sh.pictures.load(), sec, sh.pictures.load() / sec, hash ? "true" : "false", !planes ? "untouched" : (sumPlanes ? "every sample read" : "first sample read"), sh.planeSum.load(), (int)streams.size(), sh.failures.load(), syncVerdict ? "sync" : "overlapped", wallStart, wallStart + sec,
          user, sys, (long)(ru1.ru_minflt - ru0.ru_minflt), (long)(ru1.ru_nivcsw - ru0.ru_nivcsw));
+  fflush(stdout);
   return sh.failures.load() ? 1 : 0;
 }

@@ -163,6 +163,30 @@ static void pool_free_host(void* p, size_t bytes)
   cudaFreeHost(p);
 }
 
+// CUDA streams are pooled the same way: creating one is a handful of ioctls that take ~20 ms when 16 decoder threads open new
+// bitstreams against one context (tools/ioctl_trace.c, profiles/r04b_ioctl_trace.log: 3-5 % of a decoder thread at one new engine
+// per 33-picture bitstream).  A stream goes back to the pool only after cudaStreamSynchronize, i.e. empty.
+static std::vector<cudaStream_t> g_streamPool[16];
+static cudaError_t pool_stream(int device, cudaStream_t* s)
+{
+  {
+    std::lock_guard<std::mutex> g(g_poolLock);
+    if (device >= 0 && device < 16 && !g_streamPool[device].empty()) { *s = g_streamPool[device].back(); g_streamPool[device].pop_back(); return cudaSuccess; }
+  }
+  return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+}
+static void pool_stream_release(int device, cudaStream_t s)
+{
+  if (!s) return;
+  static const bool pooled = getenv("HMR_NO_STREAM_POOL") == NULL;          // A/B switch
+  if (pooled && cudaStreamSynchronize(s) == cudaSuccess && device >= 0 && device < 16)
+  {
+    std::lock_guard<std::mutex> g(g_poolLock);
+    if (g_streamPool[device].size() < 256) { g_streamPool[device].push_back(s); return; }
+  }
+  cudaStreamDestroy(s);
+}
+
 static int fail(hmr_engine* e, int code, const std::string& msg) { if (e) e->err = msg; return code; }
 #define CK(call) do { cudaError_t _r = (call); if (_r != cudaSuccess) return fail(e, HMR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); } while (0)
 
@@ -507,7 +531,7 @@ int hmr_engine_create(hmr_engine** out, int device)
   e->planeSetBytes = 0; e->markerInit = false; e->markerNext = 0; e->auxInit = false; e->md5Next = 0;
   for (int i = 0; i < MD5_RING; i++) { e->md5[i].alloc = false; e->md5[i].busy = false; e->md5[i].dState = nullptr; e->md5[i].hOut = nullptr; e->md5[i].job = 0; e->md5[i].done.store(0); }
   e->dHash = nullptr; e->dHashRows = nullptr; e->hashRowsCap = 0; e->flushBuf = nullptr; e->flushCap = 0;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+  if (cudaSetDevice(device) != cudaSuccess || pool_stream(device, &e->stream) != cudaSuccess)
   {
     fprintf(stderr, "hmrecon: cannot initialise device %d: %s\n", device, cudaGetErrorString(cudaGetLastError()));
     delete e;
@@ -555,7 +579,7 @@ void hmr_engine_destroy(hmr_engine* e)
   }
   fold_timing(e);
   for (size_t i = 0; i < e->freeEvents.size(); i++) for (int k = 0; k <= HMR_T_COUNT; k++) cudaEventDestroy(e->freeEvents[i].ev[k]);
-  cudaStreamDestroy(e->stream);
+  pool_stream_release(e->device, e->stream);
   delete e;
 }
 

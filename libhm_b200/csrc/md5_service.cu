@@ -78,8 +78,11 @@ void worker(Service* sv)
       }
       if (active.empty() && sv->pending.empty() && finishing[0].empty() && finishing[1].empty())
       {
-        // idle: linger a little, then let the thread end (a later submit starts a new one)
-        if (!sv->cv.wait_for(lk, std::chrono::milliseconds(200), [&] { return !sv->pending.empty(); })) { sv->running = false; break; }
+        // idle: sleep until the next submit.  The worker never ends on its own: a worker that tore down its stream, events and
+        // page-locked tables 200 ms after the last digest could do so while the process was already running its exit handlers
+        // (the CUDA runtime's among them) — a crash at exit that also swallowed the still-buffered stdout of the harness.
+        // A detached thread parked on a condition variable is harmless at exit (g_svc is never destroyed).
+        sv->cv.wait(lk, [&] { return !sv->pending.empty(); });
       }
       while (!sv->pending.empty() && (int)active.size() < MAXJ)
       {
@@ -113,15 +116,6 @@ void worker(Service* sv)
     }
     t++;
   }
-  // drain the last tick before leaving
-  if (t > 0)
-  {
-    const int prev = (int)((t - 1) & 1);
-    const bool fine = cudaEventSynchronize(ev[prev]) == cudaSuccess;
-    for (int k = 0; k < 2; k++) { for (size_t i = 0; i < finishing[k].size(); i++) finishing[k][i]->store(fine ? 1 : -1); finishing[k].clear(); }
-  }
-  for (int i = 0; i < 2; i++) { if (table[i]) cudaFreeHost(table[i]); cudaEventDestroy(ev[i]); }
-  cudaStreamDestroy(stream);
 }
 
 } // namespace
