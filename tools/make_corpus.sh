@@ -59,6 +59,7 @@ JOBS=(
  "s_gray400_240p     encoder_randomaccess_main_rext.cfg    416  240  5  8  400 44 --InternalBitDepth=8 -q 30"
  "s_cksum_240p       encoder_randomaccess_main10.cfg       416  240  9  10 420 42 --SEIDecodedPictureHash=3 -q 30"
  "s_mintu8_240p      encoder_intra_main.cfg                416  240  2  8  420 45 --QuadtreeTULog2MinSize=3 --MaxPartitionDepth=3 -q 32"
+ "s_cra_240p         encoder_randomaccess_main.cfg         416  240  25 8  420 46 --IntraPeriod=8 -q 30"
 )
 WANT=$1
 # s_switch_240p: five coded video sequences back to back, every one starting with an IDR and four of the five activating an SPS of
@@ -71,6 +72,33 @@ if [ "$WANT" == "s_switch_240p" ]; then
   grep -o 'POC.*' "$out.dec.log" | sed -E 's/\[DT +[0-9.]+\] //' > "$out.md5"
   md5sum < "$TMP_YUV/s_switch.dec.yuv" | awk '{print $1}' > "$out.yuvmd5"
   echo "s_switch_240p: done ($(stat -c %s "$out.bin") bytes, $(grep -c OK "$out.md5") pictures OK)"
+  exit 0
+fi
+# s_seek_240p: a caller that seeks — the parameter sets of s_cra_240p followed by everything from its SECOND CRA picture on (open GOP:
+# the CRA's leading RASL pictures reference pictures that were never sent; the decoder must drop them, TDecTop::isRandomAccessSkipPicture,
+# TDecTop.cpp:1112-1160).  The pin is what the unmodified TAppDecoder prints for this cut.
+if [ "$WANT" == "s_seek_240p" ]; then
+  out=$ROOT/corpus/s_seek_240p
+  [ -s "$ROOT/corpus/s_cra_240p.bin" ] || "$0" s_cra_240p
+  python3 - "$ROOT/corpus/s_cra_240p.bin" "$out.bin" <<'PY'
+import re, sys
+d = open(sys.argv[1], 'rb').read()
+pos = [m.start() for m in re.finditer(b'\x00\x00\x01', d)]
+pos = [p - 1 if p > 0 and d[p - 1] == 0 else p for p in pos]                 # keep 4-byte start codes whole
+nals = [(p, pos[i + 1] if i + 1 < len(pos) else len(d)) for i, p in enumerate(pos)]
+typ = lambda n: (d[n[0] + (4 if d[n[0] + 2] == 0 else 3)] >> 1) & 0x3f
+cras = [i for i, n in enumerate(nals) if typ(n) == 21]
+assert len(cras) >= 2, "need two CRA pictures"
+start = cras[1]
+while start > 0 and typ(nals[start - 1]) in (35, 39): start -= 1            # AUD / prefix SEI of the CRA's access unit (the suffix SEI before it belongs to the previous picture)
+out = b''.join(d[a:b] for i, (a, b) in enumerate(nals) if typ((a, b)) in (32, 33, 34) and i < start)
+out += d[nals[start][0]:]
+open(sys.argv[2], 'wb').write(out)
+PY
+  "$DEC" -b "$out.bin" -d 0 -o "$TMP_YUV/s_seek.dec.yuv" > "$out.dec.log" 2>&1
+  grep -o 'POC.*' "$out.dec.log" | sed -E 's/\[DT +[0-9.]+\] //' > "$out.md5"
+  md5sum < "$TMP_YUV/s_seek.dec.yuv" | awk '{print $1}' > "$out.yuvmd5"
+  echo "s_seek_240p: done ($(stat -c %s "$out.bin") bytes, $(grep -c OK "$out.md5") pictures OK)"
   exit 0
 fi
 if [ "$1" == "--list" ]; then for j in "${JOBS[@]}"; do echo "$j" | awk '{print $1}'; done; exit 0; fi
