@@ -3,6 +3,7 @@
 // libHMDEC_get_internal_info.  The library is dlopen'ed, so the same binary drives the reference wrapper
 // (oracle/_ref/liblibHMDecoderStatic.so) and this repository's drop-in; tests compare the two dumps byte for byte.
 //   hmdec_internals <library.so> <in.bin> <out.txt> [--backend N ARG]     (--backend: libHMDecB200_new_decoder_ex, drop-in only)
+// HMDEC_INTERNALS_MAX_TLAYER=N: libHMDec_set_max_temporal_layer(N) before the first NAL (both libraries).
 // HMDEC_INTERNALS_TIME=1: do not print the block lists, report the time spent inside libHMDEC_get_internal_info instead.
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,7 @@ int main(int argc, char** argv)
   else dec = p_libHMDec_new_decoder();
   if (!dec) { fprintf(stderr, "no decoder\n"); return 3; }
   p_libHMDec_set_SEI_Check(dec, true);
+  if (getenv("HMDEC_INTERNALS_MAX_TLAYER")) { RESOLVE(libHMDec_set_max_temporal_layer) p_libHMDec_set_max_temporal_layer(dec, atoi(getenv("HMDEC_INTERNALS_MAX_TLAYER"))); }
   std::vector<uint8_t> stream;
   if (!readFile(argv[2], stream)) { perror(argv[2]); return 2; }
   std::vector<std::pair<size_t, size_t> > nals;

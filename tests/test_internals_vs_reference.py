@@ -86,3 +86,27 @@ def test_drop_in_on_the_gpu_reports_what_the_reference_reports(name, tmp_path):
     ref = _dump(REF, stream, str(tmp_path / "ref.txt"))
     got = _dump(OURS, stream, str(tmp_path / "ours.txt"), env=dict(os.environ, HMDEC_B200_QUIET="1"))
     _compare(ref, got, name)
+
+
+def test_temporal_layer_limit_matches_the_reference_host_side(tmp_path):
+    """libHMDec_set_max_temporal_layer(0) (libHMDecoder.cpp:142: NAL units of higher temporal layers are dropped before they reach the
+    decoder): same pictures in the same order, same internals, on the open-GOP stream with two temporal layers."""
+    _need()
+    stream = os.path.join(GOLDEN, "s_cra_240p.bin")
+    ref = _dump(REF, stream, str(tmp_path / "ref.txt"), env=dict(os.environ, HMDEC_INTERNALS_MAX_TLAYER="0"))
+    env = dict(os.environ, HMDUMP_RECORDS_ONLY="1", HMDEC_B200_QUIET="1", HMDEC_INTERNALS_MAX_TLAYER="0")
+    got = _dump(OURS, stream, str(tmp_path / "ours.txt"), ("--backend", "1", "/dev/null"), env)
+    assert len(ref) == 13                                  # 25 pictures, 12 of them in temporal layer 1
+    for r, g in zip(ref, got):
+        g["planes"] = r["planes"]
+    _compare(ref, got, "s_cra_240p tid0")
+
+
+@pytest.mark.gpu
+def test_temporal_layer_limit_matches_the_reference_on_the_gpu(tmp_path):
+    _need()
+    stream = os.path.join(GOLDEN, "s_cra_240p.bin")
+    ref = _dump(REF, stream, str(tmp_path / "ref.txt"), env=dict(os.environ, HMDEC_INTERNALS_MAX_TLAYER="0"))
+    got = _dump(OURS, stream, str(tmp_path / "ours.txt"), env=dict(os.environ, HMDEC_B200_QUIET="1", HMDEC_INTERNALS_MAX_TLAYER="0"))
+    assert len(ref) == 13
+    _compare(ref, got, "s_cra_240p tid0")
