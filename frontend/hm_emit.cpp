@@ -10,6 +10,7 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <mutex>
 #include <list>
 #include <map>
 #include <iostream>
@@ -59,6 +60,34 @@ struct HmEmitter::CuCtx
   uint32_t    lumaOff[256]; // coef/resid offset of the luma TU starting at partition i (CCP), HMR_NO_OFFSET if none
 };
 
+// ---- record storage survives the decoder -------------------------------------------------------------------------------------
+// A new bitstream means a new decoder and a new emitter.  Its record vectors would grow from nothing again — the level arena of a
+// 2160p intra picture alone doubles twelve times up to 24 MB: 48 MB of fresh pages, copies and mmap / munmap calls per bitstream,
+// 190 page faults per picture in steady state, and every one of them takes the process's memory-map lock, which is what made the
+// 32-thread harness idle for up to a quarter of its time (profiles/r04d_e2e_thp.log).  An emitter that ends parks its (emptied)
+// vectors here with their capacity; the next one adopts them.
+namespace {
+struct RecordStorage
+{
+  std::vector<hmr_tu> tu, tuSorted; std::vector<int16_t, HmDefaultInit<int16_t> > coef; std::vector<hmr_intra> intra, intraTmp[3];
+  std::vector<hmr_ctu_intra_range> range; std::vector<hmr_pu> pu; std::vector<uint32_t> puPrefix; std::vector<hmr_ctu> ctu;
+  std::vector<uint8_t> bs, cuFlags, puRefIdx; std::vector<int8_t> qp;
+};
+std::mutex g_storageLock;
+std::vector<RecordStorage*> g_storage;
+bool storagePooled() { static const bool on = getenv("HMDEC_B200_NO_RECORD_POOL") == NULL; return on; }
+}
+
+// emptied vectors <-> the emitter's members (swap in both directions)
+void HmEmitter::swapStorage(void* p)
+{
+  RecordStorage& s = *(RecordStorage*)p;
+  m_tu.swap(s.tu); m_tuSorted.swap(s.tuSorted); m_coef.swap(s.coef); m_intra.swap(s.intra);
+  for (int c = 0; c < 3; c++) m_intraTmp[c].swap(s.intraTmp[c]);
+  m_range.swap(s.range); m_pu.swap(s.pu); m_puPrefix.swap(s.puPrefix); m_ctu.swap(s.ctu);
+  m_bs.swap(s.bs); m_cuFlags.swap(s.cuFlags); m_puRefIdx.swap(s.puRefIdx); m_qp.swap(s.qp);
+}
+
 HmEmitter::HmEmitter(HmFrameSink* sink)
   : m_sink(sink), m_lf(NULL), m_lfDepth(0), m_anyDeblock(false), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0), m_tCtu(0), m_tBs(0), m_tPic(0), m_tSink(0), m_nPic(0)
 {
@@ -66,10 +95,28 @@ HmEmitter::HmEmitter(HmFrameSink* sink)
   // product path: HM's whole-CTU coefficient zero fills are skipped (hm_fast.cpp); verification / golden generation keep them
   m_cleanCoeffs = !sink->wantHmRecon();
   memset(&m_hdr, 0, sizeof(m_hdr));
+  RecordStorage* st = NULL;
+  if (storagePooled())
+  {
+    std::lock_guard<std::mutex> g(g_storageLock);
+    if (!g_storage.empty()) { st = g_storage.back(); g_storage.pop_back(); }
+  }
+  if (st) { swapStorage(st); delete st; }
 }
 
 HmEmitter::~HmEmitter()
 {
+  if (storagePooled())
+  {
+    m_tu.clear(); m_tuSorted.clear(); m_coef.clear(); m_intra.clear(); m_range.clear(); m_pu.clear(); m_puPrefix.clear(); m_ctu.clear();
+    m_bs.clear(); m_cuFlags.clear(); m_puRefIdx.clear(); m_qp.clear();
+    for (int c = 0; c < 3; c++) m_intraTmp[c].clear();
+    RecordStorage* st = new RecordStorage;
+    swapStorage(st);
+    std::lock_guard<std::mutex> g(g_storageLock);
+    if (g_storage.size() < 128) { g_storage.push_back(st); st = NULL; }
+    delete st;
+  }
   if (m_lf) { m_lf->destroy(); delete m_lf; }
   if (getenv("HMDEC_B200_STATS") && m_nPic)
     fprintf(stderr, "hm_emit stats: %d pictures; per picture: CTU record emission %.2f ms, BS/QP maps %.2f ms, SAO+pack %.2f ms, sink submit %.2f ms\n",
@@ -954,7 +1001,8 @@ void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdap
   while (m_coef.size() & 15) m_coef.push_back(0);
   // group the residual records by transform size (stable: luma stays ahead of its co-located chroma for CCP)
   {
-    std::vector<hmr_tu> sorted;
+    std::vector<hmr_tu>& sorted = m_tuSorted;                  // a member: both vectors keep their capacity from picture to picture
+    sorted.clear();
     sorted.reserve(m_tu.size());
     for (int k = 0; k < 4; k++)
     {

@@ -100,6 +100,7 @@ private:
   void bsDirect(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, bool lfCrossTiles);   // edges enumerated from the CU / PU / TU geometry, no flag arrays
   void saoInfo(TComPic* pic, TComSampleAdaptiveOffset* sao);
   void fail(const char* what);
+  void swapStorage(void* recordStorage);   // hm_emit.cpp: record vectors are parked process-wide between decoders
 
   HmFrameSink* m_sink;
   TComLoopFilter* m_lf;              // own instance: HM's edge-flag machinery, run per CTU while the CTU is still in cache
@@ -113,7 +114,7 @@ private:
   std::string  m_failText;
 
   hmr_frame_hdr                    m_hdr;
-  std::vector<hmr_tu>              m_tu;
+  std::vector<hmr_tu>              m_tu, m_tuSorted;
   std::vector<int16_t, HmDefaultInit<int16_t> > m_coef;   // grown by resize() WITHOUT the value-initialising fill: every entry is written right after
   std::vector<hmr_intra>           m_intra;
   std::vector<hmr_intra>           m_intraTmp[3];
