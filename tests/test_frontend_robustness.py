@@ -123,6 +123,33 @@ def test_decoders_of_different_geometry_run_concurrently_as_threads(tmp_path):
     assert not errors, errors
 
 
+def test_pooled_buffers_pass_cleanly_from_one_bitstream_to_the_next(tmp_path):
+    """One thread opens one bitstream after the other (different geometries, bit depths, chroma formats, intra-only and inter): the record
+    vectors of a finished decoder's emitter and its parked picture buffers are adopted by the next decoder (frontend/hm_emit.cpp:
+    RecordStorage, frontend/hm_fast.cpp: g_picPool) — every record dump must still equal the golden one, twice over."""
+    lib = _lib()
+    order = ["s_ra8_240p", "c1_intra8_240p", "s_ra8_odd", "s_ra10_240p", "s_rext444_240p", "s_ra8_240p", "s_ra422_240p", "s_gray400_240p", "s_cra_240p", "s_seek_240p", "c1_intra8_240p"]
+    for rep, name in enumerate(order + order):
+        out = str(tmp_path / f"{rep}.hmr")
+        dec = lib.libHMDecB200_new_decoder_ex(1, out.encode())
+        assert dec
+        lib.libHMDec_set_SEI_Check(dec, False)
+        pics, rc = _decode(lib, dec, _nals(os.path.join(GOLDEN, name + ".bin")))
+        lib.libHMDec_free_decoder(dec)
+        assert rc == OK
+        got = records.read_dump(out)
+        ref = records.read_dump(os.path.join(GOLDEN, name + ".hmr.gz"))
+        assert pics == len(ref) == len(got), (name, pics, len(ref), len(got))
+        for g, f in zip(got, ref):
+            for field in records.Frame.FIELDS:
+                a, b = getattr(g, field), getattr(f, field)
+                if a is None or b is None:
+                    assert (a is None or a.size == 0) and (b is None or b.size == 0), (name, field)
+                else:
+                    assert np.array_equal(a, b), (name, rep, int(f.h["poc"]), field)
+        os.remove(out)
+
+
 def test_unsupported_feature_is_reported_through_the_reference_abi(tmp_path):
     """A stream whose smallest partition is 8x8 (min TU 8, min CU 16) is not on the GPU reconstruction path: the decoder must stop with LIBHMDEC_ERROR from libHMDec_push_nal_unit (sticky),
     name the feature through libHMDecB200_unsupported, and leave the process alive."""
