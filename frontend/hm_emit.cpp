@@ -73,8 +73,9 @@ struct RecordStorage
   std::vector<hmr_ctu_intra_range> range; std::vector<hmr_pu> pu; std::vector<uint32_t> puPrefix; std::vector<hmr_ctu> ctu;
   std::vector<uint8_t> bs, cuFlags, puRefIdx; std::vector<int8_t> qp;
 };
-std::mutex g_storageLock;
-std::vector<RecordStorage*> g_storage;
+// never destroyed: a decoder freed from a static destructor of the host program must still find them
+std::mutex& g_storageLock = *new std::mutex;
+std::vector<RecordStorage*>& g_storage = *new std::vector<RecordStorage*>;
 bool storagePooled() { static const bool on = getenv("HMDEC_B200_NO_RECORD_POOL") == NULL; return on; }
 }
 

@@ -166,7 +166,7 @@ static void pool_free_host(void* p, size_t bytes)
 // CUDA streams are pooled the same way: creating one is a handful of ioctls that take ~20 ms when 16 decoder threads open new
 // bitstreams against one context (tools/ioctl_trace.c, profiles/r04b_ioctl_trace.log: 3-5 % of a decoder thread at one new engine
 // per 33-picture bitstream).  A stream goes back to the pool only after cudaStreamSynchronize, i.e. empty.
-static std::vector<cudaStream_t> g_streamPool[16];
+static std::vector<cudaStream_t>* const g_streamPool = new std::vector<cudaStream_t>[16];   // never destroyed (engines may end during static destruction)
 static cudaError_t pool_stream(int device, cudaStream_t* s)
 {
   {
