@@ -25,6 +25,7 @@
 // direction.  An output at an even position uses NT/2 dp2a with taps (t0,t1)(t2,t3)..; an output at an odd position
 // uses NT/2+1 with the taps shifted by one half-word (0,t0)(t1,t2)..(t7,0).  All sums are exact int32, as in HM.
 #include "common.cuh"
+#include <cstdlib>
 
 #ifndef MC_WARPS
 #define MC_WARPS 4
@@ -487,11 +488,10 @@ __device__ __forceinline__ void mc_general(const FrameParams& P, const hmr_pu& t
 // 51 / 57 us per 2160p picture at 6 / 8 / 9 CTAs per SM; two tiles per warp with their loads in flight together — no gain, spills at 56
 // registers.  The CTA scheduler hides the record -> samples round trips better than either.)
 template <bool LUMA>
-__global__ void __launch_bounds__(MC_WARPS * 32, MC_MIN_BLOCKS) mc_kernel(const __grid_constant__ FrameParams P, const int warpBytes, const int chromaRows)
+__device__ __forceinline__ void mc_tile_body(const FrameParams& P, const uint32_t block, const int warpBytes, const int chromaRows, uint8_t* s_mc)
 {
-  extern __shared__ __align__(16) uint8_t s_mc[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t tile = blockIdx.x * MC_WARPS + warp;
+  const uint32_t tile = block * MC_WARPS + warp;
   if (tile >= P.hdr.n_mc_tiles) return;
   uint8_t* base = s_mc + (size_t)warp * warpBytes;
   uint32_t* tmp = (uint32_t*)base;                                        // 12 row pairs x 16 words
@@ -507,6 +507,23 @@ __global__ void __launch_bounds__(MC_WARPS * 32, MC_MIN_BLOCKS) mc_kernel(const 
   mc_general<LUMA>(P, t, tile, tmp, win, chromaRows, lane);
 }
 
+template <bool LUMA>
+__global__ void __launch_bounds__(MC_WARPS * 32, MC_MIN_BLOCKS) mc_kernel(const __grid_constant__ FrameParams P, const int warpBytes, const int chromaRows)
+{
+  extern __shared__ __align__(16) uint8_t s_mc[];
+  mc_tile_body<LUMA>(P, blockIdx.x, warpBytes, chromaRows, s_mc);
+}
+
+// 4:2:0: a warp needs the same shared memory for a luma tile as for the two chroma tiles, so both go into ONE launch — CTAs
+// with blockIdx.y == 0 predict luma, the others chroma.  One launch less per picture (a launch costs ~3 us of a saturated GPU's time,
+// DESIGN.md "what bounds value"), and for one stream alone the two halves overlap instead of running back to back.
+__global__ void __launch_bounds__(MC_WARPS * 32, MC_MIN_BLOCKS) mc_kernel_420(const __grid_constant__ FrameParams P, const int warpBytes, const int chromaRows)
+{
+  extern __shared__ __align__(16) uint8_t s_mc[];
+  if (blockIdx.y == 0) mc_tile_body<true>(P, blockIdx.x, warpBytes, chromaRows, s_mc);
+  else mc_tile_body<false>(P, blockIdx.x, warpBytes, chromaRows, s_mc);
+}
+
 int launch_mc(const FrameParams& P, cudaStream_t s)
 {
   if (P.hdr.n_mc_tiles == 0) return 0;
@@ -515,9 +532,15 @@ int launch_mc(const FrameParams& P, cudaStream_t s)
   const int chromaRows = ((16 >> P.csy) + 4) & ~1;
   const int grid = (P.hdr.n_mc_tiles + MC_WARPS - 1) / MC_WARPS;
   const int lumaBytes = 12 * MC_TMPW * 4 + 2 * 24 * MC_PITCH * 2;
+  const int chromaBytes = 12 * MC_TMPW * 4 + 4 * chromaRows * MC_PITCH * 2;
+  static const bool split = getenv("HMR_MC_SPLIT") != NULL;               // A/B switch: luma and chroma as two launches always
+  if (P.hdr.chroma_format == HMR_CHROMA_420 && chromaBytes <= lumaBytes && !split)
+  {
+    mc_kernel_420<<<dim3(grid, 2), MC_WARPS * 32, MC_WARPS * lumaBytes, s>>>(P, lumaBytes, chromaRows);
+    return 2;
+  }
   mc_kernel<true><<<grid, MC_WARPS * 32, MC_WARPS * lumaBytes, s>>>(P, lumaBytes, chromaRows);
   if (P.hdr.chroma_format == HMR_CHROMA_400) return 2;
-  const int chromaBytes = 12 * MC_TMPW * 4 + 4 * chromaRows * MC_PITCH * 2;
   mc_kernel<false><<<grid, MC_WARPS * 32, MC_WARPS * chromaBytes, s>>>(P, chromaBytes, chromaRows);
   return 3;
 }
