@@ -6,9 +6,9 @@
 //
 // Work unit: one 16x16-luma tile of a PU, owned by ONE WARP — no block-level synchronisation anywhere.  A tiny pre-pass
 // (mc_expand_kernel) turns the PU records into one 16-byte record per tile so that the main kernels need a single
-// dependent load before they can fetch samples.  Two main launches per picture: mc_kernel<true> predicts the luma tile,
-// mc_kernel<false> the two co-located chroma tiles (half the shared memory per warp each: the kernels wait on memory,
-// and warps in flight are what hides it).  Cb and Cr of an 8-wide chroma tile (4:2:0, 4:2:2) have the same geometry,
+// dependent load before they can fetch samples.  Two kinds of work item per tile: the luma tile, and the two co-located chroma
+// tiles (half the shared memory per warp each: the kernels wait on memory, and warps in flight are what hides it) — one
+// launch for both in 4:2:0 (mc_kernel_420: same shared memory per warp), mc_kernel<true> + mc_kernel<false> otherwise.  Cb and Cr of an 8-wide chroma tile (4:2:0, 4:2:2) have the same geometry,
 // phases and taps: they are staged together (16 lanes each) and filtered together (half of the active lanes each).
 //
 // Per tile: every reference window (up to 2 lists; chroma: x 2 planes) is fetched up front with 16-byte cp.async copies
