@@ -69,7 +69,7 @@ struct HmEmitter::CuCtx
 namespace {
 struct RecordStorage
 {
-  std::vector<hmr_tu> tu, tuSorted; std::vector<int16_t, HmDefaultInit<int16_t> > coef; std::vector<hmr_intra> intra, intraTmp[3];
+  std::vector<hmr_tu> tu, tuSorted; HmLevelArena coef; std::vector<hmr_intra> intra, intraTmp[3];
   std::vector<hmr_ctu_intra_range> range; std::vector<hmr_pu> pu; std::vector<uint32_t> puPrefix; std::vector<hmr_ctu> ctu;
   std::vector<uint8_t> bs, cuFlags, puRefIdx; std::vector<int8_t> qp;
 };
@@ -352,8 +352,7 @@ uint32_t HmEmitter::emitResidualTU(CuCtx& c, int compIdx, void* pTu, bool intra,
   // coefficient levels: int32 raster N x N at getCoeff()+offset (TDecSbac.cpp:1260); the dequantiser clips its
   // input to 16 bits for every legal QP/bit-depth (TComTrQuant.cpp:1284-1286), so int16 transport is exact
   t.coef_off = (uint32_t)m_coef.size();
-  m_coef.resize(m_coef.size() + (size_t)N * N);
-  int16_t* dst = &m_coef[t.coef_off];
+  int16_t* dst = m_coef.grow((size_t)N * N);
   if (coded)
   {
     const TCoeff* src = ctu->getCoeff(compID) + rTu.getCoefficientOffset(compID);
@@ -551,8 +550,7 @@ void HmEmitter::emitPcmCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth, 
       t.flags = HMR_TU_CODED | HMR_TU_INTRA | HMR_TU_BYPASS;
       t.luma_off = HMR_NO_OFFSET;
       t.coef_off = (uint32_t)m_coef.size();
-      m_coef.resize(m_coef.size() + (size_t)w * w);
-      int16_t* dst = &m_coef[t.coef_off];
+      int16_t* dst = m_coef.grow((size_t)w * w);
       const Pel* src = pcm + (size_t)part * w * w;
       for (int i = 0; i < w * w; i++) dst[i] = (int16_t)(src[i] << shift);
       m_tu.push_back(t);
@@ -999,7 +997,7 @@ void HmEmitter::onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdap
   if (m_pu.empty()) m_hdr.flags |= HMR_FRM_INTRA_ONLY;
 
   // pad the coefficient buffer to a multiple of 16 entries
-  while (m_coef.size() & 15) m_coef.push_back(0);
+  while (m_coef.size() & 15) *m_coef.grow(1) = 0;
   // group the residual records by transform size (stable: luma stays ahead of its co-located chroma for CCP)
   {
     std::vector<hmr_tu>& sorted = m_tuSorted;                  // a member: both vectors keep their capacity from picture to picture

@@ -7,6 +7,8 @@
 
 #include <stdint.h>
 #include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include <memory>
@@ -58,15 +60,37 @@ struct HmFrameSink
 
 #include "hm_fast.h"
 
-// std::allocator whose construct() default-initialises: resize() of a vector of a trivial type then leaves the new tail untouched
-// instead of zeroing it (the level arena grows by a whole TU at a time and is overwritten at once: 24 MB per 2160p I picture).
-template <class T> struct HmDefaultInit : std::allocator<T>
+// The level arena of a picture: int16 levels of every coded TU back to back.  Grown a whole TU at a time and written at once, so
+// neither a value-initialising fill nor per-element construction is wanted (std::vector::resize did the first, and with a
+// default-initialising allocator still walked every element: 4 % of an intra picture's parse) — a pointer bump, geometric growth.
+struct HmLevelArena
 {
-  template <class U> struct rebind { typedef HmDefaultInit<U> other; };
-  HmDefaultInit() {}
-  template <class U> HmDefaultInit(const HmDefaultInit<U>&) {}
-  template <class U> void construct(U* p) { ::new ((void*)p) U; }
-  template <class U, class A1> void construct(U* p, const A1& a1) { ::new ((void*)p) U(a1); }
+  int16_t* p; size_t n, cap;
+  HmLevelArena() : p(NULL), n(0), cap(0) {}
+  ~HmLevelArena() { free(p); }
+  void clear() { n = 0; }
+  size_t size() const { return n; }
+  const int16_t* data() const { return p; }
+  void swap(HmLevelArena& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
+  // `count` more entries (uninitialised); returns the first of them.  Earlier pointers into the arena are invalid afterwards.
+  inline int16_t* grow(size_t count)
+  {
+    if (n + count > cap) reserve(n + count);
+    int16_t* r = p + n;
+    n += count;
+    return r;
+  }
+  void reserve(size_t want)
+  {
+    size_t c = cap ? cap : 4096;
+    while (c < want) c *= 2;
+    int16_t* q = (int16_t*)realloc(p, c * sizeof(int16_t));
+    if (!q) throw std::bad_alloc();
+    p = q; cap = c;
+  }
+private:
+  HmLevelArena(const HmLevelArena&);
+  HmLevelArena& operator=(const HmLevelArena&);
 };
 
 class HmEmitter
@@ -115,7 +139,7 @@ private:
 
   hmr_frame_hdr                    m_hdr;
   std::vector<hmr_tu>              m_tu, m_tuSorted;
-  std::vector<int16_t, HmDefaultInit<int16_t> > m_coef;   // grown by resize() WITHOUT the value-initialising fill: every entry is written right after
+  HmLevelArena                     m_coef;
   std::vector<hmr_intra>           m_intra;
   std::vector<hmr_intra>           m_intraTmp[3];
   std::vector<hmr_ctu_intra_range> m_range;
