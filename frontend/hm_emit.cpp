@@ -634,11 +634,70 @@ void HmEmitter::intraBlk(CuCtx& c, int compIdx, void* pTu)
     const UInt idxLB = g_auiRasterToZscan[g_auiZscanToRaster[idxLT] + (hUnits - 1) * partStride];
     Bool flags[4 * MAX_NUM_SPU_W + 1];
     memset(flags, 0, sizeof(flags));
-    flags[leftUnits] = isAboveLeftAvailable(ctu, idxLT);
-    isAboveAvailable     (ctu, idxLT, idxRT, flags + leftUnits + 1);
-    isAboveRightAvailable(ctu, idxLT, idxRT, flags + leftUnits + 1 + wUnits);
-    isLeftAvailable      (ctu, idxLT, idxLB, flags + leftUnits - 1);
-    isBelowLeftAvailable (ctu, idxLT, idxLB, flags + leftUnits - 1 - hUnits);
+    // HM asks getPUAbove / getPULeft / getPUAboveRightAdi / getPUBelowLeftAdi once per 4-sample unit (z-scan conversions, slice,
+    // tile and CTU-order tests every time: 4 % of the parser thread).  In a picture of ONE slice and ONE tile without constrained
+    // intra prediction all of those rules collapse to geometry: a unit is available iff it lies inside the picture and was
+    // decoded before this block — a CTU to the left or in the row above (the above-right one included), or, inside this CTU,
+    // a unit that precedes the block in z-order (units straight above / left of it always do).  Everything else: HM's functions.
+    static const bool hmAvail = getenv("HMDEC_B200_HM_AVAIL") != NULL;      // A/B switch
+    TComSlice* sl = ctu->getSlice();
+    if (!hmAvail && !sl->getPPS()->getConstrainedIntraPred() && sl->getSliceCurStartCUAddr() == 0 &&
+        sl->getPPS()->getNumTileColumnsMinus1() == 0 && sl->getPPS()->getTileNumRowsMinus1() == 0)
+    {
+      const int ctuSize = (int)g_uiMaxCUWidth, unitsPerCtu = ctuSize / baseUnit;
+      const int picW = (int)sl->getSPS()->getPicWidthInLumaSamples(), picH = (int)sl->getSPS()->getPicHeightInLumaSamples();
+      const int ctuX = (int)ctu->getCUPelX(), ctuY = (int)ctu->getCUPelY();
+      const int rasterLT = (int)g_auiZscanToRaster[idxLT];
+      const int ux0 = rasterLT % partStride, uy0 = rasterLT / partStride;   // the block's first unit inside the CTU
+      // is the unit at (ux, uy) — CTU-relative unit coordinates, possibly outside [0, unitsPerCtu) — available to this block?
+      auto avail = [&](int ux, int uy) -> Bool
+      {
+        const int x = ctuX + ux * baseUnit, y = ctuY + uy * baseUnit;
+        if (x < 0 || y < 0 || x >= picW || y >= picH) return false;
+        if (uy < 0) return ux < 2 * unitsPerCtu;                            // the CTU row above: left, above and above-right CTUs are done
+        if (uy >= unitsPerCtu) return false;                                // the CTU row below: not yet
+        if (ux < 0) return true;                                            // the CTU to the left
+        if (ux >= unitsPerCtu) return false;                                // the CTU to the right
+        return g_auiRasterToZscan[uy * partStride + ux] < idxLT;            // inside this CTU: decoded before the block?
+      };
+      flags[leftUnits] = avail(ux0 - 1, uy0 - 1);
+      for (int i = 0; i < wUnits; i++)
+      {
+        flags[leftUnits + 1 + i] = avail(ux0 + i, uy0 - 1);
+        flags[leftUnits + 1 + wUnits + i] = avail(ux0 + wUnits + i, uy0 - 1);
+      }
+      for (int i = 0; i < hUnits; i++)
+      {
+        flags[leftUnits - 1 - i] = avail(ux0 - 1, uy0 + i);
+        flags[leftUnits - 1 - hUnits - i] = avail(ux0 - 1, uy0 + hUnits + i);
+      }
+      static const bool check = getenv("HMDEC_B200_CHECK_AVAIL") != NULL;   // development aid: compare with HM's functions
+      if (check)
+      {
+        Bool ref[4 * MAX_NUM_SPU_W + 1];
+        memset(ref, 0, sizeof(ref));
+        ref[leftUnits] = isAboveLeftAvailable(ctu, idxLT);
+        isAboveAvailable     (ctu, idxLT, idxRT, ref + leftUnits + 1);
+        isAboveRightAvailable(ctu, idxLT, idxRT, ref + leftUnits + 1 + wUnits);
+        isLeftAvailable      (ctu, idxLT, idxLB, ref + leftUnits - 1);
+        isBelowLeftAvailable (ctu, idxLT, idxLB, ref + leftUnits - 1 - hUnits);
+        for (int i = 0; i < 2 * leftUnits + 1 - 0 && i < leftUnits + 1 + 2 * wUnits; i++)
+          if ((flags[i] != 0) != (ref[i] != 0))
+          {
+            fprintf(stderr, "intra availability mismatch: POC %d CTU %u block (%d,%d) %ux%u comp %d, flag %d (corner at %d): direct %d, HM %d\n",
+                    (int)pic->getPOC(), ctu->getAddr(), (int)r.x, (int)r.y, W, Hh, compIdx, i, leftUnits, (int)flags[i], (int)ref[i]);
+            abort();
+          }
+      }
+    }
+    else
+    {
+      flags[leftUnits] = isAboveLeftAvailable(ctu, idxLT);
+      isAboveAvailable     (ctu, idxLT, idxRT, flags + leftUnits + 1);
+      isAboveRightAvailable(ctu, idxLT, idxRT, flags + leftUnits + 1 + wUnits);
+      isLeftAvailable      (ctu, idxLT, idxLB, flags + leftUnits - 1);
+      isBelowLeftAvailable (ctu, idxLT, idxLB, flags + leftUnits - 1 - hUnits);
+    }
     if (flags[leftUnits]) r.flags |= HMR_INTRA_AVAIL_CORNER;
     for (int i = 0; i < wUnits; i++)
     {
