@@ -231,7 +231,10 @@ void HmEmitter::onCtuParsed(TComDataCU* ctu)
   if (!m_open || pic != m_curPic) beginFrame(pic, ctu);
   for (int c = 0; c < 3; c++) m_intraTmp[c].clear();
   static const bool prefetch = getenv("HMDEC_B200_NO_PREFETCH") == NULL;
-  if (prefetch) hm_fast_prefetch_begin(m_prefetch, pic, ctu->getAddr() + 2);   // the parser is about to init + parse CTU addr+1
+  // which CTU: the one the parser initialises and parses next.  (Two ahead — the first choice — is 2-3 % slower alone and with 8 or 16
+  // threads: the lines arrive in time either way, but a whole CTU's parse then lies between the request and the use and pushes them out of L1.)
+  static const int pfDist = getenv("HMDEC_B200_PF_DIST") ? atoi(getenv("HMDEC_B200_PF_DIST")) : 1;
+  if (prefetch) hm_fast_prefetch_begin(m_prefetch, pic, ctu->getAddr() + pfDist);   // the parser is about to init + parse CTU addr+1
   walkCU(ctu, 0, 0);
   static const bool bsAtEnd = getenv("HMDEC_B200_BS_AT_END") != NULL;   // A/B switch: derive the deblocking side info per picture, like HM
   if (!bsAtEnd) deblockCtu(ctu);                                   // edge flags + boundary strengths while the CTU's arrays are hot

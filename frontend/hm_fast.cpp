@@ -374,7 +374,7 @@ Void TDecTop::xGetNewPicBuffer(TComSlice* pcSlice, TComPic*& rpcPic)
 // TComDataCU::initCU (TComDataCU.cpp:453) refills ~35 per-partition arrays plus both motion fields of a CTU — about
 // 13 KB spread over as many separate allocations, last touched one whole picture ago, i.e. cold in every cache level.
 // The sampling profile shows the parser thread stalled on exactly those stores (memset + initCU + clearMvField ≈ 17 %).
-// While the emitter walks CTU n it therefore asks for the lines of CTU n+2, a few per coding unit so that the
+// While the emitter walks CTU n it therefore asks for the lines of CTU n+1 (HMDEC_B200_PF_DIST), a few per coding unit so that the
 // requests trickle out between real work instead of queueing behind the core's dozen line-fill buffers.
 static inline void pfAdd(HmPrefetchCursor& c, const void* p, size_t bytes)
 {
