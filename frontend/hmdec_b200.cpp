@@ -204,8 +204,17 @@ static void tuneMallocOnce()
   });
 }
 
+extern "C" int hm_cpu_is_x86_64_v3(void);      // hm_cpu_guard.cpp
+
 libHMDec_context* libHMDecB200_new_decoder_ex(int backend, const char* arg)
 {
+#ifdef __AVX2__
+  if (!hm_cpu_is_x86_64_v3())
+  {
+    fprintf(stderr, "libHMDecoder_b200: this build needs an x86-64-v3 CPU (AVX2, BMI2); rebuild frontend/ with ARCHFLAGS=\n");
+    return NULL;
+  }
+#endif
   tuneMallocOnce();
   const bool counted = hm_wait_stats().on && ++hm_wait_stats().decoders > hm_wait_stats().skip;
   t_hmwActive = counted;
