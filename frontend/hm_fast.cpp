@@ -402,7 +402,7 @@ void hm_fast_prefetch_begin(HmPrefetchCursor& pf, TComPic* pic, unsigned ctuAddr
   {
     pfAdd(pf, cu->m_apiMVPIdx[l], n); pfAdd(pf, cu->m_apiMVPNum[l], n);
     TComCUMvField& f = cu->m_acCUMvField[l];
-    pfAdd(pf, f.m_pcMv, n * sizeof(TComMv)); pfAdd(pf, f.m_pcMvd, n * sizeof(TComMv)); pfAdd(pf, f.m_piRefIdx, n);
+    pfAdd(pf, f.m_pcMv, n * sizeof(TComMv)); pfAdd(pf, f.m_piRefIdx, n);      // (not the MVD array: see initCU)
   }
 }
 
@@ -472,7 +472,7 @@ Void TComDataCU::initCU(TComPic* pcPic, UInt ctuAddr)
   {
     TComCUMvField& f = m_acCUMvField[l];                      // clearMvField (TComMotionInfo.cpp:88-97): zero vectors, refIdx NOT_VALID
     ::memset(f.m_pcMv, 0, sizeof(TComMv) * f.m_uiNumPartition);
-    ::memset(f.m_pcMvd, 0, sizeof(TComMv) * f.m_uiNumPartition);
+    // m_pcMvd: not cleared — the decoder writes an MVD at a PU's first partition and reads it back from there at once, nothing else (frontend/Makefile)
     ::memset(f.m_piRefIdx, NOT_VALID, sizeof(*f.m_piRefIdx) * f.m_uiNumPartition);
   }
   // neighbours (TComDataCU.cpp:497-540)
