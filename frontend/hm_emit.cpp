@@ -90,7 +90,7 @@ void HmEmitter::swapStorage(void* p)
 }
 
 HmEmitter::HmEmitter(HmFrameSink* sink)
-  : m_sink(sink), m_lf(NULL), m_lfDepth(0), m_anyDeblock(false), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0), m_tCtu(0), m_tBs(0), m_tPic(0), m_tSink(0), m_nPic(0)
+  : m_sink(sink), m_lf(NULL), m_lfDepth(0), m_anyDeblock(false), m_curPic(NULL), m_open(false), m_unsupported(NULL), m_bsStride(0), m_qpStride(0), m_lgU(0), m_tCtu(0), m_tBs(0), m_tPic(0), m_tSink(0), m_nPic(0)
 {
   m_in422SubTu = false;
   // product path: HM's whole-CTU coefficient zero fills are skipped (hm_fast.cpp); verification / golden generation keep them
@@ -203,7 +203,20 @@ void HmEmitter::beginFrame(TComPic* pic, TComDataCU* ctu)
     }
   }
   if (g_uiMaxCUWidth != g_uiMaxCUHeight)     fail("non-square CTU");
-  if ((g_uiMaxCUWidth >> g_uiMaxCUDepth) != 4) fail("minimum partition size != 4");
+  // HM's per-partition arrays have one entry per (CTU size >> total depth) samples: 4 when the smallest transform block is 4x4,
+  // 8 / 16 / 32 with log2_min_luma_transform_block_size 3 / 4 / 5.  The records are per 4 samples either way (availability bits,
+  // BS map): every HM value then covers 1 << m_lgU units.  (Prediction and transform edges always lie on partition boundaries.)
+  {
+    const unsigned unit = g_uiMaxCUWidth >> g_uiMaxCUDepth;
+    if (unit != 4 && unit != 8 && unit != 16 && unit != 32) fail("minimum partition size outside 4..32");
+    m_lgU = 0;
+    while ((4u << m_lgU) < unit && m_lgU < 3) m_lgU++;
+  }
+  // test hook for the error path of the reference ABI: refuse the (n+1)-th picture as if it used an unsupported tool
+  {
+    const char* refuse = getenv("HMDEC_B200_REFUSE_AFTER");          // read per picture: a test sets it for one decoder of a long-lived process
+    if (refuse && m_nPic >= atoi(refuse)) fail("refused by HMDEC_B200_REFUSE_AFTER");
+  }
   // 4:0:0: luma records only (HM walks getNumberValidComponents() components everywhere)
 
   m_tu.clear(); m_coef.clear(); m_intra.clear(); m_pu.clear(); m_puPrefix.clear(); m_puRefIdx.clear();
@@ -425,7 +438,7 @@ void HmEmitter::emitInterCU(TComDataCU* ctu, unsigned absPartIdx, unsigned depth
   const int picW = slice->getSPS()->getPicWidthInLumaSamples(), picH = slice->getSPS()->getPicHeightInLumaSamples();
   for (int i = 0; i < n; i++)
   {
-    const unsigned partAddr = g_auiRasterToZscan[cuRaster + (py[i] >> 2) * partStride + (px[i] >> 2)];
+    const unsigned partAddr = g_auiRasterToZscan[cuRaster + (py[i] >> (2 + m_lgU)) * partStride + (px[i] >> (2 + m_lgU))];
     hmr_pu p;
     memset(&p, 0, sizeof(p));
     p.x = (uint16_t)(cuX + px[i]); p.y = (uint16_t)(cuY + py[i]);
@@ -702,15 +715,17 @@ void HmEmitter::intraBlk(CuCtx& c, int compIdx, void* pTu)
       isBelowLeftAvailable (ctu, idxLT, idxLB, flags + leftUnits - 1 - hUnits);
     }
     if (flags[leftUnits]) r.flags |= HMR_INTRA_AVAIL_CORNER;
+    // record bits are per 4 luma samples: one HM unit is 1 << m_lgU of them
+    const unsigned unitBits = (1u << (1 << m_lgU)) - 1;
     for (int i = 0; i < wUnits; i++)
     {
-      if (flags[leftUnits + 1 + i])          r.avail_above       |= (uint8_t)(1u << i);
-      if (flags[leftUnits + 1 + wUnits + i]) r.avail_above_right |= (uint8_t)(1u << i);
+      if (flags[leftUnits + 1 + i])          r.avail_above       |= (uint8_t)(unitBits << (i << m_lgU));
+      if (flags[leftUnits + 1 + wUnits + i]) r.avail_above_right |= (uint8_t)(unitBits << (i << m_lgU));
     }
     for (int i = 0; i < hUnits; i++)
     {
-      if (flags[leftUnits - 1 - i])          r.avail_left        |= (uint8_t)(1u << i);
-      if (flags[leftUnits - 1 - hUnits - i]) r.avail_below_left  |= (uint8_t)(1u << i);
+      if (flags[leftUnits - 1 - i])          r.avail_left        |= (uint8_t)(unitBits << (i << m_lgU));
+      if (flags[leftUnits - 1 - hUnits - i]) r.avail_below_left  |= (uint8_t)(unitBits << (i << m_lgU));
     }
   }
 
@@ -852,7 +867,8 @@ void HmEmitter::bsWalk(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth, T
         if (bs)
         {
           const int gx = (ctu->getCUPelX() >> 2) + ux, gy = (ctu->getCUPelY() >> 2) + uy;
-          m_bs[(size_t)gy * m_bsStride + gx] |= (uint8_t)(bs << (dir == EDGE_VER ? 0 : 2));
+          for (int j = 0; j < (1 << m_lgU); j++)                // an 8x8 partition's edge is two 4-sample units long
+            m_bs[(size_t)(gy + (dir == EDGE_VER ? j : 0)) * m_bsStride + gx + (dir == EDGE_VER ? 0 : j)] |= (uint8_t)(bs << (dir == EDGE_VER ? 0 : 2));
         }
       }
     }
@@ -930,10 +946,10 @@ void HmEmitter::bsDirect(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth,
       for (int e = 0; e < n; e += 2)                          // CU origins are multiples of 8 samples: e even = on the 8x8 grid
       {
         if (e == 0 ? !border[dir] : (oneTU && e != puEdge[dir])) continue;
-        for (int k = 0; k < n; k++)
+        for (int k = 0; k < n; k += 1 << m_lgU)                // x, y, e, k: 4-sample units; raster: HM partitions (4 or 8 samples)
         {
           const int x = dir == EDGE_VER ? e : k, y = dir == EDGE_VER ? k : e;
-          const unsigned raster = raster0 + y * stride + x;
+          const unsigned raster = raster0 + (y >> m_lgU) * stride + (x >> m_lgU);
           const unsigned part = g_auiRasterToZscan[raster];
           bool tuEdge = true;
           if (e > 0)
@@ -957,7 +973,8 @@ void HmEmitter::bsDirect(TComDataCU* ctu, unsigned absZorderIdx, unsigned depth,
           if (bs)
           {
             const int gx = (cuX >> 2) + x, gy = (cuY >> 2) + y;
-            m_bs[(size_t)gy * m_bsStride + gx] |= (uint8_t)(bs << (dir == EDGE_VER ? 0 : 2));
+            for (int j = 0; j < (1 << m_lgU); j++)
+              m_bs[(size_t)(gy + (dir == EDGE_VER ? j : 0)) * m_bsStride + gx + (dir == EDGE_VER ? 0 : j)] |= (uint8_t)(bs << (dir == EDGE_VER ? 0 : 2));
           }
         }
       }

@@ -153,6 +153,7 @@ private:
   std::vector<hmr_wp>              m_wp;
   std::vector<uint8_t>             m_puRefIdx;
   int m_bsStride, m_qpStride;
+  int m_lgU;                      // log2 of (HM's partition unit / 4 samples): 0 = 4x4 partitions, 1 = 8x8 (min TU 8)
   bool m_in422SubTu;                       // inside the two square halves of a 4:2:2 chroma TU
   bool m_cleanCoeffs;                      // hm_fast.cpp: HM's whole-CTU coefficient zero fills are skipped for this decoder
   double m_tCtu, m_tBs, m_tPic, m_tSink;   // HMDEC_B200_STATS: host time spent emitting records

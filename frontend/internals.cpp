@@ -240,7 +240,8 @@ void addEnergies(HmInternalsCache& ix)
       const TCoeff* co = ctu->getCoeff(c);
       const UChar* cbf = ctu->getCbf(c);
       const UChar* trIdx = ctu->getTransformIdx();
-      const int perPart = 16 >> (ctu->getPic()->getComponentScaleX(c) + ctu->getPic()->getComponentScaleY(c));   // levels per 4x4 partition
+      const int unit = (int)(g_uiMaxCUWidth >> g_uiMaxCUDepth);                                                  // HM's partition: 4 samples, 8 / 16 / 32 with a larger smallest transform block
+      const int perPart = (unit * unit) >> (ctu->getPic()->getComponentScaleX(c) + ctu->getPic()->getComponentScaleY(c));   // levels per partition
       const UInt deeper = (c != COMPONENT_Y && ctu->getPic()->getChromaFormat() == CHROMA_422) ? 1 : 0;
       int64_t e = 0;
       int done = 0;                                        // levels [0, done) are in e

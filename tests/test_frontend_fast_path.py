@@ -6,7 +6,7 @@ import os
 import subprocess
 import numpy as np
 import pytest
-from conftest import GOLDEN, STREAMS, ROOT
+from conftest import GOLDEN, ALL_STREAMS as STREAMS, ROOT
 from libhm_b200 import records
 
 CLI = os.path.join(ROOT, "frontend", "_build", "hmdec_cli")

@@ -84,7 +84,8 @@ def test_shipped_library_exports_only_the_wrapper_abi_and_holds_no_cpu_reconstru
         assert cpu_recon not in allsyms, f"the shipped drop-in still links {cpu_recon}"
 
 
-MIXED = ["s_ra8_240p", "s_ra10_240p", "s_ctu16_240p", "s_ctu32_240p", "s_rext444_240p", "s_ra422_240p", "s_ld10_240p", "s_switch_240p"]
+MIXED = ["s_ra8_240p", "s_ra10_240p", "s_ctu16_240p", "s_ctu32_240p", "s_rext444_240p", "s_ra422_240p", "s_ld10_240p", "s_switch_240p",
+         "s_ramintu8_240p", "s_mintu16_240p", "s_mintu32_240p"]       # the last three: HM partitions of 8 / 16 / 32 samples (other g_uiMaxCUDepth / g_uiAddCUDepth)
 
 
 def test_decoders_of_different_geometry_run_concurrently_as_threads(tmp_path):
@@ -128,7 +129,8 @@ def test_pooled_buffers_pass_cleanly_from_one_bitstream_to_the_next(tmp_path):
     vectors of a finished decoder's emitter and its parked picture buffers are adopted by the next decoder (frontend/hm_emit.cpp:
     RecordStorage, frontend/hm_fast.cpp: g_picPool) — every record dump must still equal the golden one, twice over."""
     lib = _lib()
-    order = ["s_ra8_240p", "c1_intra8_240p", "s_ra8_odd", "s_ra10_240p", "s_rext444_240p", "s_ra8_240p", "s_ra422_240p", "s_gray400_240p", "s_cra_240p", "s_seek_240p", "c1_intra8_240p"]
+    order = ["s_ra8_240p", "c1_intra8_240p", "s_ra8_odd", "s_ra10_240p", "s_rext444_240p", "s_ra8_240p", "s_ra422_240p", "s_gray400_240p", "s_cra_240p", "s_seek_240p", "c1_intra8_240p",
+             "s_mintu8_240p", "s_ra8_240p", "s_mintu32_240p", "s_ramintu8_240p", "s_mintu16_240p"]
     for rep, name in enumerate(order + order):
         out = str(tmp_path / f"{rep}.hmr")
         dec = lib.libHMDecB200_new_decoder_ex(1, out.encode())
@@ -151,15 +153,20 @@ def test_pooled_buffers_pass_cleanly_from_one_bitstream_to_the_next(tmp_path):
 
 
 def test_unsupported_feature_is_reported_through_the_reference_abi(tmp_path):
-    """A stream whose smallest partition is 8x8 (min TU 8, min CU 16) is not on the GPU reconstruction path: the decoder must stop with LIBHMDEC_ERROR from libHMDec_push_nal_unit (sticky),
-    name the feature through libHMDecB200_unsupported, and leave the process alive."""
+    """A picture the emitter refuses (every tool an HM-built stream can carry is on the GPU path by now, so the refusal is forced after the
+    first picture with HMDEC_B200_REFUSE_AFTER — the same HmEmitter::fail() an unsupported SPS tool takes): the decoder must stop with
+    LIBHMDEC_ERROR from libHMDec_push_nal_unit (sticky), name the reason through libHMDecB200_unsupported, and leave the process alive."""
     lib = _lib()
     dec = lib.libHMDecB200_new_decoder_ex(1, str(tmp_path / "g.hmr").encode())
     assert dec
-    nals = _nals(os.path.join(GOLDEN, "s_mintu8_240p.bin"))
-    pics, rc = _decode(lib, dec, nals)
+    nals = _nals(os.path.join(GOLDEN, "s_ra8_240p.bin"))
+    os.environ["HMDEC_B200_REFUSE_AFTER"] = "1"
+    try:
+        pics, rc = _decode(lib, dec, nals)
+    finally:
+        del os.environ["HMDEC_B200_REFUSE_AFTER"]
     assert rc == ERROR
-    assert b"minimum partition size" in lib.libHMDecB200_unsupported(dec)
+    assert b"HMDEC_B200_REFUSE_AFTER" in lib.libHMDecB200_unsupported(dec)
     newpic, check = C.c_bool(False), C.c_bool(False)
     buf = C.create_string_buffer(nals[-1], len(nals[-1]))
     assert lib.libHMDec_push_nal_unit(dec, buf, len(nals[-1]), True, C.byref(newpic), C.byref(check)) == ERROR

@@ -5,7 +5,7 @@ import os
 import re
 import subprocess
 import pytest
-from conftest import GOLDEN, STREAMS, ROOT, hm_digests
+from conftest import GOLDEN, GPU_STREAMS as STREAMS, ROOT, hm_digests
 
 pytestmark = pytest.mark.gpu
 CLI = os.path.join(ROOT, "frontend", "_build", "hmdec_cli")

@@ -4,7 +4,7 @@ sample by sample, with the first differing sample reported.  Integer work: the b
 import os
 import numpy as np
 import pytest
-from conftest import GOLDEN, STREAMS, ROOT, hm_digests
+from conftest import GOLDEN, GPU_STREAMS as STREAMS, ROOT, hm_digests
 from libhm_b200 import records
 
 pytestmark = pytest.mark.gpu

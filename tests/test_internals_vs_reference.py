@@ -10,7 +10,7 @@ Values the reference leaves uninitialised are not compared (they are stack garba
 import os
 import subprocess
 import pytest
-from conftest import GOLDEN, STREAMS, ROOT
+from conftest import GOLDEN, ALL_STREAMS as STREAMS, GPU_STREAMS, ROOT
 
 TOOL = os.path.join(ROOT, "frontend", "_build", "hmdec_internals")
 OURS = os.path.join(ROOT, "frontend", "_build", "libHMDecoder_b200.so")
@@ -78,7 +78,7 @@ def test_host_side_reports_what_the_reference_reports(name, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", STREAMS)
+@pytest.mark.parametrize("name", GPU_STREAMS)
 def test_drop_in_on_the_gpu_reports_what_the_reference_reports(name, tmp_path):
     """GPU: the product configuration — every visible sample and every internals block list equals the reference wrapper's."""
     _need()

@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 import ctypes as C
-from conftest import GOLDEN, STREAMS, hm_digests
+from conftest import GOLDEN, ALL_STREAMS as STREAMS, hm_digests
 from libhm_b200 import records
 from oracle import oracle
 

@@ -60,6 +60,9 @@ JOBS=(
  "s_cksum_240p       encoder_randomaccess_main10.cfg       416  240  9  10 420 42 --SEIDecodedPictureHash=3 -q 30"
  "s_mintu8_240p      encoder_intra_main.cfg                416  240  2  8  420 45 --QuadtreeTULog2MinSize=3 --MaxPartitionDepth=3 -q 32"
  "s_cra_240p         encoder_randomaccess_main.cfg         416  240  25 8  420 46 --IntraPeriod=8 -q 30"
+ "s_ramintu8_240p    encoder_randomaccess_main10.cfg       416  240  9  10 420 47 --QuadtreeTULog2MinSize=3 --MaxPartitionDepth=3 -q 27"
+ "s_mintu16_240p     encoder_randomaccess_main.cfg         416  256  5  8  420 48 --QuadtreeTULog2MinSize=4 --MaxPartitionDepth=2 -q 27"
+ "s_mintu32_240p     encoder_randomaccess_main.cfg         448  256  5  8  420 49 --QuadtreeTULog2MinSize=5 --MaxPartitionDepth=1 --QuadtreeTUMaxDepthInter=1 --QuadtreeTUMaxDepthIntra=1 -q 27"
 )
 WANT=$1
 # s_switch_240p: five coded video sequences back to back, every one starting with an IDR and four of the five activating an SPS of
