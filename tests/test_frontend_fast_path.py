@@ -32,11 +32,12 @@ def test_fast_parse_path_emits_golden_records(name, tmp_path):
                 assert np.array_equal(a, b), (name, int(f.h["poc"]), field)
 
 
-@pytest.mark.parametrize("switch", ["HMDEC_B200_HM_BS", "HMDEC_B200_BS_AT_END", "HMDEC_B200_NO_PREFETCH", "HMDEC_B200_NO_PIC_POOL"])
-@pytest.mark.parametrize("name", ["s_ra8_240p", "s_ld10_240p", "s_tiles_240p", "s_wpb_240p"])
+@pytest.mark.parametrize("switch", ["HMDEC_B200_HM_BS", "HMDEC_B200_BS_FLAGS", "HMDEC_B200_BS_AT_END", "HMDEC_B200_HM_AVAIL", "HMDEC_B200_HM_COEFF", "HMDEC_B200_NO_PREFETCH", "HMDEC_B200_NO_PIC_POOL"])
+@pytest.mark.parametrize("name", ["s_ra8_240p", "s_ld10_240p", "s_tiles_240p", "s_wpb_240p", "s_ramintu8_240p", "s_mintu16_240p", "s_mintu32_240p"])
 def test_host_side_switches_do_not_change_the_records(name, switch, tmp_path):
-    """The A/B switches of the host-side optimisations (HM's own boundary-strength routine instead of the direct rule,
-    deblocking side info per picture instead of per CTU, no CTU prefetch, no picture pool) select other code paths
+    """The A/B switches of the host-side optimisations (HM's own boundary-strength routine / HM's edge-flag arrays instead of the direct rule,
+    deblocking side info per picture instead of per CTU, HM's per-unit neighbour look-ups for the intra availability, HM's coefficient
+    parser, no CTU prefetch, no picture pool) select other code paths
     for the SAME result: the emitted records stay byte-identical to the goldens."""
     if not os.path.exists(CLI):
         pytest.skip("frontend/_build/hmdec_cli not built (needs the reference sources at build time)")
