@@ -235,6 +235,78 @@ void HmEmitter::beginFrame(TComPic* pic, TComDataCU* ctu)
 }
 
 // ---------------------------------------------------------------------------------------------
+// A reference picture that never arrived: TDecTop::xCreateLostPicture (TDecTop.cpp:233-281) takes a fresh buffer, copies the samples
+// of the closest picture of the DPB into it and marks it as a reference that is also output.  HM copies host planes; here the samples
+// live in the engine's DPB, so the stand-in is sent as a picture of its own: one uni-predicted PU per CTU with a zero vector from
+// the source's slot, no residual, no loop filters — integer-sample motion compensation is a bit-exact copy.
+void HmEmitter::onLostPicture(TComPic* fill, TComPic* src, int poc)
+{
+  if (m_open) { fail("a lost reference picture is concealed in the middle of another picture"); return; }
+  std::map<TComPic*, int>::iterator from = m_slots.find(src);
+  if (from == m_slots.end()) { fail("a lost reference picture is concealed from a picture the engine never saw"); return; }
+  TComSPS* sps = fill->getSlice(0)->getSPS();
+  const int ctu = (int)g_uiMaxCUWidth;
+  memset(&m_hdr, 0, sizeof(m_hdr));
+  m_hdr.magic   = HMR_MAGIC;
+  m_hdr.version = HMR_VERSION;
+  m_hdr.width   = sps->getPicWidthInLumaSamples();
+  m_hdr.height  = sps->getPicHeightInLumaSamples();
+  m_hdr.poc     = poc;
+  m_hdr.chroma_format    = (uint8_t)fill->getChromaFormat();
+  m_hdr.bit_depth_luma   = (uint8_t)g_bitDepth[CHANNEL_TYPE_LUMA];
+  m_hdr.bit_depth_chroma = (uint8_t)g_bitDepth[CHANNEL_TYPE_CHROMA];
+  m_hdr.log2_ctu = (uint8_t)(g_aucConvertToBit[g_uiMaxCUWidth] + 2);
+  m_hdr.out_slot = (uint8_t)slotOf(fill);
+  m_hdr.slice_type = (uint8_t)P_SLICE;
+  m_hdr.n_ctu = fill->getNumCUsInFrame();
+  m_hdr.flags = HMR_FRM_IS_REFERENCE;
+  if (m_unsupported) return;                                   // slotOf ran out of slots
+  if (g_uiMaxCUWidth != g_uiMaxCUHeight || ctu > 64) { fail("non-square CTU"); return; }
+
+  m_tu.clear(); m_coef.clear(); m_intra.clear(); m_pu.clear(); m_puPrefix.clear(); m_puRefIdx.clear();
+  m_puPrefix.push_back(0);
+  m_range.assign(m_hdr.n_ctu, hmr_ctu_intra_range());
+  memset(m_range.data(), 0, m_range.size() * sizeof(hmr_ctu_intra_range));
+  m_ctu.assign(m_hdr.n_ctu, hmr_ctu());
+  memset(m_ctu.data(), 0, m_ctu.size() * sizeof(hmr_ctu));
+  m_bsStride = (m_hdr.width + 3) >> 2;
+  m_qpStride = (m_hdr.width + 7) >> 3;
+  m_bs.assign((size_t)m_bsStride * ((m_hdr.height + 3) >> 2), 0);
+  m_qp.assign((size_t)m_qpStride * ((m_hdr.height + 7) >> 3), 0);
+  m_cuFlags.assign(m_qp.size(), 0);
+  for (int y = 0; y < m_hdr.height; y += ctu)
+    for (int x = 0; x < m_hdr.width; x += ctu)
+    {
+      hmr_pu p;
+      memset(&p, 0, sizeof(p));
+      p.x = (uint16_t)x; p.y = (uint16_t)y;
+      p.w = (uint8_t)std::min(ctu, m_hdr.width - x); p.h = (uint8_t)std::min(ctu, m_hdr.height - y);
+      p.lists = HMR_PU_L0;
+      p.slots = (uint8_t)from->second;
+      m_pu.push_back(p);
+      m_puPrefix.push_back(m_puPrefix.back() + (uint32_t)(((p.w + 15) >> 4) * ((p.h + 15) >> 4)));
+    }
+  for (int k = 0; k <= 4; k++) m_hdr.tu_first[k] = 0;
+  m_hdr.n_pu = (uint32_t)m_pu.size();
+  m_hdr.n_mc_tiles = m_puPrefix.back();
+
+  hmr_frame_desc d;
+  memset(&d, 0, sizeof(d));
+  d.hdr = &m_hdr;
+  d.tu = m_tu.data(); d.coef = m_coef.data();
+  d.intra = m_intra.data(); d.intra_range = m_range.data();
+  d.pu = m_pu.data(); d.pu_tile_prefix = m_puPrefix.data();
+  d.ctu = m_ctu.data();
+  d.qp = m_qp.data();
+  if (!m_sink->frameReady(d, fill))
+  {
+    m_failText = std::string("the reconstruction engine rejected the stand-in for a lost picture: ") + (m_sink->error() ? m_sink->error() : "unknown error");
+    fail(m_failText.c_str());
+  }
+  m_nPic++;
+}
+
+// ---------------------------------------------------------------------------------------------
 // one CTU: mirrors TDecCu::decompressCU -> xDecompressCU (TDecCu.cpp:142-145, 373-447)
 void HmEmitter::onCtuParsed(TComDataCU* ctu)
 {

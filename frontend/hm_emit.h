@@ -103,6 +103,7 @@ public:
   void onPictureParsed(TComPic* pic, TComLoopFilter* lf, TComSampleAdaptiveOffset* sao, bool lfCrossTiles); // splice at TDecGop.cpp:157
   HmFrameSink* sink() { return m_sink; }
   int  slotOf(TComPic* pic);
+  void onLostPicture(TComPic* fill, TComPic* src, int poc);               // TDecTop::xCreateLostPicture: `fill` stands in for a missing reference as a copy of `src`
   void releaseSlot(TComPic* pic);                                         // the picture buffer is gone (hm_fast.cpp): its DPB slot is free again
   const char* unsupported() const { return m_unsupported; }
   bool cleanCoeffs() const { return m_cleanCoeffs; }

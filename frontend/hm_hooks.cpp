@@ -119,6 +119,14 @@ static void printStatusAndHash(TComPic* pic, TComSlice* slice, Int hashEnabled, 
   if (!quiet) e->sink()->orderedPrint(line);
 }
 
+// TDecTop::xCreateLostPicture (TDecTop.cpp:233-281, patched at build time to call this right after its host-side copy)
+void hm_hook_lost_picture(TComPic* fill, TComPic* src, int poc)
+{
+  HmEmitter* e = requireEmitter();
+  e->onLostPicture(fill, src, poc);
+  if (e->sink()->wantHmRecon()) for (int stage = 0; stage < 3; stage++) e->sink()->hmStage(stage, fill);   // golden dumps: HM's copy is the picture at every stage
+}
+
 Void TDecGop::filterPicture(TComPic*& rpcPic)
 {
   HmEmitter* e = requireEmitter();

@@ -88,6 +88,36 @@ def test_drop_in_on_the_gpu_reports_what_the_reference_reports(name, tmp_path):
     _compare(ref, got, name)
 
 
+def test_concealed_lost_picture_matches_the_reference_host_side(tmp_path):
+    """s_lost_240p (a reference picture missing from the stream, TDecTop::xCreateLostPicture): the same pictures in the same order — the
+    stand-in for POC 8 is output too — and the same internals as the reference wrapper, for as long as the reference wrapper returns
+    pictures: on this stream its list walk (libHMDecoder.cpp:262-335) stops handing pictures out after POC 9, while TAppDecoder writes all
+    17 (corpus/s_lost_240p.yuvmd5 is of 17 frames) and so does the drop-in."""
+    _need()
+    stream = os.path.join(GOLDEN, "s_lost_240p.bin")
+    ref = _dump(REF, stream, str(tmp_path / "ref.txt"))
+    env = dict(os.environ, HMDUMP_RECORDS_ONLY="1", HMDEC_B200_QUIET="1")
+    got = _dump(OURS, stream, str(tmp_path / "ours.txt"), ("--backend", "1", "/dev/null"), env)
+    assert len(ref) == 10 and len(got) == 17
+    assert [g["head"].split()[2] for g in got] == [str(p) for p in range(17)]          # output order: POC 0..16, the stand-in (8) among them
+    got = got[:len(ref)]
+    for r, g in zip(ref, got):
+        g["planes"] = r["planes"]
+    _compare(ref, got, "s_lost_240p")
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first GPU run (written after the round's GPU budget was spent); CPU: oracle == HM on these records")
+def test_concealed_lost_picture_matches_the_reference_on_the_gpu(tmp_path):
+    """GPU: every visible sample of all 17 pictures (the stand-in included) equals the reference wrapper's."""
+    _need()
+    stream = os.path.join(GOLDEN, "s_lost_240p.bin")
+    ref = _dump(REF, stream, str(tmp_path / "ref.txt"))
+    got = _dump(OURS, stream, str(tmp_path / "ours.txt"), env=dict(os.environ, HMDEC_B200_QUIET="1"))
+    assert len(ref) == 10 and len(got) == 17                  # (see the host-side test: the reference wrapper stops after POC 9)
+    _compare(ref, got[:len(ref)], "s_lost_240p")
+
+
 def test_temporal_layer_limit_matches_the_reference_host_side(tmp_path):
     """libHMDec_set_max_temporal_layer(0) (libHMDecoder.cpp:142: NAL units of higher temporal layers are dropped before they reach the
     decoder): same pictures in the same order, same internals, on the open-GOP stream with two temporal layers."""

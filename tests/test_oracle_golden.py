@@ -48,6 +48,36 @@ def test_oracle_matches_hm_all_stages(name):
             assert _oracle_hash(kind, out.planes, bds) == want, f"final picture vs TAppDecoder/SEI {kind}, POC {fr.h['poc']}"
 
 
+def test_oracle_matches_hm_on_a_concealed_lost_picture():
+    """s_lost_240p = s_ra8_240p without its second coded picture (POC 8).  HM conceals it with a copy of the closest picture
+    (TDecTop::xCreateLostPicture, TDecTop.cpp:233-281); the emitter sends that copy to the engine's DPB as a picture of its own (zero-vector
+    PUs from the source's slot).  The oracle must reproduce HM's planes — the stand-in's and those of the 16 pictures decoded on top of it —
+    at all three stages, and the final MD5s must be the ones the unmodified TAppDecoder printed for this cut (mismatching the SEI by design)."""
+    frames = records.read_dump(os.path.join(GOLDEN, "s_lost_240p.hmr.gz"))
+    printed = {}
+    for l in open(os.path.join(GOLDEN, "s_lost_240p.md5")):
+        m = re.match(r"POC\s+(-?\d+).*?\[MD5:([0-9a-f]+),([0-9a-f]+),([0-9a-f]+),", l)
+        if m:
+            printed[int(m.group(1))] = [bytes.fromhex(m.group(k)) for k in (2, 3, 4)]
+    assert len(frames) == 17 and len(printed) == 16 and 8 not in printed
+    assert int(frames[1].h["poc"]) == 8 and len(frames[1].tu) == 0 and len(frames[1].pu) > 0          # the stand-in: prediction only
+    dec = oracle.Decoder()
+    pre = oracle.STAGE_MC | oracle.STAGE_RESID | oracle.STAGE_INTRA
+    for fr in frames:
+        bds = [fr.bit_depth(c) for c in range(3)]
+        dec.frame(fr, pre)
+        assert (records.picture_md5(dec.work.planes, bds) == fr.gold[0]).all(), f"CU recon, POC {fr.h['poc']}"
+        dec.frame(fr, pre | oracle.STAGE_DBV | oracle.STAGE_DBH)
+        assert (records.picture_md5(dec.work.planes, bds) == fr.gold[1]).all(), f"deblock, POC {fr.h['poc']}"
+        out = dec.frame(fr)
+        md5 = records.picture_md5(out.planes, bds)
+        assert (md5 == fr.gold[2]).all(), f"SAO, POC {fr.h['poc']}"
+        poc = int(fr.h["poc"])
+        if poc in printed:
+            assert [bytes(md5[c]) for c in range(3)] == printed[poc], f"final picture vs what TAppDecoder printed, POC {poc}"
+    assert (frames[1].gold[2] == frames[0].gold[2]).all()                                              # the stand-in IS picture 0
+
+
 def test_fixtures_cover_the_tools():
     """The golden set must actually exercise the tools the hot path implements."""
     seen = dict(bi=0, uni=0, frac=0, dst=0, tskip=0, rdpcm=0, rotate=0, ccp=0, n32=0, sao_eo=0, sao_bo=0, bs1=0, bs2=0, strong_flag=0, planar=0, dc=0, ang=0)

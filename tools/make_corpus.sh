@@ -104,6 +104,30 @@ PY
   echo "s_seek_240p: done ($(stat -c %s "$out.bin") bytes, $(grep -c OK "$out.md5") pictures OK)"
   exit 0
 fi
+# s_lost_240p: s_ra8_240p without its second coded picture (POC 8, a reference of everything that follows): the decoder conceals it
+# (TDecTop::xCreateLostPicture, TDecTop.cpp:233-281: a copy of the closest picture stands in and is output as well).  The pin is what the
+# unmodified TAppDecoder prints for this cut: 16 status lines, the SEI MD5s of the pictures that depend on the lost one mismatch by design.
+if [ "$WANT" == "s_lost_240p" ]; then
+  out=$ROOT/corpus/s_lost_240p
+  [ -s "$ROOT/corpus/s_ra8_240p.bin" ] || "$0" s_ra8_240p
+  python3 - "$ROOT/corpus/s_ra8_240p.bin" "$out.bin" <<'PY'
+import re, sys
+d = open(sys.argv[1], 'rb').read()
+pos = [m.start() for m in re.finditer(b'\x00\x00\x01', d)]
+pos = [p - 1 if p > 0 and d[p - 1] == 0 else p for p in pos]
+nals = [(p, pos[i + 1] if i + 1 < len(pos) else len(d)) for i, p in enumerate(pos)]
+typ = lambda n: (d[n[0] + (4 if d[n[0] + 2] == 0 else 3)] >> 1) & 0x3f
+vcl = [i for i, n in enumerate(nals) if typ(n) < 32]
+drop = {vcl[1]}
+if typ(nals[vcl[1] + 1]) == 40: drop.add(vcl[1] + 1)                      # its decoded-picture-hash SEI
+open(sys.argv[2], 'wb').write(b''.join(d[a:b] for i, (a, b) in enumerate(nals) if i not in drop))
+PY
+  "$DEC" -b "$out.bin" -d 0 -o "$TMP_YUV/s_lost.dec.yuv" > "$out.dec.log" 2>&1 || true
+  grep -o 'POC.*' "$out.dec.log" | sed -E 's/\[DT +[0-9.]+\] //' > "$out.md5"
+  md5sum < "$TMP_YUV/s_lost.dec.yuv" | awk '{print $1}' > "$out.yuvmd5"
+  echo "s_lost_240p: done ($(stat -c %s "$out.bin") bytes, $(grep -c POC "$out.md5") status lines, $(grep -c OK "$out.md5") OK)"
+  exit 0
+fi
 if [ "$1" == "--list" ]; then for j in "${JOBS[@]}"; do echo "$j" | awk '{print $1}'; done; exit 0; fi
 for j in "${JOBS[@]}"; do
   set -- $j
