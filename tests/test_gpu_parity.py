@@ -31,7 +31,7 @@ def _report(name, fr, stage, got, oracle_planes):
     return "; ".join(lines)
 
 
-@pytest.mark.parametrize("name", STREAMS + [pytest.param("s_lost_240p", marks=pytest.mark.xfail(strict=False, reason="first GPU run (added after the round's GPU budget was spent); CPU: oracle == HM on these records"))])
+@pytest.mark.parametrize("name", STREAMS)
 def test_engine_matches_hm_and_oracle(name, eng_mod):
     from oracle import oracle
     frames = records.read_dump(os.path.join(GOLDEN, name + ".hmr.gz"))
